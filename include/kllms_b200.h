@@ -1,0 +1,151 @@
+/*
+ * kllms_b200.h — C ABI of the B200-native n-way consensus consolidator.
+ *
+ * The reference (retab-dev/k-LLMs) is pure Python and has NO plugin / FFI boundary; its seam is
+ * the import at k_llms/utils/consolidation.py:11-19 (`consensus_values`, `ConsensusSettings`, ...).
+ * This header therefore declares the columnar entry points a binding for that seam calls
+ * (SURVEY.md §8b "what a C-ABI replacement must export"); each cites the reference code it replaces.
+ * INTEGRATION.md shows the ctypes stub a k_llms maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no torch types; 0 on success, negative KC_E* on failure,
+ * never an exception; caller owns every buffer; `d_` pointers are device memory on the CURRENT
+ * CUDA device, `h_` pointers host memory; calls are stream-ordered on `stream` (a cudaStream_t
+ * passed as void*, NULL = legacy default stream) and re-entrant.
+ *
+ * DATA MODEL — a "group" is the n candidate values of ONE field of ONE record (what one call of
+ * the reference's consensus_values() sees for a scalar field).  Groups are stored row-major,
+ * candidate index innermost: cells[g*n + c], g = record*n_fields + field.
+ */
+#ifndef KLLMS_B200_H
+#define KLLMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_VERSION 100 /* 0.1.0 */
+#define KC_MAX_CANDIDATES 64
+
+/* ---- error codes ---- */
+#define KC_OK 0
+#define KC_EINVAL (-1)  /* bad argument (n out of [1,64], NULL pointer, misaligned buffer, negative eps) */
+#define KC_ECUDA (-2)   /* CUDA runtime error; text via kc_last_error() */
+#define KC_ENODEV (-3)  /* no sm_100 device */
+#define KC_ENOMEM (-4)
+
+/* ---- vote cells (int32) ---- */
+#define KC_CODE_NONE (-1)   /* candidate present, value is None (cu:947,964) */
+#define KC_CODE_ABSENT (-2) /* candidate is not part of `values` at this node (parent was not a dict/list, cu:1416,1431) */
+/* codes >= 0: dictionary code of the processed value (sanitize_value(v) for strings, cu:925-933;
+ * `v or False` for bool groups, cu:956); equal code <=> equal processed value. */
+
+/* ---- numeric cells (float64) ---- */
+#define KC_F64_NONE_BITS 0x7FF8C0DE00000001ULL   /* quiet NaN payload: None */
+#define KC_F64_ABSENT_BITS 0x7FF8C0DE00000002ULL /* quiet NaN payload: absent (see KC_CODE_ABSENT) */
+/* any OTHER non-finite value means "present, non-None, but not a finite number" (bool, str, nan,
+ * inf inside a numeric group): counted in the total, excluded from clustering (cu:1105-1114). */
+
+/* ---- packed per-group result word ("meta") ----
+ * bits  0..5  idx      vote: candidate index of the FIRST cell of the winning class (cu:971)
+ *                      numeric: index of the single non-None cell when KC_FLAG_SINGLE
+ * bits  6..12 support  vote: best_count (cu:958,969); numeric: support of the chosen cluster (cu:1177,1186,1218)
+ * bits 13..19 nn       vote: number of voting cells; numeric: number of non-None cells == `total` (cu:1100)
+ * bits 20..26 present  len(values) at this node == n - #absent (vote confidence denominator, cu:944,973)
+ * bits 27..31 flags    KC_FLAG_*
+ */
+#define KC_META_IDX(m) ((uint32_t)(m) & 0x3Fu)
+#define KC_META_SUPPORT(m) (((uint32_t)(m) >> 6) & 0x7Fu)
+#define KC_META_NN(m) (((uint32_t)(m) >> 13) & 0x7Fu)
+#define KC_META_PRESENT(m) (((uint32_t)(m) >> 20) & 0x7Fu)
+#define KC_META_FLAGS(m) (((uint32_t)(m) >> 27) & 0x1Fu)
+#define KC_META_PACK(idx, support, nn, present, flags) \
+    (((uint32_t)(idx) & 0x3Fu) | (((uint32_t)(support) & 0x7Fu) << 6) | (((uint32_t)(nn) & 0x7Fu) << 13) | \
+     (((uint32_t)(present) & 0x7Fu) << 20) | (((uint32_t)(flags) & 0x1Fu) << 27))
+
+#define KC_FLAG_HAS_VALUE 1u  /* a consensus value exists (else the reference returns None) */
+#define KC_FLAG_SINGLE 2u     /* numeric: exactly one non-None cell; value is the ORIGINAL object, confidence unrounded (cu:1085-1086) */
+#define KC_FLAG_TIE 4u        /* vote: the maximum count was shared; numeric: tie resolution cu:1189-1219 ran */
+#define KC_FLAG_NO_FINITE 8u  /* numeric: >=2 non-None cells, none finite (cu:1115-1116) */
+
+/* ---- library ---- */
+int kc_version(void);
+const char *kc_last_error(void); /* thread-local text of the last KC_ECUDA / KC_EINVAL */
+int kc_device_count(void);       /* number of visible CUDA devices with compute capability 10.x */
+int kc_sm_count(int device);     /* multiprocessor count (148 on B200) or KC_E* */
+int kc_set_device(int device);   /* make `device` current for this thread's subsequent d_* calls (this library links its own
+                                    CUDA runtime instance; a torch caller passes torch.cuda.current_device()) */
+
+/*
+ * K1 — vote consensus over dictionary-coded str/bool groups.
+ * Replaces voting_consensus (consensus_utils.py:936-982) on pre-sanitised input.
+ *   d_codes     int32[n_groups][n]   KC_CODE_* or code >= 0; 16-byte aligned
+ *   d_none_code int32[n_fields] or NULL.  Per field (field = g % n_fields): -1 => None cells do not
+ *               vote (string fields, cu:964); c >= 0 => None cells vote as code c (bool fields map
+ *               None to False, cu:956; allow_none_as_candidate maps None to its own code, cu:961-962).
+ *   d_win_code  int32[n_groups]      code of the winning class, KC_CODE_NONE if no cell voted
+ *   d_meta      uint32[n_groups]     packed result word
+ * Ties go to the class seen first (cu:958,969: Counter insertion order).  1 <= n <= 64.
+ */
+int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                int32_t *d_win_code, uint32_t *d_meta, void *stream);
+
+/*
+ * K2 — numeric consensus: sort, 1-D tolerance clustering, largest cluster, numpy-order mean.
+ * Replaces the numeric branch of consensus_as_primitive (consensus_utils.py:1098-1219).
+ *   d_vals   float64[n_groups][n]  finite value, KC_F64_NONE_BITS, KC_F64_ABSENT_BITS, or any other
+ *            non-finite ("present but not a number"); 16-byte aligned
+ *   d_value  float64[n_groups]     float(np.mean(cluster)) bit-exact (numpy pairwise order); for
+ *            KC_FLAG_SINGLE the cell itself; NaN when no value
+ *   rel_eps, abs_eps >= 0          ConsensusSettings.rel_eps / abs_eps (cu:63-64)
+ */
+int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                   uint32_t *d_meta, void *stream);
+
+/*
+ * Confidences from result words, bit-exact with Python's round(x, 5) (cu:982,1178,1187,1219):
+ *   vote    (numeric == 0): round(pvf * (support / present), 5)          cu:973,982
+ *   numeric (numeric == 1): round(support / nn, 5); SINGLE: pvf * (1/present) unrounded (cu:1086,1444)
+ *   no value: all-None -> 0.0 (cu:1402); empty -> pvf (cu:1396); NO_FINITE -> pvf * nn/present (cu:1116)
+ * d_pvf float64[n_groups] or NULL (=1.0): parent_valid_frac of each group.
+ */
+int kc_confidence_f64(const uint32_t *d_meta, int64_t n_groups, int32_t numeric, const double *d_pvf, double *d_conf,
+                      void *stream);
+
+/*
+ * K3 — per-candidate sequence log-likelihood: fp32 sum of per-token logprobs (NEW feature: the
+ * reference only passes `logprobs` through, consolidation.py:129,135; SURVEY.md §0.3 — spec in DESIGN.md).
+ *   d_logprobs float32[offsets[n_seq]]   d_offsets int64[n_seq+1] (ascending)   d_sum float32[n_seq]
+ * Summation order is fixed (32 strided partial sums, then a xor-butterfly 16,8,4,2,1) so results are
+ * bit-reproducible; the oracle restates the same order.
+ */
+int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_t n_seq, float *d_sum, void *stream);
+
+/*
+ * K3b — likelihood-weighted vote: class weight = sum over its cells of exp(seq_logprob[record][c])
+ * (fp32, ascending candidate order), winner = heaviest class, ties -> first seen.
+ *   d_codes int32[n_records*n_fields][n] as kc_vote_i32; d_seq_logprob float32[n_records][n]
+ *   d_weight float32[n_groups]: winning class weight / total voting weight (0 if none)
+ */
+int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int64_t n_records, int32_t n_fields,
+                         int32_t n, const int32_t *d_none_code, int32_t *d_win_code, uint32_t *d_meta, float *d_weight,
+                         void *stream);
+
+/*
+ * End-to-end entry with HOST buffers (the call a k_llms binding makes for a batch of records of one
+ * flat schema): chunked, double-buffered H2D -> K1/K2 -> D2H on internal streams of `device`.
+ * Either half may be absent (n_vote_fields == 0 or n_num_fields == 0).  Blocks until results are in
+ * host memory.  Host buffers should be page-locked (kc_host_alloc) for full PCIe bandwidth.
+ */
+int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
+                      int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
+                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device);
+
+void *kc_host_alloc(uint64_t bytes); /* page-locked host memory, NULL on failure */
+void kc_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLLMS_B200_H */

@@ -1,0 +1,195 @@
+"""ctypes binding of libkllms_b200.so — the C ABI declared in include/kllms_b200.h.
+
+This is the ONLY compute path of the package: there is no CPU fallback.  If the shared library has not
+been built (`python -c "import __graft_entry__ as g; g.build()"` or `make -C k_llms_b200/csrc`) or no
+sm_100 device is visible, the functions below raise — loudly — instead of computing on the host.
+
+torch is used for device memory and streams only (plumbing); the ABI itself takes raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkllms_b200.so")
+
+KC_OK, KC_EINVAL, KC_ECUDA, KC_ENODEV, KC_ENOMEM = 0, -1, -2, -3, -4
+MAX_CANDIDATES = 64
+CODE_NONE, CODE_ABSENT = -1, -2
+F64_NONE_BITS = 0x7FF8C0DE00000001
+F64_ABSENT_BITS = 0x7FF8C0DE00000002
+FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
+
+EXPORTS = (
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64",
+    "kc_confidence_f64", "kc_logprob_sum_f32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
+)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"libkllms_b200: {what} (code {code})")
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and declare prototypes.  Raises if it is missing: no silent fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the sm_100a library first (make -C k_llms_b200/csrc, or "
+            "__graft_entry__.build()).  k_llms_b200 has no CPU fallback for the consensus hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, i64, f64 = c.c_void_p, c.c_int32, c.c_int64, c.c_double
+    lib.kc_version.restype = c.c_int
+    lib.kc_last_error.restype = c.c_char_p
+    lib.kc_device_count.restype = c.c_int
+    lib.kc_sm_count.argtypes = [c.c_int]
+    lib.kc_set_device.argtypes = [c.c_int]
+    lib.kc_vote_i32.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
+    lib.kc_numeric_f64.argtypes = [vp, i64, i32, f64, f64, vp, vp, vp]
+    lib.kc_confidence_f64.argtypes = [vp, i64, i32, vp, vp, vp]
+    lib.kc_logprob_sum_f32.argtypes = [vp, vp, i64, vp, vp]
+    lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int]
+    lib.kc_host_alloc.argtypes = [c.c_uint64]
+    lib.kc_host_alloc.restype = vp
+    lib.kc_host_free.argtypes = [vp]
+    lib.kc_host_free.restype = None
+    for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
+                 "kc_consensus_host"):
+        getattr(lib, name).restype = c.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != KC_OK:
+        raise NativeError(rc, load().kc_last_error().decode(errors="replace"))
+
+
+def _require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("k_llms_b200 needs a CUDA (sm_100a) device: the consensus hot path has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(torch, stream) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+def _bind(torch, t) -> None:
+    check(load().kc_set_device(t.device.index if t.device.index is not None else torch.cuda.current_device()))
+
+
+def vote(codes, none_code=None, stream=None) -> Tuple["torch.Tensor", "torch.Tensor"]:
+    """K1 on device tensors.  codes: int32 [G, n] (cuda, contiguous); none_code: int32 [F] or None.
+    Returns (win_code int32 [G], meta int32 [G] holding the packed uint32 word)."""
+    torch = _require_cuda()
+    assert codes.is_cuda and codes.dtype == torch.int32 and codes.dim() == 2 and codes.is_contiguous()
+    G, n = codes.shape
+    win = torch.empty(G, dtype=torch.int32, device=codes.device)
+    meta = torch.empty(G, dtype=torch.int32, device=codes.device)
+    nf = 0
+    nc_ptr = None
+    if none_code is not None:
+        assert none_code.is_cuda and none_code.dtype == torch.int32 and none_code.is_contiguous()
+        nf = none_code.numel()
+        assert G % nf == 0, "n_groups must be a whole number of records"
+        nc_ptr = none_code.data_ptr()
+    _bind(torch, codes)
+    check(load().kc_vote_i32(codes.data_ptr(), G, n, nc_ptr, nf, win.data_ptr(), meta.data_ptr(), _stream_ptr(torch, stream)))
+    return win, meta
+
+
+def numeric(vals, rel_eps: float = 0.03, abs_eps: float = 1e-6, stream=None):
+    """K2 on device tensors.  vals: float64 [G, n].  Returns (value float64 [G], meta int32 [G])."""
+    torch = _require_cuda()
+    assert vals.is_cuda and vals.dtype == torch.float64 and vals.dim() == 2 and vals.is_contiguous()
+    G, n = vals.shape
+    value = torch.empty(G, dtype=torch.float64, device=vals.device)
+    meta = torch.empty(G, dtype=torch.int32, device=vals.device)
+    _bind(torch, vals)
+    check(load().kc_numeric_f64(vals.data_ptr(), G, n, float(rel_eps), float(abs_eps), value.data_ptr(), meta.data_ptr(),
+                                _stream_ptr(torch, stream)))
+    return value, meta
+
+
+def confidence(meta, numeric_kind: bool, pvf=None, stream=None):
+    """Python-round(x,5)-exact confidences from result words.  meta int32 [G]; pvf float64 [G] or None."""
+    torch = _require_cuda()
+    assert meta.is_cuda and meta.dtype == torch.int32 and meta.is_contiguous()
+    conf = torch.empty(meta.numel(), dtype=torch.float64, device=meta.device)
+    pv = None
+    if pvf is not None:
+        assert pvf.is_cuda and pvf.dtype == torch.float64 and pvf.numel() == meta.numel() and pvf.is_contiguous()
+        pv = pvf.data_ptr()
+    _bind(torch, meta)
+    check(load().kc_confidence_f64(meta.data_ptr(), meta.numel(), 1 if numeric_kind else 0, pv, conf.data_ptr(),
+                                   _stream_ptr(torch, stream)))
+    return conf
+
+
+def logprob_sum(logprobs, offsets, stream=None):
+    """K3: fp32 per-sequence sums.  logprobs float32 [T], offsets int64 [S+1] -> float32 [S]."""
+    torch = _require_cuda()
+    assert logprobs.is_cuda and logprobs.dtype == torch.float32 and offsets.dtype == torch.int64 and offsets.is_cuda
+    out = torch.empty(offsets.numel() - 1, dtype=torch.float32, device=logprobs.device)
+    _bind(torch, logprobs)
+    check(load().kc_logprob_sum_f32(logprobs.data_ptr(), offsets.data_ptr(), out.numel(), out.data_ptr(),
+                                    _stream_ptr(torch, stream)))
+    return out
+
+
+def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0, out=None):
+    """End-to-end entry with HOST numpy arrays (ideally backed by pinned memory).
+    codes int32 [N, Fv, n] or None; none_code int32 [Fv] or None; vals float64 [N, Fx, n] or None.
+    Returns dict(win_code, vote_meta, value, num_meta) of numpy arrays."""
+    import numpy as np
+    lib = load()
+    N = n = Fv = Fx = 0
+    if codes is not None:
+        assert codes.dtype == np.int32 and codes.ndim == 3 and codes.flags.c_contiguous
+        N, Fv, n = codes.shape
+    if vals is not None:
+        assert vals.dtype == np.float64 and vals.ndim == 3 and vals.flags.c_contiguous
+        N2, Fx, n2 = vals.shape
+        assert codes is None or (N2 == N and n2 == n)
+        N, n = N2, n2
+    out = out or {}
+    win = out.get("win_code") if "win_code" in out else np.empty((N, Fv), dtype=np.int32)
+    vmeta = out.get("vote_meta") if "vote_meta" in out else np.empty((N, Fv), dtype=np.uint32)
+    value = out.get("value") if "value" in out else np.empty((N, Fx), dtype=np.float64)
+    nmeta = out.get("num_meta") if "num_meta" in out else np.empty((N, Fx), dtype=np.uint32)
+    if none_code is not None:
+        none_code = np.ascontiguousarray(none_code, dtype=np.int32)
+        assert none_code.size == Fv
+    p = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
+    check(lib.kc_consensus_host(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
+                                p(value), p(nmeta), device))
+    return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta}
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from kc_host_alloc (freed when the array is collected)."""
+    import numpy as np
+    lib = load()
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    ptr = lib.kc_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError(f"kc_host_alloc({nbytes}) failed")
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.kc_host_free, ptr)
+    return arr

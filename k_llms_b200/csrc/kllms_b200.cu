@@ -1,0 +1,476 @@
+// kllms_b200.cu — C ABI (include/kllms_b200.h) and launchers of the sm_100a consensus kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//        (see k_llms_b200/csrc/Makefile; __graft_entry__.build() runs it).
+// No torch, no libraries beyond the CUDA runtime; the driver entry point cuTensorMapEncodeTiled is fetched
+// through cudaGetDriverEntryPoint so libcuda is not a link-time dependency.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/kllms_b200.h"
+#include "kc_common.cuh"
+#include "kc_extra.cuh"
+#include "kc_numeric.cuh"
+#include "kc_vote.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define KC_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(KC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+};
+
+int device_info(DeviceInfo &info) {
+    int dev = 0;
+    KC_CUDA(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::vector<DeviceInfo> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    if ((int)cache.size() <= dev) cache.resize(dev + 1);
+    if (cache[dev].sm_count == 0) {
+        KC_CUDA(cudaDeviceGetAttribute(&cache[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+        KC_CUDA(cudaDeviceGetAttribute(&cache[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    }
+    info = cache[dev];
+    if (info.cc_major != 10) return fail(KC_ENODEV, "device %d has compute capability %d.x; this library is sm_100a only", dev, info.cc_major);
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------- TMA descriptor
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn &fn) {
+    static EncodeTiledFn cached = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cached) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        KC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) return fail(KC_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        cached = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    fn = cached;
+    return KC_OK;
+}
+
+// rows of `row_bytes` (a power of two in [32, 512]) viewed as a 2-D int32 tensor whose inner extent is
+// min(row_bytes, 128) bytes — the widest span a TMA swizzle mode covers; box = TILE groups.
+int make_row_tensor_map(CUtensorMap &map, const void *base, int64_t n_groups, int row_bytes, int tile_groups) {
+    EncodeTiledFn encode;
+    int rc = get_encode_fn(encode);
+    if (rc) return rc;
+    const int inner_bytes = std::min(row_bytes, 128);
+    const int rows_per_group = row_bytes / inner_bytes;
+    cuuint64_t dims[2] = {(cuuint64_t)(inner_bytes / 4), (cuuint64_t)n_groups * rows_per_group};
+    cuuint64_t strides[1] = {(cuuint64_t)inner_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(inner_bytes / 4), (cuuint32_t)(tile_groups * rows_per_group)};
+    cuuint32_t elem_strides[2] = {1, 1};
+    const CUtensorMapSwizzle swz = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                       : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(base), dims, strides, box, elem_strides,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(KC_ECUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+    return KC_OK;
+}
+
+template <typename Kernel>
+int persistent_grid(Kernel kernel, int threads, size_t smem, int64_t n_tiles, int &grid) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(KC_ECUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    grid = (int)std::min<int64_t>(n_tiles, (int64_t)info.sm_count * per_sm);  // one wave of resident CTAs
+    return KC_OK;
+}
+
+// A TMA tile coordinate is int32: launch in slabs of at most this many groups.
+constexpr int64_t kMaxGroupsPerLaunch = (int64_t)1 << 28;
+
+// ---------------------------------------------------------------- K1 launchers
+
+template <int N, int TILE, int STAGES>
+int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
+                    cudaStream_t st) {
+    auto kernel = kc::vote_tma_kernel<N, TILE, STAGES>;
+    const size_t smem = (size_t)STAGES * TILE * N * 4 + 1024;
+    // a slab starts on a record boundary so that (g - g0) % n_fields == g % n_fields
+    const int64_t slab = std::max<int64_t>(n_fields, kMaxGroupsPerLaunch / n_fields * n_fields);
+    for (int64_t g0 = 0; g0 < G; g0 += slab) {
+        const int64_t gs = std::min(slab, G - g0);
+        CUtensorMap map;
+        int rc = make_row_tensor_map(map, codes + g0 * N, gs, N * 4, TILE);
+        if (rc) return rc;
+        int grid = 0;
+        rc = persistent_grid(kernel, TILE, smem, (gs + TILE - 1) / TILE, grid);
+        if (rc) return rc;
+        kernel<<<grid, TILE, smem, st>>>(map, gs, none_code, n_fields, win + g0, meta + g0);
+        KC_CUDA(cudaGetLastError());
+    }
+    return KC_OK;
+}
+
+template <int NP, bool VEC>
+int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *none_code, int n_fields, int32_t *win,
+                       uint32_t *meta, cudaStream_t st) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int threads = 256;
+    const int64_t blocks = (G + threads - 1) / threads;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * 8);
+    kc::vote_direct_kernel<NP, VEC><<<grid, threads, 0, st>>>(codes, G, n, none_code, n_fields, win, meta);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------- K2 launchers
+
+template <int N, int TILE, int STAGES>
+int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
+                       cudaStream_t st) {
+    auto kernel = kc::numeric_tma_kernel<N, TILE, STAGES>;
+    const size_t smem = (size_t)STAGES * TILE * N * 8 + (size_t)N * TILE * 8 + 1024;
+    for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
+        const int64_t gs = std::min(kMaxGroupsPerLaunch, G - g0);
+        CUtensorMap map;
+        int rc = make_row_tensor_map(map, vals + g0 * N, gs, N * 8, TILE);
+        if (rc) return rc;
+        int grid = 0;
+        rc = persistent_grid(kernel, TILE, smem, (gs + TILE - 1) / TILE, grid);
+        if (rc) return rc;
+        kernel<<<grid, TILE, smem, st>>>(map, gs, rel_eps, abs_eps, value + g0, meta + g0);
+        KC_CUDA(cudaGetLastError());
+    }
+    return KC_OK;
+}
+
+template <int NP, int T>
+int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, double abs_eps, double *value,
+                          uint32_t *meta, cudaStream_t st) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    auto kernel = kc::numeric_direct_kernel<NP, T>;
+    const size_t smem = (size_t)NP * T * 8;
+    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+    if (per_sm < 1) return fail(KC_ECUDA, "numeric_direct_kernel<%d> does not fit", NP);
+    const int64_t blocks = (G + T - 1) / T;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * per_sm);
+    kernel<<<grid, T, smem, st>>>(vals, G, n, rel_eps, abs_eps, value, meta);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Debug / A-B knob: KC_FORCE_DIRECT=1 routes every n through the direct (non-TMA) front-ends.
+bool force_direct() {
+    static const bool v = [] {
+        const char *e = getenv("KC_FORCE_DIRECT");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host-buffer context
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t need) {
+        if (p && need <= cap) return KC_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc(&p, need) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(KC_ENOMEM, "cudaMalloc(%zu) failed", need);
+        }
+        cap = need;
+        return KC_OK;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+struct HostCtx {
+    static constexpr int kStreams = 3;
+    int device = -1;
+    cudaStream_t streams[kStreams] = {};
+    DevBuf codes[kStreams], vals[kStreams], win[kStreams], vmeta[kStreams], value[kStreams], nmeta[kStreams], none;
+};
+std::mutex g_host_mu;
+HostCtx g_host[16];
+
+}  // namespace
+
+// ================================================================ C ABI
+
+extern "C" {
+
+int kc_version(void) { return KC_VERSION; }
+
+const char *kc_last_error(void) { return g_err; }
+
+int kc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int kc_sm_count(int device) {
+    int sm = 0;
+    KC_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    return sm;
+}
+
+int kc_set_device(int device) {
+    KC_CUDA(cudaSetDevice(device));
+    return KC_OK;
+}
+
+int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                int32_t *d_win_code, uint32_t *d_meta, void *stream) {
+    if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_vote_i32: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
+    if (n_groups < 0) return fail(KC_EINVAL, "kc_vote_i32: negative n_groups");
+    if (n_groups == 0) return KC_OK;
+    if (!d_codes || !d_win_code || !d_meta) return fail(KC_EINVAL, "kc_vote_i32: NULL buffer");
+    if (d_none_code && n_fields < 1) return fail(KC_EINVAL, "kc_vote_i32: none_code given but n_fields=%d", n_fields);
+    if (!d_none_code) n_fields = 1;
+    if (!aligned16(d_codes)) return fail(KC_EINVAL, "kc_vote_i32: d_codes must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (force_direct()) {
+        switch (n) {
+            case 8: return launch_vote_direct<8, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 16: return launch_vote_direct<16, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 32: return launch_vote_direct<32, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 64: return launch_vote_direct<64, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            default: break;
+        }
+    } else
+    switch (n) {
+        case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 8: return launch_vote_tma<8, 256, 6>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 16: return launch_vote_tma<16, 256, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 32: return launch_vote_tma<32, 256, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 64: return launch_vote_tma<64, 128, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        default: break;
+    }
+    if (n < 4) return launch_vote_direct<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 8) return launch_vote_direct<8, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 16) return launch_vote_direct<16, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 32) return launch_vote_direct<32, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+}
+
+int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                   uint32_t *d_meta, void *stream) {
+    if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_numeric_f64: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
+    if (n_groups < 0) return fail(KC_EINVAL, "kc_numeric_f64: negative n_groups");
+    if (!(rel_eps >= 0.0) || !(abs_eps >= 0.0)) return fail(KC_EINVAL, "kc_numeric_f64: rel_eps/abs_eps must be >= 0");
+    if (n_groups == 0) return KC_OK;
+    if (!d_vals || !d_value || !d_meta) return fail(KC_EINVAL, "kc_numeric_f64: NULL buffer");
+    if (!aligned16(d_vals)) return fail(KC_EINVAL, "kc_numeric_f64: d_vals must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!force_direct())
+    switch (n) {
+        case 4: return launch_numeric_tma<4, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+        case 8: return launch_numeric_tma<8, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+        case 16: return launch_numeric_tma<16, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+        case 32: return launch_numeric_tma<32, 128, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+        default: break;
+    }
+    if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n == 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n == 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n == 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n == 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n < 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n < 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n < 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n < 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    return launch_numeric_direct<64, 64>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+}
+
+int kc_confidence_f64(const uint32_t *d_meta, int64_t n_groups, int32_t numeric, const double *d_pvf, double *d_conf,
+                      void *stream) {
+    if (n_groups < 0) return fail(KC_EINVAL, "kc_confidence_f64: negative n_groups");
+    if (n_groups == 0) return KC_OK;
+    if (!d_meta || !d_conf) return fail(KC_EINVAL, "kc_confidence_f64: NULL buffer");
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((n_groups + threads - 1) / threads, (int64_t)info.sm_count * 8);
+    kc::confidence_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(d_meta, n_groups, numeric != 0, d_pvf, d_conf);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
+int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_t n_seq, float *d_sum, void *stream) {
+    if (n_seq < 0) return fail(KC_EINVAL, "kc_logprob_sum_f32: negative n_seq");
+    if (n_seq == 0) return KC_OK;
+    if (!d_offsets || !d_sum) return fail(KC_EINVAL, "kc_logprob_sum_f32: NULL buffer");
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int threads = 256;  // 8 warps, one sequence per warp per iteration
+    const int64_t warps = n_seq;
+    const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)info.sm_count * 8);
+    kc::logprob_sum_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(d_logprobs, d_offsets, n_seq, d_sum);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
+void *kc_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void kc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- end-to-end with host buffers
+
+int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
+                      int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
+                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device) {
+    if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_consensus_host: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
+    if (n_records < 0 || n_vote_fields < 0 || n_num_fields < 0) return fail(KC_EINVAL, "kc_consensus_host: negative size");
+    if (device < 0 || device >= 16) return fail(KC_EINVAL, "kc_consensus_host: device %d out of range", device);
+    if (n_vote_fields > 0 && (!h_codes || !h_win_code || !h_vote_meta)) return fail(KC_EINVAL, "kc_consensus_host: NULL vote buffer");
+    if (n_num_fields > 0 && (!h_vals || !h_value || !h_num_meta)) return fail(KC_EINVAL, "kc_consensus_host: NULL numeric buffer");
+    if (n_records == 0 || (n_vote_fields == 0 && n_num_fields == 0)) return KC_OK;
+
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    int prev = 0;
+    KC_CUDA(cudaGetDevice(&prev));
+    KC_CUDA(cudaSetDevice(device));
+    HostCtx &cx = g_host[device];
+    int rc = KC_OK;
+    auto finish = [&](int code) {
+        cudaSetDevice(prev);
+        return code;
+    };
+    if (cx.device != device) {
+        for (auto &s : cx.streams)
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return finish(fail(KC_ECUDA, "cudaStreamCreate failed"));
+        cx.device = device;
+    }
+    // chunk: ~48 MiB of input per stream buffer keeps H2D, kernels and D2H of neighbouring chunks overlapped
+    const size_t rec_in = (size_t)n * ((size_t)n_vote_fields * 4 + (size_t)n_num_fields * 8);
+    int64_t chunk = std::max<int64_t>(1024, (int64_t)((48u << 20) / std::max<size_t>(rec_in, 1)));
+    chunk = std::min<int64_t>(chunk, n_records);
+    chunk = (chunk + 255) / 256 * 256;
+    for (int s = 0; s < HostCtx::kStreams && !rc; ++s) {
+        if (n_vote_fields) {
+            rc = cx.codes[s].reserve((size_t)chunk * n_vote_fields * n * 4);
+            if (!rc) rc = cx.win[s].reserve((size_t)chunk * n_vote_fields * 4);
+            if (!rc) rc = cx.vmeta[s].reserve((size_t)chunk * n_vote_fields * 4);
+        }
+        if (n_num_fields && !rc) {
+            rc = cx.vals[s].reserve((size_t)chunk * n_num_fields * n * 8);
+            if (!rc) rc = cx.value[s].reserve((size_t)chunk * n_num_fields * 8);
+            if (!rc) rc = cx.nmeta[s].reserve((size_t)chunk * n_num_fields * 4);
+        }
+    }
+    if (rc) return finish(rc);
+    const int32_t *d_none = nullptr;
+    if (h_none_code && n_vote_fields) {
+        rc = cx.none.reserve((size_t)n_vote_fields * 4);
+        if (rc) return finish(rc);
+        if (cudaMemcpyAsync(cx.none.p, h_none_code, (size_t)n_vote_fields * 4, cudaMemcpyHostToDevice, cx.streams[0]) != cudaSuccess ||
+            cudaStreamSynchronize(cx.streams[0]) != cudaSuccess)
+            return finish(fail(KC_ECUDA, "none_code upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+        d_none = cx.none.as<int32_t>();
+    }
+    int64_t r0 = 0;
+    for (int it = 0; r0 < n_records && !rc; ++it, r0 += chunk) {
+        const int s = it % HostCtx::kStreams;
+        cudaStream_t st = cx.streams[s];
+        const int64_t nr = std::min(chunk, n_records - r0);
+        cudaError_t e = cudaSuccess;
+        if (n_vote_fields) {
+            const int64_t G = nr * n_vote_fields;
+            e = cudaMemcpyAsync(cx.codes[s].as<int32_t>(), h_codes + r0 * n_vote_fields * n, (size_t)G * n * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                rc = kc_vote_i32(cx.codes[s].as<int32_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st);
+                if (rc) break;
+                e = cudaMemcpyAsync(h_win_code + r0 * n_vote_fields, cx.win[s].as<int32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(h_vote_meta + r0 * n_vote_fields, cx.vmeta[s].as<uint32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
+        }
+        if (n_num_fields && e == cudaSuccess) {
+            const int64_t G = nr * n_num_fields;
+            e = cudaMemcpyAsync(cx.vals[s].as<double>(), h_vals + r0 * n_num_fields * n, (size_t)G * n * 8, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                rc = kc_numeric_f64(cx.vals[s].as<double>(), G, n, rel_eps, abs_eps, cx.value[s].as<double>(), cx.nmeta[s].as<uint32_t>(), st);
+                if (rc) break;
+                e = cudaMemcpyAsync(h_value + r0 * n_num_fields, cx.value[s].as<double>(), (size_t)G * 8, cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(h_num_meta + r0 * n_num_fields, cx.nmeta[s].as<uint32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
+        }
+        if (e != cudaSuccess) rc = fail(KC_ECUDA, "kc_consensus_host: %s", cudaGetErrorString(e));
+    }
+    for (auto &s : cx.streams) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && !rc) rc = fail(KC_ECUDA, "kc_consensus_host sync: %s", cudaGetErrorString(e));
+    }
+    return finish(rc);
+}
+
+}  // extern "C"

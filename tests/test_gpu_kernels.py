@@ -1,0 +1,223 @@
+"""GPU parity, kernel level: CUDA K1/K2 (through the C ABI) vs the columnar C oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import columnar as OC
+
+pytestmark = pytest.mark.gpu
+
+NONE, ABSENT = OC.F64_NONE, OC.F64_ABSENT
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def random_codes(rng, G, n, vocab, p_none=0.08, p_absent=0.03, p_agree=0.6):
+    truth = rng.integers(0, vocab, (G, 1))
+    draw = rng.integers(0, vocab, (G, n))
+    codes = np.where(rng.random((G, n)) < p_agree, truth, draw).astype(np.int32)
+    codes[rng.random((G, n)) < p_none] = -1
+    codes[rng.random((G, n)) < p_absent] = -2
+    return codes
+
+
+def random_vals(rng, G, n, style):
+    if style == "ints":
+        t = np.floor(rng.random((G, 1)) * 1e6) + 1
+        d = np.floor(rng.random((G, n)) * 1e6) + 1
+    elif style == "near":  # straddle the 3% tolerance, both signs, zeros, tiny values
+        base = rng.choice([1.0, -1.0, 100.0, 1e-7, 0.0, 12.5, -3000.0], (G, 1))
+        t = base
+        d = base * (1.0 + rng.choice([-0.05, -0.031, -0.029, 0.0, 0.015, 0.0299, 0.0301, 0.06], (G, n)))
+    elif style == "pow10":  # decimal-shift and sign mistakes -> tie-resolution paths
+        base = rng.choice([12.5, 7.0, 0.125, 3.3], (G, 1))
+        t = base
+        d = base * rng.choice([1.0, 10.0, 0.1, -1.0, 100.0, 1.0, 1.0], (G, n))
+    else:
+        t = rng.uniform(1, 1e4, (G, 1))
+        d = rng.uniform(1, 1e4, (G, n))
+    p_agree = rng.choice([0.2, 0.5, 0.8], (G, 1))
+    vals = np.where(rng.random((G, n)) < p_agree, t, d).astype(np.float64)
+    vals[rng.random((G, n)) < 0.08] = NONE
+    vals[rng.random((G, n)) < 0.03] = ABSENT
+    vals[rng.random((G, n)) < 0.02] = np.nan
+    vals[rng.random((G, n)) < 0.01] = np.inf
+    return np.ascontiguousarray(vals)
+
+
+def same_bits(a: np.ndarray, b: np.ndarray) -> bool:
+    return np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 12, 16, 17, 31, 32, 33, 63, 64])
+def test_vote_matches_oracle(n):
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(100 + n)
+    F = 6
+    G = F * 4099  # not a multiple of the tile
+    for vocab, p_agree in ((3, 0.6), (1000, 0.3), (2, 0.9)):
+        codes = random_codes(rng, G, n, vocab, p_agree=p_agree)
+        none_code = np.array([-1, 0, -1, 1, vocab + 5, -1], dtype=np.int32)
+        for nc in (None, none_code):
+            exp_win, exp_meta = OC.vote(codes, nc)
+            d_nc = torch.from_numpy(nc).cuda() if nc is not None else None
+            win, meta = K.vote(torch.from_numpy(codes).cuda(), d_nc)
+            torch.cuda.synchronize()
+            assert np.array_equal(win.cpu().numpy(), exp_win)
+            assert np.array_equal(meta.cpu().numpy().view(np.uint32), exp_meta)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 16, 24, 32, 48, 64])
+@pytest.mark.parametrize("style", ["ints", "near", "pow10", "floats"])
+def test_numeric_matches_oracle(n, style):
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(7 * n + len(style))
+    G = 9001
+    vals = random_vals(rng, G, n, style)
+    exp_val, exp_meta = OC.numeric(vals)
+    val, meta = K.numeric(torch.from_numpy(vals).cuda())
+    torch.cuda.synchronize()
+    got_meta = meta.cpu().numpy().view(np.uint32)
+    bad = np.nonzero(got_meta != exp_meta)[0]
+    assert bad.size == 0, (bad[:5], vals[bad[:1]], OC.meta_fields(got_meta[bad[:1]]), OC.meta_fields(exp_meta[bad[:1]]))
+    got_val = val.cpu().numpy()
+    badv = np.nonzero(got_val.view(np.uint64) != exp_val.view(np.uint64))[0]
+    # NaN outputs ("no value") only need to be NaN on both sides
+    badv = [i for i in badv if not (np.isnan(got_val[i]) and np.isnan(exp_val[i]))]
+    assert not badv, (badv[:5], vals[badv[:1]], got_val[badv[:1]], exp_val[badv[:1]])
+
+
+def test_numeric_other_eps():
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(5)
+    vals = random_vals(rng, 5000, 16, "near")
+    for rel, ab in ((0.0, 0.0), (0.1, 1e-3), (1e-9, 0.5)):
+        exp_val, exp_meta = OC.numeric(vals, rel, ab)
+        val, meta = K.numeric(torch.from_numpy(vals).cuda(), rel, ab)
+        assert np.array_equal(meta.cpu().numpy().view(np.uint32), exp_meta)
+        g, e = val.cpu().numpy(), exp_val
+        ok = (g.view(np.uint64) == e.view(np.uint64)) | (np.isnan(g) & np.isnan(e))
+        assert ok.all()
+
+
+def test_confidence_matches_python_round():
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(11)
+    metas, pvfs, exp_v, exp_n = [], [], [], []
+    for present in range(0, 65):
+        for support in range(0, present + 1):
+            nn = int(rng.integers(max(support, 1), present + 1)) if present else 0
+            for pvf in (1.0, 0.5, 2 / 3, 0.3333333333333333, 7 / 9 * (5 / 8)):
+                for flags in ((1,), (1 | 2,), (8,), (0,)):
+                    f = flags[0]
+                    if (f & 1) and support == 0:
+                        continue
+                    metas.append((3 & 0x3F) | (support << 6) | (nn << 13) | (present << 20) | (f << 27))
+                    pvfs.append(pvf)
+                    if f & 1:
+                        exp_v.append(round(pvf * (support / present), 5))
+                        exp_n.append(pvf * (1 / present) * 1.0 if f & 2 else round(support / nn, 5))
+                    elif f & 8:
+                        exp_v.append(pvf * (nn / present))
+                        exp_n.append(pvf * (nn / present))
+                    else:
+                        exp_v.append(pvf if present == 0 else 0.0)
+                        exp_n.append(pvf if present == 0 else 0.0)
+    meta = torch.tensor(np.array(metas, dtype=np.uint32).view(np.int32)).cuda()
+    pvf = torch.tensor(pvfs, dtype=torch.float64).cuda()
+    got_v = K.confidence(meta, False, pvf).cpu().numpy()
+    got_n = K.confidence(meta, True, pvf).cpu().numpy()
+    m = np.array(metas, dtype=np.uint32)
+    has = ((m >> 27) & 1) == 1
+    nofin = ((m >> 27) & 8) == 8
+    # vote confidences are defined for HAS_VALUE / no-value words; numeric for all four kinds
+    sel_v = has | (~has & ~nofin)
+    assert np.array_equal(got_v[sel_v], np.array(exp_v)[sel_v])
+    assert np.array_equal(got_n, np.array(exp_n))
+
+
+def test_round5_random_products():
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(3)
+    # confidence = round(pvf * support/present, 5) for arbitrary pvf in (0, 1]
+    present = rng.integers(1, 65, 200000)
+    support = (rng.random(200000) * present).astype(np.int64) + 1
+    support = np.minimum(support, present)
+    pvf = rng.random(200000)
+    pvf[:1000] = np.round(pvf[:1000], 5) + 5e-6  # near-half cases
+    meta = ((support << 6) | (present << 13) | (present << 20) | (1 << 27)).astype(np.uint32)
+    got = K.confidence(torch.tensor(meta.view(np.int32)).cuda(), False, torch.tensor(pvf).cuda()).cpu().numpy()
+    exp = np.array([round(float(p) * (int(s) / int(t)), 5) for p, s, t in zip(pvf, support, present)])
+    assert np.array_equal(got, exp)
+
+
+def test_logprob_sum_matches_oracle():
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(17)
+    lens = rng.integers(0, 200, 5000)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    lp = (-rng.exponential(1.0, offsets[-1])).astype(np.float32)
+    exp = OC.logprob_sum(lp, offsets)
+    got = K.logprob_sum(torch.from_numpy(lp).cuda(), torch.from_numpy(offsets).cuda()).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    ref64 = np.array([lp[offsets[i]:offsets[i + 1]].astype(np.float64).sum() for i in range(len(lens))])
+    assert np.max(np.abs(got - ref64)) < 1e-3  # fp32 accumulation error at |sum| ~ 200; the spec is the fixed order above
+
+
+def test_s32_full_size_properties():
+    """BASELINE config 2 at full size (1M x 32 fields, n=16): size-independent properties."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    from k_llms_b200 import synth
+    N, n = 1_000_000, 16
+    codes, none_code, vals = synth.s32_torch(N, n, 20260923, "cuda")
+    win, meta = K.vote(codes.view(N * 24, n), none_code)
+    value, nmeta = K.numeric(vals.view(N * 8, n))
+    torch.cuda.synchronize()
+    m = meta.view(N, 24).to(torch.int64) & 0xFFFFFFFF
+    idx, support, nn, present = m & 0x3F, (m >> 6) & 0x7F, (m >> 13) & 0x7F, (m >> 20) & 0x7F
+    has = ((m >> 27) & 1) == 1
+    c3 = codes.to(torch.int64)
+    eff = torch.where(c3 == -1, none_code.view(1, 24, 1).to(torch.int64), c3)
+    assert bool((present == n).all())
+    assert bool((nn == (eff >= 0).sum(-1)).all())
+    # the winner's count is what the result word says, and no class beats it
+    w = win.view(N, 24, 1).to(torch.int64)
+    assert bool((((eff == w) & (eff >= 0)).sum(-1) == support)[has].all())
+    onehot_max = torch.zeros_like(support)
+    for code in range(8):
+        onehot_max = torch.maximum(onehot_max, (eff == code).sum(-1))
+    assert bool((onehot_max == support).all())
+    # first-seen: cell idx holds the winner, and no earlier cell does
+    first = torch.gather(eff, 2, idx.unsqueeze(-1)).squeeze(-1)
+    assert bool((first == win.view(N, 24))[has].all())
+    pos = torch.arange(n, device="cuda").view(1, 1, n)
+    earlier = ((eff == w) & (pos < idx.unsqueeze(-1))).any(-1)
+    assert not bool(earlier[has].any())
+    # idempotence: consensus of n copies of the consensus is the consensus
+    again, meta2 = K.vote(win.view(-1, 1).expand(-1, n).contiguous(), None)
+    assert bool((again == win).all())
+    # numeric: a value exists wherever >= 1 finite cell; it lies inside [min, max] of the finite cells
+    v = vals
+    fin = torch.isfinite(v)
+    lo = torch.where(fin, v, torch.full_like(v, float("inf"))).amin(-1)
+    hi = torch.where(fin, v, torch.full_like(v, float("-inf"))).amax(-1)
+    val = value.view(N, 8)
+    ok = (val >= lo) & (val <= hi)
+    assert bool(ok[fin.any(-1)].all())
+    # sample 20k records against the C oracle bit for bit
+    sel = torch.randperm(N, device="cuda")[:20000]
+    ew, em = OC.vote(codes[sel].cpu().numpy().reshape(-1, n), none_code.cpu().numpy())
+    assert np.array_equal(win.view(N, 24)[sel].cpu().numpy().reshape(-1), ew)
+    assert np.array_equal(meta.view(N, 24)[sel].cpu().numpy().reshape(-1).view(np.uint32), em)
+    ev, enm = OC.numeric(vals[sel].cpu().numpy().reshape(-1, n))
+    assert np.array_equal(value.view(N, 8)[sel].cpu().numpy().reshape(-1).view(np.uint64), ev.view(np.uint64))
+    assert np.array_equal(nmeta.view(N, 8)[sel].cpu().numpy().reshape(-1).view(np.uint32), enm)
