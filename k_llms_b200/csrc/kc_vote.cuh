@@ -23,38 +23,37 @@ struct MaskOf<64> {
 };
 __device__ __forceinline__ int popc_m(uint32_t m) { return __popc(m); }
 __device__ __forceinline__ int popc_m(uint64_t m) { return __popcll(m); }
+__device__ __forceinline__ int ffs_mask(uint32_t m) { return __ffs((int)m); }
+__device__ __forceinline__ int ffs_mask(uint64_t m) { return __ffsll((long long)m); }
 
-// Mode of the voting cells of one group.  raw[i]: code >= 0, KC_CODE_NONE (-1) or absent (< -1).
-// none_code >= 0 makes None cells vote as that code (bool fields: None -> False, cu:956).
-// Classes are visited in first-seen order and a later class must be STRICTLY larger to win, which is
-// exactly Counter.most_common(1) (cu:958,969).  The scan stops once the unvisited cells cannot reach
-// the best count, so agreeing data costs ~2 passes instead of n.
-template <int N>
-__device__ __forceinline__ void vote_core(const int32_t (&raw)[N], int32_t none_code, int32_t &win_code, uint32_t &meta) {
-    using M = typename MaskOf<N>::type;
-    int32_t v[N];
-    M live = 0;
-    int present = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        int32_t c = raw[i];
-        const bool absent = c < KC_CODE_NONE;
-        present += absent ? 0 : 1;
-        c = (c == KC_CODE_NONE) ? none_code : c;
-        c = absent ? KC_CODE_NONE : c;
-        v[i] = c;
-        live |= (c >= 0) ? (M(1) << i) : M(0);
-    }
+template <typename M, int N>
+__host__ __device__ constexpr M full_mask() {
+    M m = 0;
+    for (int i = 0; i < N; ++i) m |= M(1) << i;
+    return m;
+}
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {  // bitwise majority, one LOP3
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Exact first-seen-order scan (the general case).  Classes are visited in the order of their first cell and a
+// later class must be STRICTLY larger to win, which is Counter.most_common(1) (cu:958,969).  `live` = voting
+// cells, `nones` = None cells that vote as `nc` (nc >= 0) and are part of `live`.  The scan stops as soon as
+// the unvisited cells cannot reach the best count.
+template <int N, typename M>
+__device__ __forceinline__ uint32_t vote_scan(const int32_t (&v)[N], M live, M nones, int32_t nc, int present, int32_t &win_code) {
     const int voters = popc_m(live);
     int best_cnt = 0, best_idx = 0;
     int32_t best_code = KC_CODE_NONE;
     bool tie = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        if (live == 0 || popc_m(live) < best_cnt) break;
         if ((live >> i) & 1) {
-            const int32_t c = v[i];
-            M eq = 0;
+            const int32_t c = (v[i] == KC_CODE_NONE) ? nc : v[i];
+            M eq = (c == nc) ? nones : M(0);
 #pragma unroll
             for (int j = i; j < N; ++j) eq |= (v[j] == c) ? (M(1) << j) : M(0);
             const int cnt = popc_m(eq);
@@ -67,11 +66,60 @@ __device__ __forceinline__ void vote_core(const int32_t (&raw)[N], int32_t none_
                 tie = true;
             }
             live &= ~eq;
+            if (popc_m(live) < best_cnt) live = 0;  // nothing left can win or tie
         }
     }
     win_code = best_code;
-    meta = pack_meta(best_idx, best_cnt, voters, present,
+    return pack_meta(best_idx, best_cnt, voters, present,
                      best_cnt > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
+}
+
+// Mode of the voting cells of one group.  raw[i]: code >= 0, KC_CODE_NONE (-1) or absent (< -1).
+// none_code >= 0 makes None cells vote as that code (bool fields: None -> False, cu:956).
+//
+// Fast path: a bitwise majority-of-majorities over nine cells (4 LOP3) guesses the mode; ONE equality pass
+// counts it.  If the guess holds a strict majority of the voting cells it is the unique mode (no tie is
+// possible) and its first cell is the first-seen original (cu:971) — done in ~1 pass.  Any other outcome
+// (no strict majority, garbage guess) falls through to the exact scan, so correctness never depends on the guess.
+template <int N>
+__device__ __forceinline__ void vote_core(const int32_t (&raw)[N], int32_t none_code, int32_t &win_code, uint32_t &meta) {
+    using M = typename MaskOf<N>::type;
+    constexpr M kFull = full_mask<M, N>();
+    int32_t lo = raw[0];
+    M neg = 0;  // cells < 0: None or absent
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        lo = min(lo, raw[i]);
+        neg |= (raw[i] < 0) ? (M(1) << i) : M(0);
+    }
+    M absent = 0;
+    if (lo < KC_CODE_NONE) {  // rare: some candidate is not part of this node (nested payloads)
+#pragma unroll
+        for (int i = 0; i < N; ++i) absent |= (raw[i] < KC_CODE_NONE) ? (M(1) << i) : M(0);
+    }
+    const M nones_all = neg & ~absent;
+    const M nones = none_code >= 0 ? nones_all : M(0);  // None cells that vote
+    const M live = (kFull & ~neg) | nones;
+    const int present = N - popc_m(absent);
+    const int voters = popc_m(live);
+
+    if constexpr (N >= 9) {
+        const uint32_t guess = maj3(maj3(raw[0], raw[1], raw[2]), maj3(raw[3], raw[4], raw[5]), maj3(raw[6], raw[7], raw[8]));
+        const int32_t c = (int32_t)guess;
+        if (c >= 0) {
+            M eq = (c == none_code) ? nones : M(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) eq |= (raw[j] == c) ? (M(1) << j) : M(0);
+            const int cnt = popc_m(eq);
+            if (2 * cnt > voters) {
+                win_code = c;
+                meta = pack_meta(ffs_mask(eq) - 1, cnt, voters, present, KC_FLAG_HAS_VALUE);
+                return;
+            }
+        }
+    }
+    // absent cells (< -1) are never live and never equal a code >= 0, so the scan can read raw[] as is
+    meta = vote_scan<N, M>(raw, live, nones, none_code, present, win_code);
 }
 
 // ---------------------------------------------------------------- direct front-end

@@ -116,7 +116,7 @@ def test_confidence_matches_python_round():
             for pvf in (1.0, 0.5, 2 / 3, 0.3333333333333333, 7 / 9 * (5 / 8)):
                 for flags in ((1,), (1 | 2,), (8,), (0,)):
                     f = flags[0]
-                    if (f & 1) and support == 0:
+                    if (f & (1 | 8)) and (support == 0 or present == 0):
                         continue
                     metas.append((3 & 0x3F) | (support << 6) | (nn << 13) | (present << 20) | (f << 27))
                     pvfs.append(pvf)
@@ -211,7 +211,7 @@ def test_s32_full_size_properties():
     lo = torch.where(fin, v, torch.full_like(v, float("inf"))).amin(-1)
     hi = torch.where(fin, v, torch.full_like(v, float("-inf"))).amax(-1)
     val = value.view(N, 8)
-    ok = (val >= lo) & (val <= hi)
+    ok = (val >= lo * (1 - 1e-15)) & (val <= hi * (1 + 1e-15))  # np.mean of k equal floats may round by an ulp
     assert bool(ok[fin.any(-1)].all())
     # sample 20k records against the C oracle bit for bit
     sel = torch.randperm(N, device="cuda")[:20000]

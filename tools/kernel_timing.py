@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--n", type=int, nargs="+", default=[16])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--p-agree", type=float, default=0.8)
+    ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
     peak = 6571.2
     try:
@@ -42,8 +43,8 @@ def main():
         codes, none_code, vals = synth.s32_torch(N, n, 20260923, "cuda", p_agree=args.p_agree)
         c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
         win = torch.empty(N * 24, dtype=torch.int32, device="cuda")
-        t_v, t_v0 = timeit(lambda: K.vote(c2, none_code), args.iters)
-        t_n, t_n0 = timeit(lambda: K.numeric(v2), args.iters)
+        t_v, t_v0 = timeit(lambda: K.vote(c2, none_code), args.iters, args.warmup)
+        t_n, t_n0 = timeit(lambda: K.numeric(v2), args.iters, args.warmup)
         bv, bn = N * 24 * (4 * n + 8), N * 8 * (8 * n + 12)
         out = {"n": n, "records": N, "p_agree": args.p_agree, "force_direct": os.environ.get("KC_FORCE_DIRECT", "0"),
                "vote_ms": round(t_v, 4), "vote_GBps": round(bv / t_v / 1e6, 1), "vote_frac": round(bv / t_v / 1e6 / peak, 3),
