@@ -71,6 +71,20 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// Same, with a register the issue must wait for (orders the copy after the instructions that produce `dep`).
+__device__ __forceinline__ void tma_load_2d_dep(void *smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1,
+                                                uint64_t *bar, uint64_t policy, uint32_t dep) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 kc_dep;\n\t"
+        "mov.b32 kc_dep, %6;\n\t"
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+        "[%4], %5;\n\t"
+        "}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy), "r"(dep)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- global memory: streaming loads / stores
 
 __device__ __forceinline__ int4 ldg_stream_v4(const void *p) {
@@ -78,6 +92,14 @@ __device__ __forceinline__ int4 ldg_stream_v4(const void *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
+    return r;
+}
+
+// read-only path, default L1 allocation: a thread's neighbouring 16-byte pieces share 32-byte sectors, so the
+// second piece should hit L1 instead of going back to L2
+__device__ __forceinline__ int4 ldg_nc_v4(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 

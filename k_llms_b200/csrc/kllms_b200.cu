@@ -121,25 +121,42 @@ constexpr int64_t kMaxGroupsPerLaunch = (int64_t)1 << 28;
 
 // ---------------------------------------------------------------- K1 launchers
 
-template <int N, int TILE, int STAGES>
-int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
-                    cudaStream_t st) {
-    auto kernel = kc::vote_tma_kernel<N, TILE, STAGES>;
-    const size_t smem = (size_t)STAGES * TILE * N * 4 + 1024;
+kc::FieldMap make_field_map(const int32_t *none_code, int n_fields) {
+    kc::FieldMap fm;
+    fm.none_code = none_code;
+    fm.n_fields = (uint32_t)std::max(n_fields, 1);
+    fm.magic = (uint32_t)(((uint64_t)1 << 32) / fm.n_fields + 1);
+    return fm;
+}
+
+template <int N, int WARPS, int STAGES, bool HAS_NC>
+int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
+                       cudaStream_t st) {
+    auto kernel = kc::vote_tma_kernel<N, WARPS, STAGES, HAS_NC>;
+    const size_t smem = (size_t)WARPS * STAGES * 32 * N * 4 + 1024;
     // a slab starts on a record boundary so that (g - g0) % n_fields == g % n_fields
     const int64_t slab = std::max<int64_t>(n_fields, kMaxGroupsPerLaunch / n_fields * n_fields);
     for (int64_t g0 = 0; g0 < G; g0 += slab) {
         const int64_t gs = std::min(slab, G - g0);
         CUtensorMap map;
-        int rc = make_row_tensor_map(map, codes + g0 * N, gs, N * 4, TILE);
+        int rc = make_row_tensor_map(map, codes + g0 * N, gs, N * 4, 32);
         if (rc) return rc;
         int grid = 0;
-        rc = persistent_grid(kernel, TILE, smem, (gs + TILE - 1) / TILE, grid);
+        rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
         if (rc) return rc;
-        kernel<<<grid, TILE, smem, st>>>(map, gs, none_code, n_fields, win + g0, meta + g0);
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, gs, make_field_map(none_code, n_fields), win + g0, meta + g0);
         KC_CUDA(cudaGetLastError());
     }
     return KC_OK;
+}
+
+template <int N, int WARPS, int STAGES>
+int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
+                    cudaStream_t st) {
+    if (none_code && n_fields < 60000)
+        return launch_vote_tma_nc<N, WARPS, STAGES, true>(codes, G, none_code, n_fields, win, meta, st);
+    if (none_code) return fail(KC_EINVAL, "kc_vote_i32: more than 60000 fields with none_code is not supported");
+    return launch_vote_tma_nc<N, WARPS, STAGES, false>(codes, G, nullptr, 1, win, meta, st);
 }
 
 template <int NP, bool VEC>
@@ -151,7 +168,11 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     const int threads = 256;
     const int64_t blocks = (G + threads - 1) / threads;
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * 8);
-    kc::vote_direct_kernel<NP, VEC><<<grid, threads, 0, st>>>(codes, G, n, none_code, n_fields, win, meta);
+    const kc::FieldMap fm = make_field_map(none_code, n_fields);
+    if (none_code)
+        kc::vote_direct_kernel<NP, VEC, true><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+    else
+        kc::vote_direct_kernel<NP, VEC, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }
@@ -297,10 +318,10 @@ int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32
         case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
         case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
         case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 8: return launch_vote_tma<8, 256, 6>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 16: return launch_vote_tma<16, 256, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 32: return launch_vote_tma<32, 256, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 64: return launch_vote_tma<64, 128, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 8: return launch_vote_tma<8, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 16: return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 32: return launch_vote_tma<32, 8, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 64: return launch_vote_tma<64, 4, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
         default: break;
     }
     if (n < 4) return launch_vote_direct<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
