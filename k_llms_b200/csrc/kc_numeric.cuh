@@ -8,35 +8,62 @@
 // left-to-right, reduction seeded with +0.0); every add/mul/div/sqrt below is a single IEEE-754
 // round-to-nearest operation in that order (the file is compiled with -fmad=false as well).
 //
-// The sort is a Batcher merge-exchange network on registers (static indices).  The sorted row is then
-// parked in shared memory as scratch[i*T + tid]: for a fixed i a warp touches 32 consecutive doubles, and
-// because T*8 is a multiple of 128 B the bank of a word depends on tid only, so the data-dependent indices
-// of the cluster walk never cause a bank conflict.
+// Cost model: the op is HBM-streaming (8n bytes in, 12 out per group) but a 64-bit sort in 32-bit registers is
+// select-bound, so the sort runs on 32-bit KEYS instead: the order-preserving image of each cell's high word
+// with the candidate index in the low log2(n) bits.  A compare-exchange is then one IMNMX pair.  The cells
+// themselves stay in shared memory ("row memory": the thread's row of the TMA tile, or a [cell][thread] plane)
+// and are fetched once in key order.  Keys drop the low mantissa bits, so values that differ only there may
+// come out swapped; the adjacent differences the clustering needs anyway detect that, and a bubble pass on
+// the (rare) offending run repairs it.  Non-finite cells get keys above every finite key and sort to the end.
 #pragma once
 
 #include <utility>
 
 #include "kc_common.cuh"
-#include "kc_vote.cuh"  // MaskOf, Swizzle
+#include "kc_vote.cuh"  // MaskOf, Swizzle, popc_m
 
 namespace kc {
 
-constexpr uint32_t kNoneHi = (uint32_t)(KC_F64_NONE_BITS >> 32);
+constexpr uint32_t kTagHi = (uint32_t)(KC_F64_NONE_BITS >> 32);
 constexpr uint32_t kNoneLo = (uint32_t)(KC_F64_NONE_BITS & 0xFFFFFFFFu);
 constexpr uint32_t kAbsentLo = (uint32_t)(KC_F64_ABSENT_BITS & 0xFFFFFFFFu);
+constexpr uint32_t kKeyNonFinite = 0xFFE00000u;  // keys >= this belong to non-finite cells
 
 __device__ __forceinline__ int ffs_m(uint32_t m) { return __ffs((int)m); }
 __device__ __forceinline__ int ffs_m(uint64_t m) { return __ffsll((long long)m); }
 
-// 10.0**k for k = -6..6 exactly as CPython computes it (correctly rounded decimal literals; checked in
-// oracle/gen_golden.py's environment): consensus_utils.py:1156-1157.
+// 10.0**k for k = -6..6 exactly as CPython computes it (correctly rounded decimal literals): cu:1156-1157.
 __device__ __constant__ double kPow10[13] = {1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6};
 
-struct Scratch {  // per-thread view of the [i][tid] scratch plane
-    const double *base;
-    int stride;
-    __device__ __forceinline__ double operator[](int i) const { return base[(size_t)i * stride]; }
+// ---------------------------------------------------------------- row memory
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int ROW_BYTES>
+struct SwzRow {  // this thread's row of a TMA-swizzled tile
+    uint32_t base, row_off;
+    __device__ __forceinline__ uint32_t addr(uint32_t elem) const {
+        return base + Swizzle<ROW_BYTES>::apply(row_off + elem * 8u);
+    }
 };
+struct PlaneRow {  // [cell][thread] plane: pitch = threads*8 bytes, a multiple of 128 => bank depends on tid only
+    uint32_t base, pitch;
+    __device__ __forceinline__ uint32_t addr(uint32_t elem) const { return base + elem * pitch; }
+};
+
+// ---------------------------------------------------------------- numpy reductions over sorted row memory
 
 // numpy DOUBLE_pairwise_sum (n <= 128) over f(0..n-1), then the +0.0 seed of add.reduce.
 template <typename F>
@@ -65,29 +92,35 @@ __device__ __forceinline__ double np_sum(F f, int n) {
     return __dadd_rn(0.0, res);
 }
 
-__device__ __forceinline__ double np_mean(const Scratch &xs, int s, int len) {
-    return __ddiv_rn(np_sum([&](int i) { return xs[s + i]; }, len), (double)len);
+template <typename Row>
+__device__ __forceinline__ double np_mean(const Row &xs, int s, int len) {
+    return __ddiv_rn(np_sum([&](int i) { return lds_f64(xs.addr(s + i)); }, len), (double)len);
 }
 
-__device__ __forceinline__ double np_median(const Scratch &xs, int s, int len) {  // ascending input
-    if (len & 1) return __dadd_rn(0.0, __dadd_rn(-0.0, xs[s + len / 2]));
-    return __ddiv_rn(__dadd_rn(0.0, __dadd_rn(__dadd_rn(-0.0, xs[s + len / 2 - 1]), xs[s + len / 2])), 2.0);
+template <typename Row>
+__device__ __forceinline__ double np_median(const Row &xs, int s, int len) {  // ascending input
+    if (len & 1) return __dadd_rn(0.0, __dadd_rn(-0.0, lds_f64(xs.addr(s + len / 2))));
+    return __ddiv_rn(
+        __dadd_rn(0.0, __dadd_rn(__dadd_rn(-0.0, lds_f64(xs.addr(s + len / 2 - 1))), lds_f64(xs.addr(s + len / 2)))), 2.0);
 }
 
-__device__ __forceinline__ double np_std(const Scratch &xs, int s, int len) {
+template <typename Row>
+__device__ __forceinline__ double np_std(const Row &xs, int s, int len) {
     const double mean = np_mean(xs, s, len);
     const double ss = np_sum(
         [&](int i) {
-            const double d = __dadd_rn(xs[s + i], -mean);
+            const double d = __dadd_rn(lds_f64(xs.addr(s + i)), -mean);
             return __dmul_rn(d, d);
         },
         len);
     return __dsqrt_rn(__ddiv_rn(ss, (double)len));
 }
 
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }  // NaN-free operands only
+
 __device__ __forceinline__ bool is_close(double a, double b, double rel_eps, double abs_eps) {  // cu:1146-1148
-    const double denom = fmax(fmax(fabs(a), fabs(b)), 1.0);
-    return fabs(__dadd_rn(a, -b)) <= fmax(abs_eps, __dmul_rn(rel_eps, denom));
+    const double denom = dmax(dmax(fabs(a), fabs(b)), 1.0);
+    return fabs(__dadd_rn(a, -b)) <= dmax(abs_eps, __dmul_rn(rel_eps, denom));
 }
 
 __device__ __forceinline__ bool is_close_pow10(double a, double b, double rel_eps, double abs_eps) {  // cu:1153-1160
@@ -97,14 +130,14 @@ __device__ __forceinline__ bool is_close_pow10(double a, double b, double rel_ep
     return false;
 }
 
-// Tie between equally large clusters (cu:1189-1219).  `starts` has one bit per cluster start (< m).
 struct TieResult {
     double value;
     int support;
 };
 
-template <typename M>
-__device__ __noinline__ TieResult numeric_tie(const Scratch xs, M starts, int m, int top, double rel_eps, double abs_eps) {
+// Tie between equally large clusters (cu:1189-1219).  `starts` has one bit per cluster start (< m).
+template <typename M, typename Row>
+__device__ __noinline__ TieResult numeric_tie(const Row xs, M starts, int m, int top, double rel_eps, double abs_eps) {
     int best_s = -1, best_support = 0;
     double best_spread = 0.0, best_center = 0.0;
     M sk = starts;
@@ -129,6 +162,7 @@ __device__ __noinline__ TieResult numeric_tie(const Scratch xs, M starts, int m,
                 support += olen;
         }
         const double spread = len > 1 ? np_std(xs, s, len) : 0.0;
+        // sort key (-support, spread, -|center|), stable (cu:1211): only a strict improvement replaces the best
         const bool better = best_s < 0 || support > best_support ||
                             (support == best_support &&
                              (spread < best_spread || (spread == best_spread && fabs(center) > fabs(best_center))));
@@ -142,9 +176,10 @@ __device__ __noinline__ TieResult numeric_tie(const Scratch xs, M starts, int m,
     return TieResult{np_mean(xs, best_s, top), best_support};
 }
 
-// Batcher merge-exchange sorting network, ascending, N a power of two.  The comparator list is built at
-// compile time and expanded as a fold over an index_sequence so that every register index is a constant
-// (a loop nest with data-free but irregular bounds is not reliably unrolled and would push x[] to local memory).
+// ---------------------------------------------------------------- 32-bit key sort
+
+// Batcher merge-exchange network, ascending, N a power of two; comparator list built at compile time and
+// expanded as a fold so every register index is a constant.
 template <int N>
 struct BatcherNet {
     int a[N * N / 2 + 1];
@@ -164,90 +199,126 @@ struct BatcherNet {
 };
 
 template <int A, int B, int N>
-__device__ __forceinline__ void compare_exchange(double (&x)[N]) {
-    const double lo = x[A], hi = x[B];
-    const bool sw = hi < lo;
-    x[A] = sw ? hi : lo;
-    x[B] = sw ? lo : hi;
+__device__ __forceinline__ void compare_exchange(uint32_t (&x)[N]) {
+    const uint32_t lo = min(x[A], x[B]), hi = max(x[A], x[B]);
+    x[A] = lo;
+    x[B] = hi;
 }
 
 template <int N, size_t... I>
-__device__ __forceinline__ void sort_network_impl(double (&x)[N], std::index_sequence<I...>) {
+__device__ __forceinline__ void sort_keys_impl(uint32_t (&x)[N], std::index_sequence<I...>) {
     constexpr BatcherNet<N> net{};
     (compare_exchange<net.a[I], net.b[I], N>(x), ...);
 }
 
 template <int N>
-__device__ __forceinline__ void sort_network(double (&x)[N]) {
-    if constexpr (N > 1) {
-        constexpr BatcherNet<N> net{};
-        sort_network_impl<N>(x, std::make_index_sequence<net.count>{});
-    }
+__device__ __forceinline__ void sort_keys(uint32_t (&x)[N]) {
+    constexpr BatcherNet<N> net{};
+    sort_keys_impl<N>(x, std::make_index_sequence<net.count>{});
 }
 
-// x[]: raw cells of one group.  scratch: this thread's column of the [N][T] plane (stride T doubles).
-template <int N>
-__device__ __forceinline__ void numeric_core(double (&x)[N], double rel_eps, double abs_eps, double *scratch, int stride,
-                                             double &value, uint32_t &meta) {
+// ---------------------------------------------------------------- the core
+
+// hi[i] = high word of raw cell i; the raw cells are also resident in `row` (cell i at row.addr(i)).
+// On return row memory holds the sorted finite values (scratch).  thr = max(abs_eps, rel_eps*1.0).
+template <int N, typename Row>
+__device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row row, double rel_eps, double abs_eps,
+                                             double thr, double &value, uint32_t &meta) {
     using M = typename MaskOf<N>::type;
-    int present = 0, nn = 0, m = 0, first_nn = 0;
-    double single = 0.0;
-    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    static_assert(N >= 2 && (N & (N - 1)) == 0, "N must be a power of two >= 2");
+    constexpr uint32_t IDX = N - 1;
+    const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+
+    // A. keys + non-finite mask
+    uint32_t key[N];
+    M nf = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const uint32_t hi = (uint32_t)__double2hiint(x[i]);
-        const uint32_t lo = (uint32_t)__double2loint(x[i]);
-        const bool tagged = hi == kNoneHi;
-        const bool absent = tagged && lo == kAbsentLo;
-        const bool none = tagged && lo == kNoneLo;
-        const bool counted = !absent && !none;
-        const bool finite = counted && ((hi & 0x7FF00000u) != 0x7FF00000u);  // cu:1105-1114
-        present += absent ? 0 : 1;
-        const bool first_counted = counted && nn == 0;
-        first_nn = first_counted ? i : first_nn;
-        single = first_counted ? x[i] : single;  // the cell the single-value rule returns
-        nn += counted ? 1 : 0;
-        m += finite ? 1 : 0;
-        x[i] = finite ? x[i] : inf;  // non-numbers sort to the end
+        const uint32_t s = (uint32_t)((int32_t)hi[i] >> 31);
+        const uint32_t t = (hi[i] ^ (s | 0x80000000u)) - 0x00100000u;  // monotone in the value; non-finite -> >= 0xFFE00000
+        key[i] = (t & ~IDX) | (uint32_t)i;
+        nf |= (t >= kKeyNonFinite) ? (M(1) << i) : M(0);
+    }
+    const int m = N - popc_m(nf);  // finite cells (cu:1105-1114)
+
+    // B. classify the non-finite cells: None / absent / "present but not a number"
+    int present = N, nn = N, skip_idx = 0;
+    for (M w = nf; w;) {
+        const int i = ffs_m(w) - 1;
+        w &= w - 1;
+        const uint2 c = lds_u32x2(row.addr(i));  // .x = low word, .y = high word
+        const bool tagged = c.y == kTagHi;
+        if (tagged && c.x == kAbsentLo) {
+            --present;
+            --nn;
+        } else if (tagged && c.x == kNoneLo) {
+            --nn;
+        } else {
+            skip_idx = i;
+        }
     }
     if (nn == 0) {
-        value = __longlong_as_double(0x7FF8000000000000LL);
+        value = qnan;
         meta = pack_meta(0, 0, 0, present, 0);
         return;
     }
-    if (nn == 1) {  // cu:1085-1086: the original object
-        value = single;
-        meta = pack_meta(first_nn, 1, 1, present, KC_FLAG_HAS_VALUE | KC_FLAG_SINGLE);
+    if (nn == 1) {  // cu:1085-1086: the original object, whatever it is
+        M fin = ~nf;
+        if constexpr (N < 32) fin &= (M(1) << N) - 1;
+        const int idx = m == 1 ? ffs_m(fin) - 1 : skip_idx;
+        value = lds_f64(row.addr(idx));
+        meta = pack_meta(idx, 1, 1, present, KC_FLAG_HAS_VALUE | KC_FLAG_SINGLE);
         return;
     }
     if (m == 0) {  // cu:1115-1116
-        value = __longlong_as_double(0x7FF8000000000000LL);
+        value = qnan;
         meta = pack_meta(0, 0, nn, present, KC_FLAG_NO_FINITE);
         return;
     }
-    sort_network<N>(x);
 
-    // cluster starts: bit i set <=> x[i] opens a cluster (not close to x[i-1]); cu:1130-1143.
-    // |b-a| <= max(abs_eps, rel_eps*max(|a|,|b|,1))  <=>  (b-a) <= tol(a) or (b-a) <= tol(b),
-    // tol(v) = max(abs_eps, rel_eps*max(|v|,1)): exact because fl(rel_eps * .) is monotone for rel_eps >= 0.
-    M starts = 1;
-    {
-        double tol_prev = fmax(abs_eps, __dmul_rn(rel_eps, fmax(fabs(x[0]), 1.0)));
+    // D. sort keys; E. fetch the cells in key order
+    sort_keys<N>(key);
+    double xs[N];
 #pragma unroll
-        for (int i = 1; i < N; ++i) {
-            const double tol = fmax(abs_eps, __dmul_rn(rel_eps, fmax(fabs(x[i]), 1.0)));
-            const double d = __dadd_rn(x[i], -x[i - 1]);
-            const bool close = (d <= tol_prev) || (d <= tol);
-            starts |= close ? M(0) : (M(1) << i);
-            tol_prev = tol;
+    for (int k = 0; k < N; ++k) xs[k] = lds_f64(row.addr(key[k] & IDX));
+
+    // F. cluster starts: bit k set <=> xs[k] opens a cluster (not close to xs[k-1]); cu:1130-1143.
+    //    For a <= b:  |b-a| <= max(abs_eps, rel*max(|a|,|b|,1))
+    //            <=>  (b-a) <= rel*b  or  (b-a) <= rel*(-a)  or  (b-a) <= max(abs_eps, rel)
+    //    (max(|a|,|b|) = max(-a, b) for a <= b; fl(rel * .) is monotone for rel >= 0, so the product of the max is
+    //    the max of the products.)  `neg` collects the sign bits of the differences: a set bit below position m
+    //    means the truncated keys mis-ordered a pair.
+    M starts;
+    for (;;) {
+        starts = 1;
+        M neg = 0;
+        double p_prev = __dmul_rn(rel_eps, xs[0]);
+#pragma unroll
+        for (int k = 1; k < N; ++k) {
+            const double p = __dmul_rn(rel_eps, xs[k]);
+            const double d = __dadd_rn(xs[k], -xs[k - 1]);
+            const bool close = (d <= p) || (d <= -p_prev) || (d <= thr);
+            starts |= close ? M(0) : (M(1) << k);
+            neg = (neg << 1) | (M)((uint32_t)__double2hiint(d) >> 31);
+            p_prev = p;
+        }
+        // pairs k >= m involve the non-finite tail: drop them (they were shifted in last)
+        if ((m >= N ? neg : (neg >> (N - m))) == 0) break;
+#pragma unroll
+        for (int k = 1; k < N; ++k) {  // one bubble pass over the finite prefix
+            const bool sw = k < m && xs[k] < xs[k - 1];
+            const double a = xs[k - 1], b = xs[k];
+            xs[k - 1] = sw ? b : a;
+            xs[k] = sw ? a : b;
         }
     }
-    if (m < N) starts &= (M(1) << m) - 1;  // drop the +inf tail (m >= 1 here)
+    if (m < N) starts &= (M(1) << m) - 1;  // m >= 1 here
 
+    // G. park the sorted values in row memory for the data-dependent ranges below
 #pragma unroll
-    for (int i = 0; i < N; ++i) scratch[(size_t)i * stride] = x[i];
-    const Scratch xs{scratch, stride};
+    for (int k = 0; k < N; ++k) sts_f64(row.addr(k), xs[k]);
 
+    // H. largest cluster
     int top = 0, n_top = 0, top_s = 0;
     {
         M sk = starts;
@@ -268,9 +339,9 @@ __device__ __forceinline__ void numeric_core(double (&x)[N], double rel_eps, dou
     uint32_t flags = KC_FLAG_HAS_VALUE;
     int support = top;
     if (n_top == 1) {
-        value = np_mean(xs, top_s, top);  // cu:1174-1178 / 1183-1187
+        value = np_mean(row, top_s, top);  // cu:1174-1178 / 1183-1187
     } else {
-        const TieResult tr = numeric_tie<M>(xs, starts, m, top, rel_eps, abs_eps);
+        const TieResult tr = numeric_tie<M, Row>(row, starts, m, top, rel_eps, abs_eps);
         value = tr.value;
         support = tr.support;
         flags |= KC_FLAG_TIE;
@@ -285,102 +356,114 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
                                                            double rel_eps, double abs_eps, double *__restrict__ out_value,
                                                            uint32_t *__restrict__ out_meta) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    double *scratch = reinterpret_cast<double *>(smem_raw) + threadIdx.x;
-    const double absent = __longlong_as_double((long long)KC_F64_ABSENT_BITS);
+    const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
+    const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
     const int64_t stride = (int64_t)gridDim.x * T;
     for (int64_t g = (int64_t)blockIdx.x * T + threadIdx.x; g < n_groups; g += stride) {
-        double x[NP];
+        uint32_t hi[NP];
         const double *p = vals + g * n;
-        if (n == NP && NP >= 2) {
+        if (n == NP) {
             const int4 *p4 = reinterpret_cast<const int4 *>(p);
 #pragma unroll
             for (int q = 0; q < NP / 2; ++q) {
-                const int4 t = ldg_stream_v4(p4 + q);
-                x[2 * q + 0] = __hiloint2double(t.y, t.x);
-                x[2 * q + 1] = __hiloint2double(t.w, t.z);
+                const int4 t = ldg_nc_v4(p4 + q);
+                hi[2 * q + 0] = (uint32_t)t.y;
+                hi[2 * q + 1] = (uint32_t)t.w;
+                sts_f64(row.addr(2 * q + 0), __hiloint2double(t.y, t.x));
+                sts_f64(row.addr(2 * q + 1), __hiloint2double(t.w, t.z));
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) x[i] = (i < n) ? __ldg(p + i) : absent;
+            for (int i = 0; i < NP; ++i) {
+                const double v = (i < n) ? __ldg(p + i) : __longlong_as_double((long long)KC_F64_ABSENT_BITS);
+                hi[i] = (uint32_t)__double2hiint(v);
+                sts_f64(row.addr(i), v);
+            }
         }
         double v;
         uint32_t m;
-        numeric_core<NP>(x, rel_eps, abs_eps, scratch, T, v, m);
+        numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
         stg_stream_f64(out_value + g, v);
         stg_stream_u32(out_meta + g, m);
     }
 }
 
-// ---------------------------------------------------------------- TMA front-end (n in {4,8,16,32})
+// ---------------------------------------------------------------- TMA front-end (n in {4,8,16,32,64})
 
-// Same ring as vote_tma_kernel; rows are n*8 bytes.  Box rows are at most 128 B wide (the widest TMA
-// swizzle span), so a 256 B row (n = 32) is two box rows.
-template <int N, int TILE, int STAGES>
-__global__ void __launch_bounds__(TILE) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_groups,
-                                                           double rel_eps, double abs_eps, double *__restrict__ out_value,
-                                                           uint32_t *__restrict__ out_meta) {
+// Warp-private pipelines exactly as vote_tma_kernel; rows are n*8 bytes (box rows are at most 128 B wide, the
+// widest TMA swizzle span, so wider rows are several box rows).  The thread's row doubles as its scratch
+// (sorted values are written back in place), so a stage is re-armed only after the warp has finished the tile.
+template <int N, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                 int64_t n_groups, double rel_eps, double abs_eps,
+                                                                 double *__restrict__ out_value,
+                                                                 uint32_t *__restrict__ out_meta) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
-    constexpr uint32_t STAGE_BYTES = TILE * ROW_BYTES;
-    static_assert(STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
+    constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
+    static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    double *scratch = reinterpret_cast<double *>(smem + (size_t)STAGES * STAGE_BYTES) + threadIdx.x;
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
 
-    const int tid = threadIdx.x;
-    const int64_t n_tiles = (n_groups + TILE - 1) / TILE;
-    const int64_t first = blockIdx.x;
-    const int64_t step = gridDim.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t *my_smem = smem + (size_t)warp * STAGES * TILE_BYTES;
+    uint64_t *my_bar = full_bar + warp * STAGES;
+    const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
+
+    const int64_t n_tiles = (n_groups + 31) >> 5;
+    const int64_t first = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t step = (int64_t)gridDim.x * WARPS;
     uint64_t policy = 0;
 
-    if (tid == 0) {
+    if (lane == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&my_bar[s], 1);
         fence_barrier_init();
         policy = policy_evict_first();
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int64_t t = first + (int64_t)s * step;
             if (t < n_tiles) {
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(smem + (size_t)s * STAGE_BYTES, &tmap, 0, (int32_t)(t * TILE * BOX_ROWS_PER_GROUP), &full_bar[s],
+                mbar_arrive_expect_tx(&my_bar[s], TILE_BYTES);
+                tma_load_2d(my_smem + (size_t)s * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP), &my_bar[s],
                             policy);
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 
     int stage = 0;
     uint32_t parity = 0;
     for (int64_t t = first; t < n_tiles; t += step) {
-        mbar_wait(&full_bar[stage], parity);
-        double x[N];
-        const uint32_t base = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint32_t row_off = (uint32_t)tid * ROW_BYTES;
+        mbar_wait(&my_bar[stage], parity);
+        const SwzRow<ROW_BYTES> row{smem_u32(my_smem + (size_t)stage * TILE_BYTES), (uint32_t)lane * ROW_BYTES};
+        uint32_t hi[N];
 #pragma unroll
         for (int q = 0; q < N / 2; ++q) {
-            const int4 v4 = lds_v4(base + Swizzle<ROW_BYTES>::apply(row_off + q * 16));
-            x[2 * q + 0] = __hiloint2double(v4.y, v4.x);
-            x[2 * q + 1] = __hiloint2double(v4.w, v4.z);
+            const int4 v4 = lds_v4(row.addr(2 * q));
+            hi[2 * q + 0] = (uint32_t)v4.y;
+            hi[2 * q + 1] = (uint32_t)v4.w;
         }
-        __syncthreads();
-        if (tid == 0) {
-            const int64_t tn = t + (int64_t)STAGES * step;
-            if (tn < n_tiles) {
-                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &tmap, 0, (int32_t)(tn * TILE * BOX_ROWS_PER_GROUP),
-                            &full_bar[stage], policy);
-            }
-        }
-        const int64_t g = t * TILE + tid;
+        const int64_t g = t * 32 + lane;
+        double v = 0.0;
+        uint32_t m = 0;
         if (g < n_groups) {
-            double v;
-            uint32_t m;
-            numeric_core<N>(x, rel_eps, abs_eps, scratch, TILE, v, m);
+            numeric_core<N, SwzRow<ROW_BYTES>>(hi, row, rel_eps, abs_eps, thr, v, m);
             stg_stream_f64(out_value + g, v);
             stg_stream_u32(out_meta + g, m);
+        }
+        __syncwarp();  // every lane is done with its row (memory ordering among the warp's shared accesses)
+        if (lane == 0) {
+            const int64_t tn = t + (int64_t)STAGES * step;
+            if (tn < n_tiles) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&my_bar[stage], TILE_BYTES);
+                tma_load_2d_dep(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP),
+                                &my_bar[stage], policy, m);
+            }
         }
         if (++stage == STAGES) {
             stage = 0;

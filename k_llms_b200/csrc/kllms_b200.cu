@@ -179,20 +179,20 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
 
 // ---------------------------------------------------------------- K2 launchers
 
-template <int N, int TILE, int STAGES>
+template <int N, int WARPS, int STAGES>
 int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
                        cudaStream_t st) {
-    auto kernel = kc::numeric_tma_kernel<N, TILE, STAGES>;
-    const size_t smem = (size_t)STAGES * TILE * N * 8 + (size_t)N * TILE * 8 + 1024;
+    auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES>;
+    const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
         const int64_t gs = std::min(kMaxGroupsPerLaunch, G - g0);
         CUtensorMap map;
-        int rc = make_row_tensor_map(map, vals + g0 * N, gs, N * 8, TILE);
+        int rc = make_row_tensor_map(map, vals + g0 * N, gs, N * 8, 32);
         if (rc) return rc;
         int grid = 0;
-        rc = persistent_grid(kernel, TILE, smem, (gs + TILE - 1) / TILE, grid);
+        rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
         if (rc) return rc;
-        kernel<<<grid, TILE, smem, st>>>(map, gs, rel_eps, abs_eps, value + g0, meta + g0);
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, gs, rel_eps, abs_eps, value + g0, meta + g0);
         KC_CUDA(cudaGetLastError());
     }
     return KC_OK;
@@ -341,22 +341,19 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
     if (!aligned16(d_vals)) return fail(KC_EINVAL, "kc_numeric_f64: d_vals must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!force_direct())
-    switch (n) {
-        case 4: return launch_numeric_tma<4, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-        case 8: return launch_numeric_tma<8, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-        case 16: return launch_numeric_tma<16, 128, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-        case 32: return launch_numeric_tma<32, 128, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-        default: break;
-    }
+        switch (n) {
+            case 4: return launch_numeric_tma<4, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 8: return launch_numeric_tma<8, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 16: return launch_numeric_tma<16, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 32: return launch_numeric_tma<32, 4, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 64: return launch_numeric_tma<64, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            default: break;
+        }
     if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n == 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n == 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n == 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n == 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n < 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n < 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n < 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n < 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n <= 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n <= 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n <= 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n <= 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
     return launch_numeric_direct<64, 64>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
 }
 

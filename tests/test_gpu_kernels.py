@@ -35,6 +35,10 @@ def random_vals(rng, G, n, style):
         base = rng.choice([12.5, 7.0, 0.125, 3.3], (G, 1))
         t = base
         d = base * rng.choice([1.0, 10.0, 0.1, -1.0, 100.0, 1.0, 1.0], (G, n))
+    elif style == "lowbits":  # values that differ only in low mantissa bits (32-bit sort keys tie; repair path)
+        base = rng.choice([1.0, -1.0, 3.141592653589793, 1e-300, -7e5, 123456.0], (G, 1))
+        t = base
+        d = base * (1.0 + rng.integers(-40, 40, (G, n)) * 2.0 ** rng.choice([-52, -50, -45, -40, -33, -30, -20], (G, 1)))
     else:
         t = rng.uniform(1, 1e4, (G, 1))
         d = rng.uniform(1, 1e4, (G, n))
@@ -71,7 +75,7 @@ def test_vote_matches_oracle(n):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 16, 24, 32, 48, 64])
-@pytest.mark.parametrize("style", ["ints", "near", "pow10", "floats"])
+@pytest.mark.parametrize("style", ["ints", "near", "pow10", "floats", "lowbits"])
 def test_numeric_matches_oracle(n, style):
     torch = _torch()
     from k_llms_b200 import _native as K
