@@ -1,0 +1,234 @@
+"""Host prologue / epilogue of the CUDA consensus path: flatten candidate objects into columnar groups,
+run K1/K2 once over ALL groups of ALL records, rebuild the (value, confidence) trees.
+
+The recursion mirrors the reference dispatcher `consensus_values` (consensus_utils.py:1376-1454, "cu") but
+instead of computing a scalar field it RECORDS it as a group:
+
+  * vote group    (cu:1405-1411 -> voting_consensus cu:936-982): cells = local dictionary codes of the
+    processed values (`sanitize_value(v)` cu:925-933 for strings, `v or False` cu:956 for bools), None = -1
+  * numeric group (cu:1443-1453 -> consensus_as_primitive cu:1098-1219): cells = float(v); None, bools,
+    strings, nan/inf are tagged so the kernel counts them exactly as the reference does (cu:1100-1114)
+
+The shape of the result (dict keys in first-seen order cu:1281-1282, list lengths cu:1332-1341, the
+parent_valid_frac products cu:1418,1433,1444) depends only on the input structure, so it is fixed while
+planning; the GPU fills in the leaves.  Multi-word strings and mixed payloads (the similarity medoid,
+cu:1221-1237) are computed by `k_llms_b200.utils.similarity` on the host (next row).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+
+MAX_CANDIDATES = _native.MAX_CANDIDATES
+SKIPPED_KEY_MARKERS = ("reasoning___", "source___")  # cu:1287
+
+_F64_NONE = np.array([_native.F64_NONE_BITS], dtype=np.uint64).view(np.float64)[0]
+_F64_ABSENT = np.array([_native.F64_ABSENT_BITS], dtype=np.uint64).view(np.float64)[0]
+
+
+# ----------------------------------------------------------------------------- sanitising (cu:925-933)
+
+try:  # the reference needs `unidecode`; it is optional here (ASCII input never reaches it)
+    from unidecode import unidecode as _unidecode  # type: ignore
+except Exception:  # pragma: no cover - depends on the image
+    _unidecode = None
+
+
+def _fold_non_ascii(s: str) -> str:
+    if _unidecode is not None:
+        return _unidecode(s)
+    import unicodedata  # documented deviation: NFKD + drop combining marks when `unidecode` is not installed
+    return "".join(ch for ch in unicodedata.normalize("NFKD", s) if not unicodedata.combining(ch))
+
+
+def sanitize_value(v: Any) -> str:
+    """str() -> lower -> drop spaces -> unidecode -> keep [a-zA-Z0-9]  (cu:925-933)."""
+    s = str(v).lower().replace(" ", "")
+    if not s.isascii():
+        s = _fold_non_ascii(s)
+    return "".join(ch for ch in s if ch.isascii() and ch.isalnum())
+
+
+# ----------------------------------------------------------------------------- plan nodes
+
+
+class _Const:
+    __slots__ = ("value", "conf")
+
+    def __init__(self, value, conf):
+        self.value, self.conf = value, conf
+
+
+class _VoteLeaf:
+    __slots__ = ("row", "cells", "pvf")
+
+    def __init__(self, row: int, cells: list, pvf: float):
+        self.row, self.cells, self.pvf = row, cells, pvf  # cells[i] = value returned when cell i wins
+
+
+class _NumLeaf:
+    __slots__ = ("row", "cells", "pvf")
+
+    def __init__(self, row: int, cells: list, pvf: float):
+        self.row, self.cells, self.pvf = row, cells, pvf
+
+
+class _DictNode:
+    __slots__ = ("children",)
+
+    def __init__(self, children: dict):
+        self.children = children
+
+
+class _ListNode:
+    __slots__ = ("children",)
+
+    def __init__(self, children: list):
+        self.children = children
+
+
+class Plan:
+    """Leaf groups of one or many records, ready for one K1 and one K2 launch."""
+
+    def __init__(self, n: int, allow_none_as_candidate: bool, rel_eps: float, abs_eps: float, host_primitive: Callable):
+        if n > MAX_CANDIDATES:
+            raise NotImplementedError(f"{n} candidates per field: the CUDA path supports at most {MAX_CANDIDATES}")
+        self.n = max(n, 1)
+        self.allow_none = allow_none_as_candidate
+        self.rel_eps, self.abs_eps = rel_eps, abs_eps
+        self.host_primitive = host_primitive
+        self.vote_rows: List[List[int]] = []
+        self.num_rows: List[List[float]] = []
+
+    # -- leaves ---------------------------------------------------------------------------------------
+    def _vote(self, values: Sequence[Any], pvf: float) -> _VoteLeaf:
+        first = next(v for v in values if v is not None)
+        codes: List[int] = []
+        table: dict = {}
+        if isinstance(first, bool):  # cu:954-958: None and every falsy value become False
+            cells = [v or False for v in values]
+            for k in cells:
+                codes.append(table.setdefault(k, len(table)))
+        else:
+            cells = list(values)
+            for v in values:
+                if v is None and not self.allow_none:
+                    codes.append(_native.CODE_NONE)  # cu:964: None does not vote
+                else:
+                    k = None if v is None else sanitize_value(v)
+                    codes.append(table.setdefault(k, len(table)))
+        codes.extend([_native.CODE_ABSENT] * (self.n - len(codes)))
+        self.vote_rows.append(codes)
+        return _VoteLeaf(len(self.vote_rows) - 1, cells, pvf)
+
+    def _numeric(self, values: Sequence[Any], pvf: float) -> _NumLeaf:
+        row: List[float] = []
+        for v in values:
+            if v is None:
+                row.append(_F64_NONE)
+            elif isinstance(v, bool) or not isinstance(v, (int, float)):
+                row.append(math.nan)  # present, counted in `total`, never clustered (cu:1106-1108)
+            else:
+                try:
+                    row.append(float(v))  # non-finite floats are dropped by the kernel (cu:1111)
+                except OverflowError:
+                    row.append(math.nan)  # cu:1113-1114
+        row.extend([_F64_ABSENT] * (self.n - len(row)))
+        self.num_rows.append(row)
+        return _NumLeaf(len(self.num_rows) - 1, list(values), pvf)
+
+    # -- dispatcher (cu:1376-1454) ----------------------------------------------------------------------
+    def add(self, values: Sequence[Any], pvf: float, embed: Optional[Callable]):
+        if not values:
+            return _Const(None, pvf)  # cu:1395-1396
+        live = [v for v in values if v is not None]
+        if not live:
+            return _Const(None, 0.0)  # cu:1401-1402
+        head = live[0]
+        if isinstance(head, (str, bool)) and all(len(str(v).strip().split()) < 3 for v in live):
+            return self._vote(values, pvf)  # cu:1405-1411
+        if isinstance(head, dict):  # cu:1414-1426 -> consensus_dict cu:1269-1306
+            dicts = [v for v in values if isinstance(v, dict)]
+            sub = pvf * (len(dicts) / len(values))
+            keys: dict = {}
+            for d in dicts:
+                for k in d:
+                    keys.setdefault(k, None)
+            children = {}
+            for k in keys:
+                if any(mark in k for mark in SKIPPED_KEY_MARKERS):
+                    continue
+                children[k] = self.add([d.get(k) for d in dicts], sub, embed)
+            return _DictNode(children)
+        if isinstance(head, list):  # cu:1429-1441 -> consensus_list cu:1309-1352
+            lists = [v for v in values if isinstance(v, list)]
+            sub = pvf * (len(lists) / len(values))
+            longest = max(len(l) for l in lists)
+            return _ListNode([self.add([l[i] if i < len(l) else None for l in lists], sub, embed) for i in range(longest)])
+        if embed is None:  # cu:1445-1446
+            raise ValueError("sync_get_openai_embeddings_from_text is required for primitive consensus")
+        try:
+            numeric_like = isinstance(type(head)(), (int, float))  # cu:1099
+        except Exception:
+            numeric_like = False
+        if numeric_like or all(isinstance(v, (int, float)) for v in live):
+            # the kernel applies the None-stripping and len(values) bookkeeping of cu:1444 / cu:1082-1086 itself
+            return self._numeric(values, pvf)
+        sub = pvf * (len(live) / len(values))  # cu:1444
+        if len(live) == 1:
+            return _Const(live[0], sub * (1 / 1))  # cu:1085-1086
+        value, conf = self.host_primitive(live, sub, embed)  # similarity medoid, cu:1221-1237
+        return _Const(value, conf)
+
+    # -- device ----------------------------------------------------------------------------------------
+    def run(self, device=None):
+        """One K1 and one K2 launch over every recorded group; returns numpy result columns."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("k_llms_b200: no CUDA device — the consensus hot path has no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        out = {}
+        if self.vote_rows:
+            codes = torch.from_numpy(np.asarray(self.vote_rows, dtype=np.int32)).to(dev)
+            _, meta = _native.vote(codes, None)
+            out["vote_meta"] = meta.cpu().numpy().view(np.uint32)
+        if self.num_rows:
+            vals = torch.from_numpy(np.asarray(self.num_rows, dtype=np.float64)).to(dev)
+            value, meta = _native.numeric(vals, self.rel_eps, self.abs_eps)
+            out["num_value"] = value.cpu().numpy()
+            out["num_meta"] = meta.cpu().numpy().view(np.uint32)
+        return out
+
+    # -- epilogue --------------------------------------------------------------------------------------
+    @staticmethod
+    def _fields(m: int) -> Tuple[int, int, int, int, int]:
+        return m & 0x3F, (m >> 6) & 0x7F, (m >> 13) & 0x7F, (m >> 20) & 0x7F, (m >> 27) & 0x1F
+
+    def materialise(self, node, res) -> Tuple[Any, Any]:
+        if isinstance(node, _Const):
+            return node.value, node.conf
+        if isinstance(node, _DictNode):
+            val, conf = {}, {}
+            for k, child in node.children.items():
+                val[k], conf[k] = self.materialise(child, res)
+            return val, conf
+        if isinstance(node, _ListNode):
+            pairs = [self.materialise(c, res) for c in node.children]
+            return [p[0] for p in pairs], [p[1] for p in pairs]
+        if isinstance(node, _VoteLeaf):
+            idx, support, _nn, present, flags = self._fields(int(res["vote_meta"][node.row]))
+            if not flags & _native.FLAG_HAS_VALUE:  # cannot happen for a planned vote group (>= 1 voter)
+                return None, (node.pvf if present == 0 else 0.0)
+            return node.cells[idx], round(node.pvf * (support / present), 5)  # cu:971,973,982
+        idx, support, nn, present, flags = self._fields(int(res["num_meta"][node.row]))
+        if flags & _native.FLAG_HAS_VALUE:
+            if flags & _native.FLAG_SINGLE:
+                return node.cells[idx], node.pvf * (1 / present) * (1 / 1)  # cu:1444, cu:1085-1086
+            return float(res["num_value"][node.row]), round(support / nn, 5)  # cu:1176-1178,1217-1219
+        if flags & _native.FLAG_NO_FINITE:
+            return None, node.pvf * (nn / present)  # cu:1444, cu:1115-1116
+        return None, (node.pvf if present == 0 else 0.0)

@@ -217,6 +217,38 @@ __device__ __forceinline__ void sort_keys(uint32_t (&x)[N]) {
     sort_keys_impl<N>(x, std::make_index_sequence<net.count>{});
 }
 
+// `bit` unless d <= p or d <= q or d <= thr (ordered compares: NaN -> not close).  Written in PTX so the three
+// tests stay three predicate-combining DSETPs; left to the optimiser they turn into fmax() expansions.
+__device__ __forceinline__ uint32_t far_bit(double d, double p, double q, double thr, uint32_t bit) {
+    uint32_t r;
+    asm("{\n\t"
+        ".reg .pred c;\n\t"
+        "setp.le.f64 c, %1, %2;\n\t"
+        "setp.le.or.f64 c, %1, %3, c;\n\t"
+        "setp.le.or.f64 c, %1, %4, c;\n\t"
+        "selp.u32 %0, 0, %5, c;\n\t"
+        "}"
+        : "=r"(r)
+        : "d"(d), "d"(p), "d"(q), "d"(thr), "r"(bit));
+    return r;
+}
+
+// Insertion sort of row[0..m) (finite values) — only reached when two distinct values share a truncated key.
+template <typename Row>
+__device__ __noinline__ void repair_sorted_prefix(const Row row, int m) {
+    for (int i = 1; i < m; ++i) {
+        const double v = lds_f64(row.addr(i));
+        int j = i - 1;
+        while (j >= 0) {
+            const double u = lds_f64(row.addr(j));
+            if (!(u > v)) break;
+            sts_f64(row.addr(j + 1), u);
+            --j;
+        }
+        sts_f64(row.addr(j + 1), v);
+    }
+}
+
 // ---------------------------------------------------------------- the core
 
 // hi[i] = high word of raw cell i; the raw cells are also resident in `row` (cell i at row.addr(i)).
@@ -282,41 +314,37 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 #pragma unroll
     for (int k = 0; k < N; ++k) xs[k] = lds_f64(row.addr(key[k] & IDX));
 
+    // Keys drop low mantissa bits: values that differ only there may be swapped.  (NaN compares false; a -inf in
+    // the non-finite tail can raise a false alarm, which only costs the repair call.)
+    bool unsorted = false;
+#pragma unroll
+    for (int k = 1; k < N; ++k) unsorted |= xs[k] < xs[k - 1];
+    // G. park the sorted values in row memory for the data-dependent ranges below
+#pragma unroll
+    for (int k = 0; k < N; ++k) sts_f64(row.addr(k), xs[k]);
+    if (unsorted) {  // rare: insertion-sort the finite prefix in row memory, then reload
+        repair_sorted_prefix<Row>(row, m);
+#pragma unroll
+        for (int k = 0; k < N; ++k) xs[k] = lds_f64(row.addr(k));
+    }
+
     // F. cluster starts: bit k set <=> xs[k] opens a cluster (not close to xs[k-1]); cu:1130-1143.
     //    For a <= b:  |b-a| <= max(abs_eps, rel*max(|a|,|b|,1))
     //            <=>  (b-a) <= rel*b  or  (b-a) <= rel*(-a)  or  (b-a) <= max(abs_eps, rel)
     //    (max(|a|,|b|) = max(-a, b) for a <= b; fl(rel * .) is monotone for rel >= 0, so the product of the max is
-    //    the max of the products.)  `neg` collects the sign bits of the differences: a set bit below position m
-    //    means the truncated keys mis-ordered a pair.
-    M starts;
-    for (;;) {
-        starts = 1;
-        M neg = 0;
+    //    the max of the products.)  Pairs that touch the non-finite tail are masked off below.
+    M starts = 1;
+    {
         double p_prev = __dmul_rn(rel_eps, xs[0]);
 #pragma unroll
         for (int k = 1; k < N; ++k) {
             const double p = __dmul_rn(rel_eps, xs[k]);
             const double d = __dadd_rn(xs[k], -xs[k - 1]);
-            const bool close = (d <= p) || (d <= -p_prev) || (d <= thr);
-            starts |= close ? M(0) : (M(1) << k);
-            neg = (neg << 1) | (M)((uint32_t)__double2hiint(d) >> 31);
+            starts |= (M)far_bit(d, p, -p_prev, thr, 1u << (k & 31)) << (k & 32);
             p_prev = p;
-        }
-        // pairs k >= m involve the non-finite tail: drop them (they were shifted in last)
-        if ((m >= N ? neg : (neg >> (N - m))) == 0) break;
-#pragma unroll
-        for (int k = 1; k < N; ++k) {  // one bubble pass over the finite prefix
-            const bool sw = k < m && xs[k] < xs[k - 1];
-            const double a = xs[k - 1], b = xs[k];
-            xs[k - 1] = sw ? b : a;
-            xs[k] = sw ? a : b;
         }
     }
     if (m < N) starts &= (M(1) << m) - 1;  // m >= 1 here
-
-    // G. park the sorted values in row memory for the data-dependent ranges below
-#pragma unroll
-    for (int k = 0; k < N; ++k) sts_f64(row.addr(k), xs[k]);
 
     // H. largest cluster
     int top = 0, n_top = 0, top_s = 0;
@@ -391,8 +419,10 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
 // ---------------------------------------------------------------- TMA front-end (n in {4,8,16,32,64})
 
 // Warp-private pipelines exactly as vote_tma_kernel; rows are n*8 bytes (box rows are at most 128 B wide, the
-// widest TMA swizzle span, so wider rows are several box rows).  The thread's row doubles as its scratch
-// (sorted values are written back in place), so a stage is re-armed only after the warp has finished the tile.
+// widest TMA swizzle span, so wider rows are several box rows).  The swizzled tile is read ONCE with static,
+// conflict-free LDS.128 and copied to a [cell][thread] plane: the data-dependent accesses of the core would
+// bank-conflict on a row-per-thread layout, while in the plane the bank depends on the thread only.  The stage
+// is handed back to the TMA unit right after that copy.
 template <int N, int WARPS, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,
@@ -401,6 +431,7 @@ __global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_co
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
+    constexpr int T = WARPS * 32;
     static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -410,6 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_co
     const int warp = threadIdx.x >> 5;
     uint8_t *my_smem = smem + (size_t)warp * STAGES * TILE_BYTES;
     uint64_t *my_bar = full_bar + warp * STAGES;
+    const PlaneRow row{smem_u32(smem + (size_t)WARPS * STAGES * TILE_BYTES) + threadIdx.x * 8u, T * 8u};
     const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
 
     const int64_t n_tiles = (n_groups + 31) >> 5;
@@ -439,31 +471,37 @@ __global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_co
     uint32_t parity = 0;
     for (int64_t t = first; t < n_tiles; t += step) {
         mbar_wait(&my_bar[stage], parity);
-        const SwzRow<ROW_BYTES> row{smem_u32(my_smem + (size_t)stage * TILE_BYTES), (uint32_t)lane * ROW_BYTES};
+        const uint32_t base = smem_u32(my_smem + (size_t)stage * TILE_BYTES);
+        const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
         uint32_t hi[N];
+        uint32_t touch = 0;
 #pragma unroll
         for (int q = 0; q < N / 2; ++q) {
-            const int4 v4 = lds_v4(row.addr(2 * q));
+            const int4 v4 = lds_v4(base + Swizzle<ROW_BYTES>::apply(row_off + q * 16));
             hi[2 * q + 0] = (uint32_t)v4.y;
             hi[2 * q + 1] = (uint32_t)v4.w;
+            sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
+            sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
+            touch |= (uint32_t)v4.y | (uint32_t)v4.w;
         }
-        const int64_t g = t * 32 + lane;
-        double v = 0.0;
-        uint32_t m = 0;
-        if (g < n_groups) {
-            numeric_core<N, SwzRow<ROW_BYTES>>(hi, row, rel_eps, abs_eps, thr, v, m);
-            stg_stream_f64(out_value + g, v);
-            stg_stream_u32(out_meta + g, m);
-        }
-        __syncwarp();  // every lane is done with its row (memory ordering among the warp's shared accesses)
+        // the tile is in registers (touch depends on every LDS, and a warp instruction issues only when all lanes'
+        // operands are ready): hand the stage back
         if (lane == 0) {
             const int64_t tn = t + (int64_t)STAGES * step;
             if (tn < n_tiles) {
                 fence_proxy_async();
                 mbar_arrive_expect_tx(&my_bar[stage], TILE_BYTES);
                 tma_load_2d_dep(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP),
-                                &my_bar[stage], policy, m);
+                                &my_bar[stage], policy, touch);
             }
+        }
+        const int64_t g = t * 32 + lane;
+        if (g < n_groups) {
+            double v;
+            uint32_t m;
+            numeric_core<N, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+            stg_stream_f64(out_value + g, v);
+            stg_stream_u32(out_meta + g, m);
         }
         if (++stage == STAGES) {
             stage = 0;

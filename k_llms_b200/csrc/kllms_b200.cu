@@ -183,7 +183,7 @@ template <int N, int WARPS, int STAGES>
 int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
                        cudaStream_t st) {
     auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES>;
-    const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + 1024;
+    const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
         const int64_t gs = std::min(kMaxGroupsPerLaunch, G - g0);
         CUtensorMap map;
