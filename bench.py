@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — consensus records/s on schema S32 (BASELINE.json `metric`), device-resident and end-to-end.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 16] [--records 1000000] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: K1 (vote, 24 fields) + K2 (numeric, 8 fields) over
+`records` records per GPU with n candidates (BASELINE configs[1]: 1M x 32 fields, n=16); at N > 1 every rank owns
+its own 1M-record shard (weak scaling, configs[4]) and a step ends with the NCCL all-gather that reassembles the
+packed output columns on every rank.  One JSON line on stdout (rank 0).
+
+value      whole-job records/s, inputs resident in HBM, CUDA events, max over ranks, barrier + synchronize on both sides.
+e2e        same metric through the C-ABI call with HOST buffers (kc_consensus_host: pinned host -> H2D -> K1/K2 -> D2H),
+           timed with CUDA events inside the call (copies included), max over ranks.
+roofline   dominant kernel: algorithmic bytes / its mean launch time, over MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the oracle port of the reference's per-record Python path on the host cores (bounded sample).
+--impl reference  times that CPU path alone (the reference is pure Python and cannot travel to the GPU box; the oracle
+           port restates it — DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "consensus records/sec at n=16 (1M x 32-field); achieved HBM GB/s vs peak"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+
+def _cpu_worker(args):
+    """Build `count` S32 records as Python candidate dicts (untimed), then time the per-record consensus loop."""
+    seed, count, n = args
+    import numpy as np  # noqa: F401
+    from k_llms_b200 import synth
+    from oracle import consensus_py as O
+    codes, none_code, vals = synth.s32_numpy(count, n, seed)
+    vocab = ["alpha", "Bravo", "charlie", "DELTA", "echo", "foxtrot", "golf", "Hotel"]
+    variants = [lambda w: w, lambda w: w.upper(), lambda w: w.lower() + "!", lambda w: " " + w]
+    records = []
+    for r in range(count):
+        cands = []
+        for c in range(n):
+            d = {}
+            for f in range(16):
+                k = int(codes[r, f, c])
+                d[f"f{f:02d}"] = None if k < 0 else variants[(r + c + f) % 4](vocab[k])
+            for f in range(16, 24):
+                k = int(codes[r, f, c])
+                d[f"f{f:02d}"] = None if k < 0 else bool(k)
+            for f in range(8):
+                v = vals[r, f, c]
+                d[f"f{24 + f:02d}"] = None if v != v else (int(v) if f < 6 else float(v))
+            cands.append(d)
+        records.append(cands)
+    embed = lambda texts: [[0.0] for _ in texts]  # noqa: E731
+    t0 = time.perf_counter()
+    for cands in records:
+        O.consensus(cands, embed=embed)
+    return count, time.perf_counter() - t0
+
+
+def cpu_baseline(n: int, per_worker: int, cores: int):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(20260921 + 2 + 1000 * i, per_worker, n) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return {"value": total / busy, "unit": "records/s", "cores": cores, "kind": "port",
+            "sample": f"{total} records ({per_worker}/core) of the S32 n={n} workload as Python candidate dicts, "
+                      f"oracle/consensus_py.consensus per record, multiprocessing.Pool({cores}); slowest worker {busy:.1f}s, "
+                      f"wall incl. record construction {wall:.1f}s",
+            "cpu_model": _cpu_model()}
+
+
+def _cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_worker = max(200, int(args.cpu_records_per_core))
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):  # each step = one bounded sample; keep the whole arm within minutes
+        base = cpu_baseline(args.n, per_worker, cores)
+        vals.append(base["value"])
+    value = statistics.median(vals)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "records/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * (per_worker * cores) / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "python objects (float64 / str)", "data": "synthetic",
+            "config": {"workload": f"S32 schema (16 str-enum + 8 bool + 6 int + 2 float fields), n={args.n}, "
+                                   f"{per_worker * cores} records per step (bounded sample of the 1M-record batch)"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is pure Python and absent on the GPU box; this arm runs the oracle port of its per-record path"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.time(), parts))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0: float, t1: float):
+        win = [p for t, p in self.samples if t0 <= t <= t1]
+        scope = "timed region"
+        if len(win) < 3:
+            win, scope = [p for _, p in self.samples], "whole run (timed region shorter than the sampling period)"
+        if not win:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "nvidia-smi unavailable"}
+        sm = [float(p[0]) for p in win if p[0].replace(".", "").isdigit()]
+        reasons = set()
+        for p in win:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(win[0][1]) if win[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(win), "window": scope}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    from k_llms_b200 import _native as K
+    from k_llms_b200 import synth
+    from k_llms_b200.distributed import OutputLayout, ShardedConsensus
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N, n = args.records, args.n
+    codes, none_code, vals = synth.s32_torch(N, n, 20260921 + 2 + rank, dev)  # §8d: seed 20260921 + cfg, per-rank shard
+    c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
+    layout = OutputLayout(N, 24, 8)
+    sharded = ShardedConsensus(layout, dev)
+    win, vmeta, value, nmeta = layout.views(sharded.my_slot())
+    lib = K.load()
+    K.check(lib.kc_set_device(local_rank))
+    stream = torch.cuda.current_stream()
+    sp = int(stream.cuda_stream)
+
+    def compute(_views=None):
+        K.check(lib.kc_vote_i32(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
+        K.check(lib.kc_numeric_f64(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
+
+    def step(gather=True):
+        sharded.step(compute, gather=gather)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # --- timed: exactly K steps; per-kernel events on the launching stream ride along
+    K_steps = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K_steps)]
+    t_wall0 = time.time()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(K_steps):
+        ev[i][0].record()
+        K.check(lib.kc_vote_i32(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
+        ev[i][1].record()
+        K.check(lib.kc_numeric_f64(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
+        ev[i][2].record()
+        if dist is not None:
+            dist.all_gather_into_tensor(sharded.gathered.view(-1), sharded.my_slot())
+        ev[i][3].record()
+    stop.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(start.elapsed_time(stop))
+    ms_step = ms_total / K_steps
+    vote_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    num_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+    gather_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev) if dist is not None else 0.0
+    compute_ms = max_over_ranks(vote_ms + num_ms)
+    value_rps = world * N / (ms_step / 1e3)
+
+    # --- end to end through the host-buffer C-ABI entry (rank-local shard, pinned host memory)
+    e2e = None
+    if not args.no_e2e:
+        h_codes = K.pinned_empty((N, 24, n), np.int32)
+        h_vals = K.pinned_empty((N, 8, n), np.float64)
+        h_codes[...] = codes.cpu().numpy()
+        h_vals[...] = vals.cpu().numpy()
+        h_none = none_code.cpu().numpy()
+        out = {"win_code": K.pinned_empty((N, 24), np.int32), "vote_meta": K.pinned_empty((N, 24), np.uint32),
+               "value": K.pinned_empty((N, 8), np.float64), "num_meta": K.pinned_empty((N, 8), np.uint32)}
+        e2e_steps = max(1, min(K_steps, args.e2e_steps))
+        for _ in range(2):
+            K.consensus_host(h_codes, h_none, h_vals, device=local_rank, out=out)
+        barrier()
+        ms = []
+        for _ in range(e2e_steps):
+            r = K.consensus_host(h_codes, h_none, h_vals, device=local_rank, out=out)
+            ms.append(r["device_ms"])
+        barrier()
+        e2e_ms = max_over_ranks(statistics.mean(ms))
+        # the host-buffer path must agree with the device-resident one
+        assert np.array_equal(out["win_code"].reshape(-1), win.cpu().numpy()), "e2e result differs from device-resident result"
+        assert np.array_equal(out["value"].reshape(-1).view(np.uint64), value.cpu().numpy().view(np.uint64))
+        e2e = {"value": world * N / (e2e_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(h_codes.nbytes + h_vals.nbytes),
+               "d2h_bytes_per_step": int(sum(a.nbytes for a in out.values())), "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "path": "kc_consensus_host (C ABI): pinned host buffers -> chunked H2D -> K1/K2 -> D2H on 3 streams, per rank"}
+
+    clocks = None
+    if sampler is not None:
+        sampler.stop()
+        clocks = sampler.summary(t_wall0, t_wall1)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bytes_vote, bytes_num = N * 24 * (4 * n + 8), N * 8 * (8 * n + 12)
+        kernels = {"vote": {"ms": vote_ms, "bytes": bytes_vote}, "numeric": {"ms": num_ms, "bytes": bytes_num}}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        ach = kernels[dom]["bytes"] / (kernels[dom]["ms"] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": {"vote": f"kc::vote_*_kernel<{n}>", "numeric": f"kc::numeric_*_kernel<{n}>"}[dom],
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
+                    "all_kernels": {k: {"ms_per_launch": v["ms"], "achieved_GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9,
+                                        "frac": v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak} for k, v in kernels.items()},
+                    "step_frac": (bytes_vote + bytes_num) / ((vote_ms + num_ms) / 1e3) / 1e9 / peak}
+        base = None
+        if world == 1 and not args.no_cpu:
+            base = cpu_baseline(n, int(args.cpu_records_per_core), os.cpu_count() or 1)
+        line = {"metric": METRIC, "value": value_rps, "unit": "records/s", "n_gpus": world, "steps": K_steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 codes / f64 values",
+                "data": "synthetic",
+                "config": {"workload": f"S32: {N} records/GPU x 32 fields (16 str-enum + 8 bool as int32 codes, 6 int + 2 float as f64), "
+                                       f"n={n}, p_agree=0.8, p_none=0.05; {world} GPU(s), {world * N} records total",
+                           "l2": f"inputs are {(bytes_vote + bytes_num) / 1e9:.2f} GB per step per GPU, > 126 MB L2: no flush needed",
+                           "step": "K1 vote + K2 numeric" + (" + NCCL all-gather of packed outputs" if world > 1 else ""),
+                           "parallelism": f"records sharded {world}-way, all-gather reassembly" if world > 1 else "single GPU"},
+                "e2e": e2e, "gpu_launches": 2 * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
+                "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
+                                 "all_gather_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world)}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=16)
+    ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-records-per-core", type=int, default=1500)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: spawn torchrun ourselves when asked for N GPUs outside a launcher
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

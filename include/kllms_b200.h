@@ -123,16 +123,6 @@ int kc_confidence_f64(const uint32_t *d_meta, int64_t n_groups, int32_t numeric,
 int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_t n_seq, float *d_sum, void *stream);
 
 /*
- * K3b — likelihood-weighted vote: class weight = sum over its cells of exp(seq_logprob[record][c])
- * (fp32, ascending candidate order), winner = heaviest class, ties -> first seen.
- *   d_codes int32[n_records*n_fields][n] as kc_vote_i32; d_seq_logprob float32[n_records][n]
- *   d_weight float32[n_groups]: winning class weight / total voting weight (0 if none)
- */
-int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int64_t n_records, int32_t n_fields,
-                         int32_t n, const int32_t *d_none_code, int32_t *d_win_code, uint32_t *d_meta, float *d_weight,
-                         void *stream);
-
-/*
  * End-to-end entry with HOST buffers (the call a k_llms binding makes for a batch of records of one
  * flat schema): chunked, double-buffered H2D -> K1/K2 -> D2H on internal streams of `device`.
  * Either half may be absent (n_vote_fields == 0 or n_num_fields == 0).  Blocks until results are in
@@ -140,7 +130,8 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
  */
 int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
                       int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
-                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device);
+                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device,
+                      float *device_ms /* optional: CUDA-event time of the whole call (copies + kernels), NULL to skip */);
 
 void *kc_host_alloc(uint64_t bytes); /* page-locked host memory, NULL on failure */
 void kc_host_free(void *p);

@@ -58,7 +58,7 @@ def load() -> ctypes.CDLL:
     lib.kc_numeric_f64.argtypes = [vp, i64, i32, f64, f64, vp, vp, vp]
     lib.kc_confidence_f64.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.kc_logprob_sum_f32.argtypes = [vp, vp, i64, vp, vp]
-    lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int]
+    lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int, vp]
     lib.kc_host_alloc.argtypes = [c.c_uint64]
     lib.kc_host_alloc.restype = vp
     lib.kc_host_free.argtypes = [vp]
@@ -174,9 +174,10 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
         none_code = np.ascontiguousarray(none_code, dtype=np.int32)
         assert none_code.size == Fv
     p = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
+    ms = ctypes.c_float(0.0)
     check(lib.kc_consensus_host(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
-                                p(value), p(nmeta), device))
-    return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta}
+                                p(value), p(nmeta), device, ctypes.addressof(ms)))
+    return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
 
 
 def pinned_empty(shape, dtype):

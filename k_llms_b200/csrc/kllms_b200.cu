@@ -84,7 +84,7 @@ int get_encode_fn(EncodeTiledFn &fn) {
 // rows of `row_bytes` (a power of two in [32, 512]) viewed as a 2-D int32 tensor whose inner extent is
 // min(row_bytes, 128) bytes — the widest span a TMA swizzle mode covers; box = TILE groups.
 int make_row_tensor_map(CUtensorMap &map, const void *base, int64_t n_groups, int row_bytes, int tile_groups) {
-    EncodeTiledFn encode;
+    EncodeTiledFn encode = nullptr;
     int rc = get_encode_fn(encode);
     if (rc) return rc;
     const int inner_bytes = std::min(row_bytes, 128);
@@ -404,7 +404,9 @@ void kc_host_free(void *p) {
 
 int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
                       int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
-                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device) {
+                      int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device,
+                      float *device_ms) {
+    if (device_ms) *device_ms = 0.0f;
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_consensus_host: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_records < 0 || n_vote_fields < 0 || n_num_fields < 0) return fail(KC_EINVAL, "kc_consensus_host: negative size");
     if (device < 0 || device >= 16) return fail(KC_EINVAL, "kc_consensus_host: device %d out of range", device);
@@ -454,6 +456,16 @@ int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32
             return finish(fail(KC_ECUDA, "none_code upload failed: %s", cudaGetErrorString(cudaGetLastError())));
         d_none = cx.none.as<int32_t>();
     }
+    // device-side timing of the whole call: start on stream 0 before the first copy; stop on stream 0 after it has
+    // waited for the other streams' last work
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join[HostCtx::kStreams] = {};
+    if (device_ms) {
+        cudaEventCreate(&ev_start);
+        cudaEventCreate(&ev_stop);
+        for (auto &e : ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventRecord(ev_start, cx.streams[0]);
+        for (int s = 1; s < HostCtx::kStreams; ++s) cudaStreamWaitEvent(cx.streams[s], ev_start, 0);  // nothing starts earlier
+    }
     int64_t r0 = 0;
     for (int it = 0; r0 < n_records && !rc; ++it, r0 += chunk) {
         const int s = it % HostCtx::kStreams;
@@ -484,9 +496,22 @@ int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32
         }
         if (e != cudaSuccess) rc = fail(KC_ECUDA, "kc_consensus_host: %s", cudaGetErrorString(e));
     }
+    if (device_ms) {
+        for (int s = 1; s < HostCtx::kStreams; ++s) {
+            cudaEventRecord(ev_join[s], cx.streams[s]);
+            cudaStreamWaitEvent(cx.streams[0], ev_join[s], 0);
+        }
+        cudaEventRecord(ev_stop, cx.streams[0]);
+    }
     for (auto &s : cx.streams) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess && !rc) rc = fail(KC_ECUDA, "kc_consensus_host sync: %s", cudaGetErrorString(e));
+    }
+    if (device_ms) {
+        if (!rc) cudaEventElapsedTime(device_ms, ev_start, ev_stop);
+        cudaEventDestroy(ev_start);
+        cudaEventDestroy(ev_stop);
+        for (auto &e : ev_join) cudaEventDestroy(e);
     }
     return finish(rc);
 }

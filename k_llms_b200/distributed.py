@@ -1,0 +1,76 @@
+"""Multi-GPU sharding of a batch of independent records: one process per GPU, contiguous record
+ranges, no collective during compute, ONE all-gather of the packed output columns to reassemble the batch.
+
+Output packing per rank (bytes, in this order): win_code int32[G_v] | vote_meta uint32[G_v] | value f64[G_x] |
+num_meta uint32[G_x], padded to 16 B — so a single NCCL all-gather moves everything, and the kernels write
+straight into the rank's slot of the gathered buffer (in-place all-gather, send = recv + rank*chunk).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+
+def shard_range(n_records: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split: the first (n % world) ranks get one extra record."""
+    base, extra = divmod(n_records, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+@dataclass
+class OutputLayout:
+    n_records: int  # records per rank (equal on every rank: pad the batch if needed)
+    n_vote_fields: int
+    n_num_fields: int
+
+    @property
+    def gv(self) -> int:
+        return self.n_records * self.n_vote_fields
+
+    @property
+    def gx(self) -> int:
+        return self.n_records * self.n_num_fields
+
+    @property
+    def nbytes(self) -> int:
+        raw = self.gv * 8 + self.gx * 12
+        return (raw + 15) // 16 * 16
+
+    def views(self, buf):
+        """Typed views into one rank's slot (a 1-D uint8 tensor of nbytes)."""
+        import torch
+        o = 0
+        win = buf[o:o + self.gv * 4].view(torch.int32); o += self.gv * 4
+        vmeta = buf[o:o + self.gv * 4].view(torch.int32); o += self.gv * 4
+        value = buf[o:o + self.gx * 8].view(torch.float64); o += self.gx * 8
+        nmeta = buf[o:o + self.gx * 4].view(torch.int32)
+        return win, vmeta, value, nmeta
+
+
+class ShardedConsensus:
+    """Per-rank consensus + all-gather reassembly.  `compute(slot_views)` fills the rank's slot; on the GPU it is the
+    two kernel launches, in the gloo/CPU tests it is a stand-in."""
+
+    def __init__(self, layout: OutputLayout, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.layout, self.device = layout, device
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.gathered = torch.empty((self.world, layout.nbytes), dtype=torch.uint8, device=device)
+
+    def my_slot(self):
+        return self.gathered[self.rank]
+
+    def step(self, compute: Callable, gather: bool = True):
+        compute(self.layout.views(self.my_slot()))
+        if gather and self.dist and self.world > 1:
+            # in-place: the input is this rank's slice of the output buffer
+            self.dist.all_gather_into_tensor(self.gathered.view(-1), self.my_slot(), group=self.group)
+        return self.gathered
+
+    def rank_views(self, r: int):
+        return self.layout.views(self.gathered[r])

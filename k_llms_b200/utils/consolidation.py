@@ -1,0 +1,179 @@
+"""Consolidation glue: n choices -> align -> consensus -> choices[0] = consensus, choices[1..n] = originals.
+
+Same four entry points, signatures and result shape as reference k_llms/utils/consolidation.py:63-493; the four
+near-identical bodies there share one implementation here.  The consensus itself runs on the GPU
+(`consensus_utils.consensus_values`); JSON parsing and object rebuilding stay host Python.
+"""
+from __future__ import annotations
+
+import json
+from typing import Any, List, Optional, Union
+
+from openai.types.chat import ChatCompletion, ChatCompletionMessage, ParsedChatCompletion
+from openai.types.chat.chat_completion import Choice
+from openai.types.chat.parsed_chat_completion import ParsedChatCompletionMessage, ParsedChoice
+from pydantic import BaseModel
+
+from ..types.completions import KLLMsChatCompletion
+from ..types.parsed import KLLMsParsedChatCompletion
+from .consensus_utils import (
+    ASYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    SYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    ConsensusSettings,
+    async_consensus_values,
+    async_recursive_list_alignments,
+    consensus_values,
+    recursive_list_alignments,
+)
+
+
+def _safe_parse_content(content: str) -> dict:
+    """JSON if it parses, else {"text": content} (reference consolidation.py:25-38)."""
+    try:
+        return json.loads(content)
+    except (json.JSONDecodeError, TypeError):
+        return {"text": content}
+
+
+def _format_consensus_content(consensus_content: Any) -> str:
+    """Inverse of _safe_parse_content for the consensus message (reference consolidation.py:41-60)."""
+    if consensus_content is None:
+        return ""
+    if isinstance(consensus_content, dict) and len(consensus_content) == 1 and isinstance(consensus_content.get("text"), str):
+        return consensus_content["text"]
+    return json.dumps(consensus_content)
+
+
+def _contents_of(choices) -> List[dict]:
+    return [_safe_parse_content(c.message.content) for c in choices if c.message.content]
+
+
+def _consensus_sync(contents, settings, embed, client):
+    if len(contents) >= 2:  # reference consolidation.py:96-104
+        aligned, _ = recursive_list_alignments(contents, settings.string_similarity_method, embed, client, settings.min_support_ratio)
+        contents = [(d if isinstance(d, dict) else {}) for d in aligned]
+    return consensus_values(contents, settings, embed, client=client)
+
+
+async def _consensus_async(contents, settings, embed, client):
+    if len(contents) >= 2:
+        aligned, _ = await async_recursive_list_alignments(contents, settings.string_similarity_method, embed, client,
+                                                           settings.min_support_ratio)
+        contents = [(d if isinstance(d, dict) else {}) for d in aligned]
+    return await async_consensus_values(contents, settings, embed, client=client)
+
+
+def _assemble_plain(base: ChatCompletion, heads, consensus_content, likelihoods) -> KLLMsChatCompletion:
+    """heads: the choices whose message/finish_reason/logprobs become choices[1..]; heads[0] lends its
+    function_call / tool_calls / refusal / finish_reason / logprobs to the consensus choice."""
+    first = heads[0] if heads else None
+    message = ChatCompletionMessage(
+        role="assistant",
+        content=_format_consensus_content(consensus_content),
+        function_call=first.message.function_call if first else None,
+        tool_calls=first.message.tool_calls if first else None,
+        refusal=first.message.refusal if first else None,
+    )
+    consensus_choice = Choice(finish_reason=first.finish_reason if first else "stop", index=0, message=message,
+                              logprobs=first.logprobs if first else None)
+    originals = [Choice(finish_reason=c.finish_reason, index=i + 1, message=c.message, logprobs=c.logprobs)
+                 for i, c in enumerate(heads)]
+    return KLLMsChatCompletion.model_validate(
+        {**base.model_dump(), "choices": [consensus_choice] + originals, "likelihoods": likelihoods, "usage": base.usage})
+
+
+def consolidate_chat_completions(
+    completions: Union[List[ChatCompletion], ChatCompletion],
+    get_openai_embeddings_from_text: SYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    client: Any,
+    consensus_settings: ConsensusSettings = ConsensusSettings(),
+) -> KLLMsChatCompletion:
+    """One ChatCompletion with n choices, or a list of completions (reference consolidation.py:63-216)."""
+    if isinstance(completions, ChatCompletion):
+        completion = completions
+        assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
+        if len(completion.choices) == 1:
+            return KLLMsChatCompletion.model_validate(completion.model_dump())
+        content, likelihoods = _consensus_sync(_contents_of(completion.choices), consensus_settings,
+                                               get_openai_embeddings_from_text, client)
+        return _assemble_plain(completion, list(completion.choices), content, likelihoods)
+    completion_list = completions
+    assert len(completion_list) > 0, "Cannot consolidate empty list of completions"
+    if len(completion_list) == 1:
+        return KLLMsChatCompletion.model_validate(completion_list[0].model_dump())
+    firsts = [c.choices[0] for c in completion_list if c.choices]
+    content, likelihoods = _consensus_sync(_contents_of(firsts), consensus_settings, get_openai_embeddings_from_text, client)
+    return _assemble_plain(completion_list[0], firsts, content, likelihoods)
+
+
+async def async_consolidate_chat_completions(
+    completion: ChatCompletion,
+    async_get_openai_embeddings_from_text: ASYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    client: Any,
+    consensus_settings: ConsensusSettings = ConsensusSettings(),
+) -> KLLMsChatCompletion:
+    """Reference consolidation.py:219-303."""
+    assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
+    if len(completion.choices) == 1:
+        return KLLMsChatCompletion.model_validate(completion.model_dump())
+    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                  async_get_openai_embeddings_from_text, client)
+    return _assemble_plain(completion, list(completion.choices), content, likelihoods)
+
+
+def _assemble_parsed(completion: ParsedChatCompletion, consensus_content, likelihoods, response_format, keep_usage: bool):
+    parsed = None
+    if response_format and consensus_content is not None:
+        try:  # validation failures are swallowed: parsed stays None (reference consolidation.py:358-365)
+            if isinstance(response_format, type) and issubclass(response_format, BaseModel):
+                parsed = response_format.model_validate(consensus_content)
+        except Exception:
+            parsed = None
+    first = completion.choices[0]
+    message = ParsedChatCompletionMessage(
+        role="assistant",
+        content=_format_consensus_content(consensus_content),
+        function_call=first.message.function_call,
+        tool_calls=first.message.tool_calls,
+        refusal=first.message.refusal,
+        parsed=parsed,
+    )
+    consensus_choice = ParsedChoice(finish_reason=first.finish_reason, index=0, message=message, logprobs=first.logprobs)
+    originals = [ParsedChoice(finish_reason=c.finish_reason, index=i + 1, message=c.message, logprobs=c.logprobs)
+                 for i, c in enumerate(completion.choices)]
+    payload = {**completion.model_dump(), "choices": [consensus_choice] + originals, "likelihoods": likelihoods}
+    if keep_usage:
+        payload["usage"] = completion.usage
+    return KLLMsParsedChatCompletion.model_validate(payload)
+
+
+def consolidate_parsed_chat_completions(
+    completion: ParsedChatCompletion,
+    get_openai_embeddings_from_text: SYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    client: Any,
+    consensus_settings: ConsensusSettings = ConsensusSettings(),
+    response_format: Optional[type] = None,
+) -> KLLMsParsedChatCompletion:
+    """Reference consolidation.py:306-399."""
+    assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
+    if len(completion.choices) == 1:
+        return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
+    content, likelihoods = _consensus_sync(_contents_of(completion.choices), consensus_settings,
+                                           get_openai_embeddings_from_text, client)
+    return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=True)
+
+
+async def async_consolidate_parsed_chat_completions(
+    completion: ParsedChatCompletion,
+    async_get_openai_embeddings_from_text: ASYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
+    client: Any,
+    consensus_settings: ConsensusSettings = ConsensusSettings(),
+    response_format: Optional[type] = None,
+) -> KLLMsParsedChatCompletion:
+    """Reference consolidation.py:402-493 (the reference's async twin does not re-attach `usage`; model_dump keeps it)."""
+    assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
+    if len(completion.choices) == 1:
+        return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
+    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                  async_get_openai_embeddings_from_text, client)
+    return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=False)
