@@ -42,9 +42,10 @@ extern "C" {
  * `v or False` for bool groups, cu:956); equal code <=> equal processed value. */
 
 /* ---- numeric cells (float64) ---- */
-#define KC_F64_NONE_BITS 0x7FF8C0DE00000001ULL   /* quiet NaN payload: None */
-#define KC_F64_ABSENT_BITS 0x7FF8C0DE00000002ULL /* quiet NaN payload: absent (see KC_CODE_ABSENT) */
-/* any OTHER non-finite value means "present, non-None, but not a finite number" (bool, str, nan,
+#define KC_F64_NONE_BITS 0x7FF8C0DE00000000ULL   /* quiet NaN whose HIGH 32 bits are 0x7FF8C0DE: None */
+#define KC_F64_ABSENT_BITS 0x7FF8C0DF00000000ULL /* quiet NaN whose HIGH 32 bits are 0x7FF8C0DF: absent (see KC_CODE_ABSENT) */
+/* Only the high word is examined (the low word is ignored), so a cell is tagged by one 32-bit compare.
+ * any OTHER non-finite value means "present, non-None, but not a finite number" (bool, str, nan,
  * inf inside a numeric group): counted in the total, excluded from clustering (cu:1105-1114). */
 
 /* ---- packed per-group result word ("meta") ----

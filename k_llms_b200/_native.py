@@ -18,8 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libkllms_b200.so")
 KC_OK, KC_EINVAL, KC_ECUDA, KC_ENODEV, KC_ENOMEM = 0, -1, -2, -3, -4
 MAX_CANDIDATES = 64
 CODE_NONE, CODE_ABSENT = -1, -2
-F64_NONE_BITS = 0x7FF8C0DE00000001
-F64_ABSENT_BITS = 0x7FF8C0DE00000002
+F64_NONE_BITS = 0x7FF8C0DE00000000
+F64_ABSENT_BITS = 0x7FF8C0DF00000000
 FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 
 EXPORTS = (

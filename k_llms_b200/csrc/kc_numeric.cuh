@@ -24,13 +24,14 @@
 
 namespace kc {
 
-constexpr uint32_t kTagHi = (uint32_t)(KC_F64_NONE_BITS >> 32);
-constexpr uint32_t kNoneLo = (uint32_t)(KC_F64_NONE_BITS & 0xFFFFFFFFu);
-constexpr uint32_t kAbsentLo = (uint32_t)(KC_F64_ABSENT_BITS & 0xFFFFFFFFu);
+constexpr uint32_t kNoneHi = (uint32_t)(KC_F64_NONE_BITS >> 32);      // only the HIGH word of a cell tags it
+constexpr uint32_t kAbsentHi = (uint32_t)(KC_F64_ABSENT_BITS >> 32);
 constexpr uint32_t kKeyNonFinite = 0xFFE00000u;  // keys >= this belong to non-finite cells
 
 __device__ __forceinline__ int ffs_m(uint32_t m) { return __ffs((int)m); }
 __device__ __forceinline__ int ffs_m(uint64_t m) { return __ffsll((long long)m); }
+__device__ __forceinline__ int clz_m(uint32_t m) { return __clz((int)m); }
+__device__ __forceinline__ int clz_m(uint64_t m) { return __clzll((long long)m); }
 
 // 10.0**k for k = -6..6 exactly as CPython computes it (correctly rounded decimal literals): cu:1156-1157.
 __device__ __constant__ double kPow10[13] = {1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6};
@@ -261,34 +262,26 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     constexpr uint32_t IDX = N - 1;
     const double qnan = __longlong_as_double(0x7FF8000000000000LL);
 
-    // A. keys + non-finite mask
+    // A. keys, non-finite mask, and the None / absent census.  t is a bijective, order-preserving image of the
+    //    high word; the two tags are adjacent high words, so u = t - T_NONE is 0 (None) or 1 (absent) for tagged
+    //    cells and one packed counter (tagged << 16 | absent) takes a single predicated add per cell.
+    constexpr uint32_t T_NONE = (kNoneHi ^ 0x80000000u) - 0x00100000u;
+    static_assert(kAbsentHi == kNoneHi + 1, "tags must be adjacent high words");
     uint32_t key[N];
     M nf = 0;
+    uint32_t census = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t s = (uint32_t)((int32_t)hi[i] >> 31);
         const uint32_t t = (hi[i] ^ (s | 0x80000000u)) - 0x00100000u;  // monotone in the value; non-finite -> >= 0xFFE00000
         key[i] = (t & ~IDX) | (uint32_t)i;
         nf |= (t >= kKeyNonFinite) ? (M(1) << i) : M(0);
+        const uint32_t u = t - T_NONE;
+        census += (u < 2u) ? (u + 0x10000u) : 0u;
     }
-    const int m = N - popc_m(nf);  // finite cells (cu:1105-1114)
-
-    // B. classify the non-finite cells: None / absent / "present but not a number"
-    int present = N, nn = N, skip_idx = 0;
-    for (M w = nf; w;) {
-        const int i = ffs_m(w) - 1;
-        w &= w - 1;
-        const uint2 c = lds_u32x2(row.addr(i));  // .x = low word, .y = high word
-        const bool tagged = c.y == kTagHi;
-        if (tagged && c.x == kAbsentLo) {
-            --present;
-            --nn;
-        } else if (tagged && c.x == kNoneLo) {
-            --nn;
-        } else {
-            skip_idx = i;
-        }
-    }
+    const int m = N - popc_m(nf);                                // finite cells (cu:1105-1114)
+    const int present = N - (int)(census & 0xFFFFu);             // len(values) at this node
+    const int nn = N - (int)(census >> 16);                      // non-None cells == `total` (cu:1100)
     if (nn == 0) {
         value = qnan;
         meta = pack_meta(0, 0, 0, present, 0);
@@ -297,7 +290,17 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     if (nn == 1) {  // cu:1085-1086: the original object, whatever it is
         M fin = ~nf;
         if constexpr (N < 32) fin &= (M(1) << N) - 1;
-        const int idx = m == 1 ? ffs_m(fin) - 1 : skip_idx;
+        int idx;
+        if (m == 1) {
+            idx = ffs_m(fin) - 1;
+        } else {  // the lone non-None cell is itself not a finite number: find the non-finite cell that is not a tag
+            idx = 0;
+            for (M w = nf; w; w &= w - 1) {
+                const int i = ffs_m(w) - 1;
+                const uint32_t h = lds_u32x2(row.addr(i)).y;
+                if (h != kNoneHi && h != kAbsentHi) idx = i;
+            }
+        }
         value = lds_f64(row.addr(idx));
         meta = pack_meta(idx, 1, 1, present, KC_FLAG_HAS_VALUE | KC_FLAG_SINGLE);
         return;
@@ -348,7 +351,19 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 
     // H. largest cluster
     int top = 0, n_top = 0, top_s = 0;
-    {
+    {   // a cluster holding a strict majority of the finite values must contain the middle one: test that first
+        const int c = m >> 1;
+        const M below = starts & ((M(2) << c) - 1);          // starts at or below c (bit 0 is always set)
+        const int s0 = (int)(sizeof(M) * 8 - 1) - clz_m(below);
+        const M above = c + 1 < (int)(sizeof(M) * 8) ? (starts >> (c + 1)) : M(0);
+        const int e0 = above ? c + ffs_m(above) : m;
+        if (2 * (e0 - s0) > m) {
+            top = e0 - s0;
+            n_top = 1;
+            top_s = s0;
+        }
+    }
+    if (n_top == 0) {
         M sk = starts;
         while (sk) {
             const int s = ffs_m(sk) - 1;

@@ -9,8 +9,8 @@ from __future__ import annotations
 
 import numpy as np
 
-F64_NONE = np.array([0x7FF8C0DE00000001], dtype=np.uint64).view(np.float64)[0]
-F64_ABSENT = np.array([0x7FF8C0DE00000002], dtype=np.uint64).view(np.float64)[0]
+F64_NONE = np.array([0x7FF8C0DE00000000], dtype=np.uint64).view(np.float64)[0]
+F64_ABSENT = np.array([0x7FF8C0DF00000000], dtype=np.uint64).view(np.float64)[0]
 
 S32_VOTE_FIELDS = 24  # 16 string-enum + 8 bool
 S32_NUM_FIELDS = 8    # 6 int + 2 float
@@ -54,7 +54,7 @@ def s32_torch(n_records: int, n: int, seed: int, device, p_agree: float = 0.8, p
     codes = torch.empty((N, 24, n), dtype=torch.int32, device=device)
     vals = torch.empty((N, 8, n), dtype=torch.float64, device=device)
     step = 1 << 16
-    none_val = torch.tensor([0x7FF8C0DE00000001], dtype=torch.int64, device=device).view(torch.float64)
+    none_val = torch.tensor([0x7FF8C0DE00000000], dtype=torch.int64, device=device).view(torch.float64)
     for r0 in range(0, N, step):
         r1 = min(N, r0 + step)
         m = r1 - r0

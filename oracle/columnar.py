@@ -15,8 +15,8 @@ _SO = os.path.join(_HERE, "_build", "libkllms_oracle.so")
 
 NONE_CODE = -1
 ABSENT_CODE = -2
-F64_NONE_BITS = 0x7FF8C0DE00000001
-F64_ABSENT_BITS = 0x7FF8C0DE00000002
+F64_NONE_BITS = 0x7FF8C0DE00000000
+F64_ABSENT_BITS = 0x7FF8C0DF00000000
 F64_NONE = np.array([F64_NONE_BITS], dtype=np.uint64).view(np.float64)[0]
 F64_ABSENT = np.array([F64_ABSENT_BITS], dtype=np.uint64).view(np.float64)[0]
 

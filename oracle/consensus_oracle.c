@@ -134,9 +134,9 @@ void ko_numeric_f64(const double *vals, int64_t n_groups, int32_t n, double rel_
             double v = vals[g * n + c];
             uint64_t bits;
             memcpy(&bits, &v, 8);
-            if (bits == KC_F64_ABSENT_BITS) continue;
+            if ((bits >> 32) == (KC_F64_ABSENT_BITS >> 32)) continue; /* the high word tags a cell */
             present++;
-            if (bits == KC_F64_NONE_BITS) continue;
+            if ((bits >> 32) == (KC_F64_NONE_BITS >> 32)) continue;
             if (nn == 0) first_nn = c;
             nn++;
             if (isfinite(v)) xs[m++] = v; /* cu:1105-1114 */
