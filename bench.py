@@ -205,51 +205,66 @@ def run_gpu_arm(args):
     codes, none_code, vals = synth.s32_torch(N, n, 20260921 + 2 + rank, dev)  # §8d: seed 20260921 + cfg, per-rank shard
     c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
     layout = OutputLayout(N, 24, 8)
-    sharded = ShardedConsensus(layout, dev)
-    win, vmeta, value, nmeta = layout.views(sharded.my_slot())
+    chunks = args.chunks if world > 1 else 1  # pipeline depth of compute vs all-gather (meaningless on one GPU)
+    while N % chunks:
+        chunks -= 1
+    sharded = ShardedConsensus(layout, dev, chunks=chunks)
+    R = N // chunks
     lib = K.load()
     K.check(lib.kc_set_device(local_rank))
-    stream = torch.cuda.current_stream()
-    sp = int(stream.cuda_stream)
+    sp = int(torch.cuda.current_stream().cuda_stream)
+    kernel_events = []  # (start, mid, end) per chunk launch, only while timing
 
-    def compute(_views=None):
-        K.check(lib.kc_vote_i32(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
-        K.check(lib.kc_numeric_f64(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
+    def compute(c, views):
+        win, vmeta, value, nmeta = views
+        cc, vv = c2[c * R * 24:(c + 1) * R * 24], v2[c * R * 8:(c + 1) * R * 8]
+        if kernel_events is not None and timing[0]:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+        K.check(lib.kc_vote_i32(cc.data_ptr(), R * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
+        if timing[0]:
+            e[1].record()
+        K.check(lib.kc_numeric_f64(vv.data_ptr(), R * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
+        if timing[0]:
+            e[2].record()
+            kernel_events.append(e)
 
-    def step(gather=True):
-        sharded.step(compute, gather=gather)
-
+    timing = [False]
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
-        step()
+        sharded.step(compute)
     barrier()
 
     # --- timed: exactly K steps; per-kernel events on the launching stream ride along
     K_steps = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K_steps)]
+    timing[0] = True
     t_wall0 = time.time()
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(K_steps):
-        ev[i][0].record()
-        K.check(lib.kc_vote_i32(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
-        ev[i][1].record()
-        K.check(lib.kc_numeric_f64(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
-        ev[i][2].record()
-        if dist is not None:
-            dist.all_gather_into_tensor(sharded.gathered.view(-1), sharded.my_slot())
-        ev[i][3].record()
+        sharded.step(compute)
     stop.record()
     barrier()
     t_wall1 = time.time()
+    timing[0] = False
     ms_total = max_over_ranks(start.elapsed_time(stop))
     ms_step = ms_total / K_steps
-    vote_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
-    num_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
-    gather_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev) if dist is not None else 0.0
+    vote_ms = sum(e[0].elapsed_time(e[1]) for e in kernel_events) / K_steps   # per step (all chunks)
+    num_ms = sum(e[1].elapsed_time(e[2]) for e in kernel_events) / K_steps
     compute_ms = max_over_ranks(vote_ms + num_ms)
     value_rps = world * N / (ms_step / 1e3)
+    gather_ms = 0.0
+    if dist is not None:  # the all-gather alone (no compute to hide behind), for the record
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            sharded.step(lambda c, v: None)
+        g1.record()
+        barrier()
+        gather_ms = max_over_ranks(g0.elapsed_time(g1) / 5)
+    win, vmeta, value, nmeta = [torch.cat([sharded.my_views(c)[k] for c in range(chunks)]) for k in range(4)]
 
     # --- end to end through the host-buffer C-ABI entry (rank-local shard, pinned host memory)
     e2e = None
@@ -286,7 +301,9 @@ def run_gpu_arm(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         bytes_vote, bytes_num = N * 24 * (4 * n + 8), N * 8 * (8 * n + 12)
-        kernels = {"vote": {"ms": vote_ms, "bytes": bytes_vote}, "numeric": {"ms": num_ms, "bytes": bytes_num}}
+        # per-launch figures: a step is `chunks` launches of each kernel
+        kernels = {"vote": {"ms": vote_ms / chunks, "bytes": bytes_vote // chunks},
+                   "numeric": {"ms": num_ms / chunks, "bytes": bytes_num // chunks}}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         ach = kernels[dom]["bytes"] / (kernels[dom]["ms"] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"vote": f"kc::vote_*_kernel<{n}>", "numeric": f"kc::numeric_*_kernel<{n}>"}[dom],
@@ -306,9 +323,10 @@ def run_gpu_arm(args):
                            "l2": f"inputs are {(bytes_vote + bytes_num) / 1e9:.2f} GB per step per GPU, > 126 MB L2: no flush needed",
                            "step": "K1 vote + K2 numeric" + (" + NCCL all-gather of packed outputs" if world > 1 else ""),
                            "parallelism": f"records sharded {world}-way, all-gather reassembly" if world > 1 else "single GPU"},
-                "e2e": e2e, "gpu_launches": 2 * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
+                "e2e": e2e, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
-                                 "all_gather_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world)}}
+                                 "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
+                                 "pipeline_chunks": chunks}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -323,6 +341,7 @@ def main():
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--chunks", type=int, default=8, help="N>1: pipeline chunks of compute vs all-gather")
     ap.add_argument("--cpu-records-per-core", type=int, default=1500)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

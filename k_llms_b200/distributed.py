@@ -49,28 +49,39 @@ class OutputLayout:
 
 
 class ShardedConsensus:
-    """Per-rank consensus + all-gather reassembly.  `compute(slot_views)` fills the rank's slot; on the GPU it is the
-    two kernel launches, in the gloo/CPU tests it is a stand-in."""
+    """Per-rank consensus + all-gather reassembly, pipelined: the shard is cut into `chunks` record ranges; the packed
+    outputs of chunk c are all-gathered (asynchronously, on NCCL's stream) while chunk c+1 is being computed.
 
-    def __init__(self, layout: OutputLayout, device, group=None):
+    gathered[c][r] holds rank r's outputs for its chunk c.  `compute(c, views)` fills this rank's slot of chunk c; on
+    the GPU it is the two kernel launches, in the gloo/CPU tests it is a stand-in."""
+
+    def __init__(self, layout: OutputLayout, device, group=None, chunks: int = 1):
         import torch
         import torch.distributed as dist
-        self.layout, self.device = layout, device
+        assert layout.n_records % chunks == 0, "records per rank must divide into equal chunks"
+        self.layout, self.device, self.chunks = layout, device, chunks
+        self.chunk_layout = OutputLayout(layout.n_records // chunks, layout.n_vote_fields, layout.n_num_fields)
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
-        self.gathered = torch.empty((self.world, layout.nbytes), dtype=torch.uint8, device=device)
+        self.gathered = torch.empty((chunks, self.world, self.chunk_layout.nbytes), dtype=torch.uint8, device=device)
 
-    def my_slot(self):
-        return self.gathered[self.rank]
+    def my_views(self, c: int = 0):
+        return self.chunk_layout.views(self.gathered[c, self.rank])
+
+    def rank_views(self, r: int, c: int = 0):
+        return self.chunk_layout.views(self.gathered[c, r])
 
     def step(self, compute: Callable, gather: bool = True):
-        compute(self.layout.views(self.my_slot()))
-        if gather and self.dist and self.world > 1:
-            # in-place: the input is this rank's slice of the output buffer
-            self.dist.all_gather_into_tensor(self.gathered.view(-1), self.my_slot(), group=self.group)
+        works = []
+        for c in range(self.chunks):
+            compute(c, self.my_views(c))
+            if gather and self.dist and self.world > 1:
+                # in-place all-gather (input = this rank's slice of the output); async: it waits for the kernels just
+                # enqueued on the current stream, then runs on the communicator's stream beside the next chunk's kernels
+                works.append(self.dist.all_gather_into_tensor(self.gathered[c].view(-1), self.gathered[c, self.rank],
+                                                              group=self.group, async_op=True))
+        for w in works:
+            w.wait()
         return self.gathered
-
-    def rank_views(self, r: int):
-        return self.layout.views(self.gathered[r])

@@ -28,19 +28,22 @@ def _worker(rank, world, port, n_records, n, out_dir):
         per = n_records // world
         assert hi - lo == per
         layout = OutputLayout(per, 24, 8)
-        sharded = ShardedConsensus(layout, torch.device("cpu"))
+        chunks = 4
+        sharded = ShardedConsensus(layout, torch.device("cpu"), chunks=chunks)
+        step = per // chunks
 
-        def compute(views):
+        def compute(c, views):
             win, vmeta, value, nmeta = views
-            w, m = OC.vote(codes[lo:hi].reshape(-1, n), none_code)
-            v, nm = OC.numeric(vals[lo:hi].reshape(-1, n))
+            a, b = lo + c * step, lo + (c + 1) * step
+            w, m = OC.vote(codes[a:b].reshape(-1, n), none_code)
+            v, nm = OC.numeric(vals[a:b].reshape(-1, n))
             win.copy_(torch.from_numpy(w))
             vmeta.copy_(torch.from_numpy(m.view(np.int32)))
             value.copy_(torch.from_numpy(v))
             nmeta.copy_(torch.from_numpy(nm.view(np.int32)))
 
         sharded.step(compute)
-        parts = [sharded.rank_views(r) for r in range(world)]
+        parts = [sharded.rank_views(r, c) for r in range(world) for c in range(chunks)]  # global record order
         full = [torch.cat([p[k] for p in parts]).numpy() for k in range(4)]
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), win=full[0], vmeta=full[1], value=full[2], nmeta=full[3])
     finally:
