@@ -49,6 +49,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// Variants taking 32-bit shared-space addresses (no generic->shared conversion in the loop).
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "KC_WAITA_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KC_DONEA_%=;\n\t"
+        "bra KC_WAITA_%=;\n\t"
+        "KC_DONEA_%=:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMA: 2-D tiled tensor load, global -> swizzled smem
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
@@ -82,6 +103,20 @@ __device__ __forceinline__ void tma_load_2d_dep(void *smem_dst, const CUtensorMa
         "[%4], %5;\n\t"
         "}\n" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy), "r"(dep)
+        : "memory");
+}
+
+// 32-bit shared-space addresses + dependency register.
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar,
+                                              uint64_t policy, uint32_t dep) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 kc_dep;\n\t"
+        "mov.b32 kc_dep, %6;\n\t"
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+        "[%4], %5;\n\t"
+        "}\n" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "l"(policy), "r"(dep)
         : "memory");
 }
 

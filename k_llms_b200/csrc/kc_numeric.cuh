@@ -394,7 +394,7 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 
 // ---------------------------------------------------------------- direct front-end (any n <= NP)
 
-template <int NP, int T>
+template <int NP, int T, bool PREFETCH>
 __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restrict__ vals, int64_t n_groups, int n,
                                                            double rel_eps, double abs_eps, double *__restrict__ out_value,
                                                            uint32_t *__restrict__ out_meta) {
@@ -402,32 +402,64 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
     const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
     const int64_t stride = (int64_t)gridDim.x * T;
-    for (int64_t g = (int64_t)blockIdx.x * T + threadIdx.x; g < n_groups; g += stride) {
+    int64_t g = (int64_t)blockIdx.x * T + threadIdx.x;
+    int4 cur[NP / 2 > 0 ? NP / 2 : 1];
+    if constexpr (PREFETCH) {  // requires n == NP
+        if (g < n_groups) {
+            const int4 *p4 = reinterpret_cast<const int4 *>(vals + g * NP);
+#pragma unroll
+            for (int q = 0; q < NP / 2; ++q) cur[q] = ldg_nc_v4(p4 + q);
+        }
+    }
+    for (; g < n_groups; g += stride) {
         uint32_t hi[NP];
-        const double *p = vals + g * n;
-        if (n == NP) {
-            const int4 *p4 = reinterpret_cast<const int4 *>(p);
+        if constexpr (PREFETCH) {
+            int4 nxt[NP / 2];
+            if (g + stride < n_groups) {  // request the next row before working on this one
+                const int4 *p4 = reinterpret_cast<const int4 *>(vals + (g + stride) * NP);
+#pragma unroll
+                for (int q = 0; q < NP / 2; ++q) nxt[q] = ldg_nc_v4(p4 + q);
+            }
 #pragma unroll
             for (int q = 0; q < NP / 2; ++q) {
-                const int4 t = ldg_nc_v4(p4 + q);
-                hi[2 * q + 0] = (uint32_t)t.y;
-                hi[2 * q + 1] = (uint32_t)t.w;
-                sts_f64(row.addr(2 * q + 0), __hiloint2double(t.y, t.x));
-                sts_f64(row.addr(2 * q + 1), __hiloint2double(t.w, t.z));
+                hi[2 * q + 0] = (uint32_t)cur[q].y;
+                hi[2 * q + 1] = (uint32_t)cur[q].w;
+                sts_f64(row.addr(2 * q + 0), __hiloint2double(cur[q].y, cur[q].x));
+                sts_f64(row.addr(2 * q + 1), __hiloint2double(cur[q].w, cur[q].z));
             }
-        } else {
+            double v;
+            uint32_t m;
+            numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+            stg_stream_f64(out_value + g, v);
+            stg_stream_u32(out_meta + g, m);
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const double v = (i < n) ? __ldg(p + i) : __longlong_as_double((long long)KC_F64_ABSENT_BITS);
-                hi[i] = (uint32_t)__double2hiint(v);
-                sts_f64(row.addr(i), v);
+            for (int q = 0; q < NP / 2; ++q) cur[q] = nxt[q];
+        } else {
+            const double *p = vals + g * n;
+            if (n == NP) {
+                const int4 *p4 = reinterpret_cast<const int4 *>(p);
+#pragma unroll
+                for (int q = 0; q < NP / 2; ++q) {
+                    const int4 t = ldg_nc_v4(p4 + q);
+                    hi[2 * q + 0] = (uint32_t)t.y;
+                    hi[2 * q + 1] = (uint32_t)t.w;
+                    sts_f64(row.addr(2 * q + 0), __hiloint2double(t.y, t.x));
+                    sts_f64(row.addr(2 * q + 1), __hiloint2double(t.w, t.z));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const double v = (i < n) ? __ldg(p + i) : __longlong_as_double((long long)KC_F64_ABSENT_BITS);
+                    hi[i] = (uint32_t)__double2hiint(v);
+                    sts_f64(row.addr(i), v);
+                }
             }
+            double v;
+            uint32_t m;
+            numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+            stg_stream_f64(out_value + g, v);
+            stg_stream_u32(out_meta + g, m);
         }
-        double v;
-        uint32_t m;
-        numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-        stg_stream_f64(out_value + g, v);
-        stg_stream_u32(out_meta + g, m);
     }
 }
 
@@ -501,13 +533,15 @@ __global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_co
         }
         // the tile is in registers (touch depends on every LDS, and a warp instruction issues only when all lanes'
         // operands are ready): hand the stage back
+        // 0 on lane 0, but only the hardware knows (shuffle result): a true register dependency of the copy on the
+        // loaded data that neither nvvm nor ptxas can schedule away
+        const uint32_t order = __shfl_sync(0xFFFFFFFFu, touch, 0) ^ touch;
         if (lane == 0) {
             const int64_t tn = t + (int64_t)STAGES * step;
             if (tn < n_tiles) {
-                fence_proxy_async();
                 mbar_arrive_expect_tx(&my_bar[stage], TILE_BYTES);
-                tma_load_2d_dep(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP),
-                                &my_bar[stage], policy, touch);
+                tma_load_2d(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0,
+                            (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP) + (int32_t)order, &my_bar[stage], policy);
             }
         }
         const int64_t g = t * 32 + lane;

@@ -174,7 +174,36 @@ struct FieldMap {
 // ---------------------------------------------------------------- direct front-end
 
 // NP = n rounded up to a power of two (compile-time register array); cells beyond n are padded absent.
-template <int NP, bool VEC, bool HAS_NC>
+template <int NP, bool VEC>
+__device__ __forceinline__ void load_row(const int32_t *__restrict__ codes, int64_t g, int n, int32_t (&raw)[NP]) {
+    if constexpr (VEC) {  // n == NP, rows are 16-byte aligned multiples of 16 bytes
+        if constexpr (NP >= 4) {
+            const int4 *p = reinterpret_cast<const int4 *>(codes + g * NP);
+#pragma unroll
+            for (int q = 0; q < NP / 4; ++q) {
+                const int4 t = ldg_nc_v4(p + q);
+                raw[4 * q + 0] = t.x;
+                raw[4 * q + 1] = t.y;
+                raw[4 * q + 2] = t.z;
+                raw[4 * q + 3] = t.w;
+            }
+        } else if constexpr (NP == 2) {
+            const int2 t = __ldg(reinterpret_cast<const int2 *>(codes + g * 2));
+            raw[0] = t.x;
+            raw[1] = t.y;
+        } else {
+            raw[0] = __ldg(codes + g);
+        }
+    } else {
+        const int32_t *p = codes + g * n;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) raw[i] = (i < n) ? __ldg(p + i) : KC_CODE_ABSENT;
+    }
+}
+
+// Grid-stride, one group per thread per iteration.  With PREFETCH the next iteration's row is requested before
+// the current one is processed (twice the bytes in flight per thread, for ~NP more registers).
+template <int NP, bool VEC, bool HAS_NC, bool PREFETCH>
 __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restrict__ codes, int64_t n_groups, int n,
                                                           FieldMap fm, int32_t *__restrict__ win,
                                                           uint32_t *__restrict__ meta) {
@@ -185,30 +214,14 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
         f = (uint32_t)(g % fm.n_fields);
         fstep = (uint32_t)(stride % fm.n_fields);
     }
+    int32_t raw[NP];
+    if (PREFETCH && g < n_groups) load_row<NP, VEC>(codes, g, n, raw);
     for (; g < n_groups; g += stride) {
-        int32_t raw[NP];
-        if constexpr (VEC) {  // n == NP, rows are 16-byte aligned multiples of 16 bytes
-            if constexpr (NP >= 4) {
-                const int4 *p = reinterpret_cast<const int4 *>(codes + g * NP);
-#pragma unroll
-                for (int q = 0; q < NP / 4; ++q) {
-                    const int4 t = ldg_nc_v4(p + q);
-                    raw[4 * q + 0] = t.x;
-                    raw[4 * q + 1] = t.y;
-                    raw[4 * q + 2] = t.z;
-                    raw[4 * q + 3] = t.w;
-                }
-            } else if constexpr (NP == 2) {
-                const int2 t = __ldg(reinterpret_cast<const int2 *>(codes + g * 2));
-                raw[0] = t.x;
-                raw[1] = t.y;
-            } else {
-                raw[0] = __ldg(codes + g);
-            }
+        int32_t nxt[NP];
+        if constexpr (PREFETCH) {
+            if (g + stride < n_groups) load_row<NP, VEC>(codes, g + stride, n, nxt);
         } else {
-            const int32_t *p = codes + g * n;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) raw[i] = (i < n) ? __ldg(p + i) : KC_CODE_ABSENT;
+            load_row<NP, VEC>(codes, g, n, raw);
         }
         int32_t nc = KC_CODE_NONE;
         if constexpr (HAS_NC) {
@@ -221,6 +234,10 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
         vote_core<NP, HAS_NC>(raw, row_min<NP>(raw), nc, w, m);
         stg_stream_u32(win + g, (uint32_t)w);
         stg_stream_u32(meta + g, m);
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) raw[i] = nxt[i];
+        }
     }
 }
 
@@ -239,61 +256,67 @@ struct Swizzle {  // TMA swizzle mode for a row of ROW_BYTES (rows wider than 12
 // stage for the tile STAGES ahead before the warp computes.  Out-of-range rows of the last tile are
 // zero-filled by TMA and never stored.  There is no __syncthreads(): warps never wait for each other.
 template <int N, int WARPS, int STAGES, bool HAS_NC>
-__global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_groups,
+__global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t n_groups,
                                                               FieldMap fm, int32_t *__restrict__ win,
                                                               uint32_t *__restrict__ meta) {
     constexpr int ROW_BYTES = N * 4;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
     static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
+    static_assert((STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    uint8_t *my_smem = smem + (size_t)warp * STAGES * TILE_BYTES;
-    uint64_t *my_bar = full_bar + warp * STAGES;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);  // warp-uniform by construction
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t my_smem = smem_base + warp * (STAGES * TILE_BYTES);
+    const uint32_t my_bar = smem_u32(full_bar) + warp * (STAGES * 8);
 
-    const int64_t n_tiles = (n_groups + 31) >> 5;
-    const int64_t first = (int64_t)blockIdx.x * WARPS + warp;
-    const int64_t step = (int64_t)gridDim.x * WARPS;
+    // all indices are 32-bit: the launcher cuts the input into slabs of < 2^28 groups
+    const uint32_t n_tiles = (n_groups + 31u) >> 5;
+    const uint32_t first = blockIdx.x * WARPS + warp;
+    const uint32_t step = gridDim.x * WARPS;
     uint64_t policy = 0;
 
     if (lane == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&my_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init_a(my_bar + s * 8, 1);
         fence_barrier_init();
         policy = policy_evict_first();
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            const int64_t t = first + (int64_t)s * step;
+            const uint32_t t = first + (uint32_t)s * step;
             if (t < n_tiles) {
-                mbar_arrive_expect_tx(&my_bar[s], TILE_BYTES);
-                tma_load_2d(my_smem + (size_t)s * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP), &my_bar[s],
-                            policy);
+                mbar_arrive_expect_tx_a(my_bar + s * 8, TILE_BYTES);
+                tma_load_2d_a(my_smem + s * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP), my_bar + s * 8, policy, 0);
             }
         }
     }
     __syncwarp();
 
-    uint32_t f0 = 0, fstep = 0;  // field of the tile's first group, advanced without 64-bit division
+    uint32_t f0 = 0, fstep = 0;  // field of the tile's first group, advanced without division
     if constexpr (HAS_NC) {
-        f0 = (uint32_t)((first * 32) % fm.n_fields);
-        fstep = (uint32_t)((step * 32) % fm.n_fields);
+        f0 = (uint32_t)(((uint64_t)first * 32) % fm.n_fields);
+        fstep = (uint32_t)(((uint64_t)step * 32) % fm.n_fields);
     }
+    // this lane's four (or N/4) 16-byte pieces inside a tile: constant across tiles
+    uint32_t piece[N / 4];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) piece[q] = Swizzle<ROW_BYTES>::apply(lane * ROW_BYTES + q * 16);
 
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int64_t t = first; t < n_tiles; t += step) {
-        mbar_wait(&my_bar[stage], parity);
+    uint32_t it = 0;
+    for (uint32_t t = first; t < n_tiles; t += step, ++it) {
+        const uint32_t stage = it & (STAGES - 1);
+        const uint32_t parity = (it / STAGES) & 1;
+        const uint32_t bar = my_bar + stage * 8;
+        const uint32_t tile = my_smem + stage * TILE_BYTES;
+        mbar_wait_a(bar, parity);
         int32_t raw[N];
-        const uint32_t base = smem_u32(my_smem + (size_t)stage * TILE_BYTES);
-        const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) {
-            const int4 v4 = lds_v4(base + Swizzle<ROW_BYTES>::apply(row_off + q * 16));
+            const int4 v4 = lds_v4(tile + piece[q]);
             raw[4 * q + 0] = v4.x;
             raw[4 * q + 1] = v4.y;
             raw[4 * q + 2] = v4.z;
@@ -303,16 +326,16 @@ __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_const
         // loaded words, a warp instruction issues only when its operands are ready in every lane, and the
         // re-arm below consumes `lo`, so it is ordered after the warp's LDS have returned.
         const int32_t lo = row_min<N>(raw);
-        if (lane == 0) {
-            const int64_t tn = t + (int64_t)STAGES * step;
-            if (tn < n_tiles) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&my_bar[stage], TILE_BYTES);
-                tma_load_2d_dep(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP),
-                                &my_bar[stage], policy, (uint32_t)lo);
-            }
+        // `order` is 0 on lane 0 but only the hardware knows it (a shuffle result): folding it into the TMA
+        // coordinate gives the copy a true register dependency on the loaded data, which neither nvvm nor ptxas
+        // can schedule away.
+        const uint32_t order = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, 0) ^ (uint32_t)lo;
+        const uint32_t tn = t + STAGES * step;
+        if (lane == 0 && tn < n_tiles) {
+            mbar_arrive_expect_tx_a(bar, TILE_BYTES);
+            tma_load_2d_a(tile, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP + order), bar, policy, 0);
         }
-        const int64_t g = t * 32 + lane;
+        const uint32_t g = t * 32 + lane;
         int32_t nc = KC_CODE_NONE;
         if constexpr (HAS_NC) {
             nc = __ldg(fm.none_code + fm.mod_small(f0 + lane));
@@ -325,10 +348,6 @@ __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_const
             vote_core<N, HAS_NC>(raw, lo, nc, w, m);
             stg_stream_u32(win + g, (uint32_t)w);
             stg_stream_u32(meta + g, m);
-        }
-        if (++stage == STAGES) {
-            stage = 0;
-            parity ^= 1;
         }
     }
 }

@@ -144,7 +144,7 @@ int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code
         int grid = 0;
         rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
         if (rc) return rc;
-        kernel<<<grid, WARPS * 32, smem, st>>>(map, gs, make_field_map(none_code, n_fields), win + g0, meta + g0);
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, (uint32_t)gs, make_field_map(none_code, n_fields), win + g0, meta + g0);
         KC_CUDA(cudaGetLastError());
     }
     return KC_OK;
@@ -169,10 +169,18 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     const int64_t blocks = (G + threads - 1) / threads;
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * 8);
     const kc::FieldMap fm = make_field_map(none_code, n_fields);
-    if (none_code)
-        kc::vote_direct_kernel<NP, VEC, true><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
-    else
-        kc::vote_direct_kernel<NP, VEC, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+    static const bool prefetch = [] { const char *e = getenv("KC_VOTE_PREFETCH"); return !e || e[0] != '0'; }();
+    constexpr bool kCanPrefetch = VEC && NP >= 4 && NP <= 16;
+    if (kCanPrefetch && prefetch) {
+        if (none_code)
+            kc::vote_direct_kernel<NP, VEC, true, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+        else
+            kc::vote_direct_kernel<NP, VEC, false, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+    } else if (none_code) {
+        kc::vote_direct_kernel<NP, VEC, true, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+    } else {
+        kc::vote_direct_kernel<NP, VEC, false, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+    }
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }
@@ -204,22 +212,36 @@ int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, 
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
-    auto kernel = kc::numeric_direct_kernel<NP, T>;
+    static const bool prefetch_env = [] { const char *e = getenv("KC_NUM_PREFETCH"); return !e || e[0] != '0'; }();
+    const bool prefetch = prefetch_env && n == NP && NP >= 4 && NP <= 16;
     const size_t smem = (size_t)NP * T * 8;
-    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
-    if (per_sm < 1) return fail(KC_ECUDA, "numeric_direct_kernel<%d> does not fit", NP);
-    const int64_t blocks = (G + T - 1) / T;
-    const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * per_sm);
-    kernel<<<grid, T, smem, st>>>(vals, G, n, rel_eps, abs_eps, value, meta);
-    KC_CUDA(cudaGetLastError());
-    return KC_OK;
+    auto launch = [&](auto kernel) -> int {
+        KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+        if (per_sm < 1) return fail(KC_ECUDA, "numeric_direct_kernel<%d> does not fit", NP);
+        const int64_t blocks = (G + T - 1) / T;
+        const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * per_sm);
+        kernel<<<grid, T, smem, st>>>(vals, G, n, rel_eps, abs_eps, value, meta);
+        KC_CUDA(cudaGetLastError());
+        return KC_OK;
+    };
+    if constexpr (NP >= 4 && NP <= 16) {
+        if (prefetch) return launch(kc::numeric_direct_kernel<NP, T, true>);
+    }
+    return launch(kc::numeric_direct_kernel<NP, T, false>);
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Debug / A-B knob: KC_FORCE_DIRECT=1 routes every n through the direct (non-TMA) front-ends.
+// A-B knobs: KC_FORCE_DIRECT=1 / KC_FORCE_TMA=1 route every n through one family of front-ends.
+bool force_tma() {
+    static const bool v = [] {
+        const char *e = getenv("KC_FORCE_TMA");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
 bool force_direct() {
     static const bool v = [] {
         const char *e = getenv("KC_FORCE_DIRECT");
@@ -305,8 +327,12 @@ int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32
     if (!d_none_code) n_fields = 1;
     if (!aligned16(d_codes)) return fail(KC_EINVAL, "kc_vote_i32: d_codes must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (force_direct()) {
+    // measured on B200 (profiles/README.md): the direct front-end wins up to n = 16, the TMA pipeline from n = 32
+    if (force_direct() || (!force_tma() && n <= 16)) {
         switch (n) {
+            case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
             case 8: return launch_vote_direct<8, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
             case 16: return launch_vote_direct<16, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
             case 32: return launch_vote_direct<32, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
@@ -319,9 +345,17 @@ int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32
         case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
         case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
         case 8: return launch_vote_tma<8, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 16: return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 32: return launch_vote_tma<32, 8, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 64: return launch_vote_tma<64, 4, 3>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 16: {
+            static const int cfg = [] { const char *e = getenv("KC_VOTE_CFG"); return e ? atoi(e) : 0; }();
+            if (cfg == 1) return launch_vote_tma<16, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            if (cfg == 2) return launch_vote_tma<16, 4, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            if (cfg == 3) return launch_vote_tma<16, 16, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            if (cfg == 4) return launch_vote_tma<16, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            if (cfg == 5) return launch_vote_tma<16, 8, 8>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        }
+        case 32: return launch_vote_tma<32, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 64: return launch_vote_tma<64, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
         default: break;
     }
     if (n < 4) return launch_vote_direct<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
@@ -340,11 +374,20 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
     if (!d_vals || !d_value || !d_meta) return fail(KC_EINVAL, "kc_numeric_f64: NULL buffer");
     if (!aligned16(d_vals)) return fail(KC_EINVAL, "kc_numeric_f64: d_vals must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!force_direct())
+    // measured on B200: TMA pipeline wins at n = 16 and 32; direct at n <= 8 (tiles too small to prefetch far enough)
+    // and at n = 64 (register pressure)
+    if (!force_direct() && (force_tma() || n == 16 || n == 32))
         switch (n) {
             case 4: return launch_numeric_tma<4, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             case 8: return launch_numeric_tma<8, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-            case 16: return launch_numeric_tma<16, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 16: {
+                static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
+                if (cfg == 1) return launch_numeric_tma<16, 4, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 4) return launch_numeric_tma<16, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                return launch_numeric_tma<16, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            }
             case 32: return launch_numeric_tma<32, 4, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             case 64: return launch_numeric_tma<64, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             default: break;
