@@ -470,8 +470,8 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
 // conflict-free LDS.128 and copied to a [cell][thread] plane: the data-dependent accesses of the core would
 // bank-conflict on a row-per-thread layout, while in the plane the bank depends on the thread only.  The stage
 // is handed back to the TMA unit right after that copy.
-template <int N, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+template <int N, int WARPS, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,
                                                                  double *__restrict__ out_value,
                                                                  uint32_t *__restrict__ out_meta) {

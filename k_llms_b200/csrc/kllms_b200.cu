@@ -187,10 +187,10 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
 
 // ---------------------------------------------------------------- K2 launchers
 
-template <int N, int WARPS, int STAGES>
+template <int N, int WARPS, int STAGES, int MIN_CTAS = 1>
 int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
                        cudaStream_t st) {
-    auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES>;
+    auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES, MIN_CTAS>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
         const int64_t gs = std::min(kMaxGroupsPerLaunch, G - g0);
@@ -378,18 +378,24 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
     // and at n = 64 (register pressure)
     if (!force_direct() && (force_tma() || n == 16 || n == 32))
         switch (n) {
-            case 4: return launch_numeric_tma<4, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-            case 8: return launch_numeric_tma<8, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 4: return launch_numeric_tma<4, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             case 16: {
                 static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
-                if (cfg == 1) return launch_numeric_tma<16, 4, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 1) return launch_numeric_tma<16, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
                 if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
                 if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
                 if (cfg == 4) return launch_numeric_tma<16, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                return launch_numeric_tma<16, 8, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 5) return launch_numeric_tma<16, 4, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 6) return launch_numeric_tma<16, 8, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 7) return launch_numeric_tma<16, 2, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 8) return launch_numeric_tma<16, 8, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 9) return launch_numeric_tma<16, 4, 1, 8>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 10) return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             }
-            case 32: return launch_numeric_tma<32, 4, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-            case 64: return launch_numeric_tma<64, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 32: return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
             default: break;
         }
     if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
