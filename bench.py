@@ -34,6 +34,16 @@ METRIC = "consensus records/sec at n=16 (1M x 32-field); achieved HBM GB/s vs pe
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
 
 
+def ncu_traffic(kind: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    workload (profiles/r1_ncu_traffic.json) — not measured live (a number taken under a profiler is not a bench value)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            return float(json.load(f)["kernels"][kind]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -307,7 +317,10 @@ def run_gpu_arm(args):
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         ach = kernels[dom]["bytes"] / (kernels[dom]["ms"] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"vote": f"kc::vote_*_kernel<{n}>", "numeric": f"kc::numeric_*_kernel<{n}>"}[dom],
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic(dom) if (n == 16 and N == 1_000_000 and chunks == 1) else None,
+                    "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full of this workload; bytes per launch)",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
                     "all_kernels": {k: {"ms_per_launch": v["ms"], "achieved_GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9,
                                         "frac": v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak} for k, v in kernels.items()},

@@ -124,6 +124,17 @@ int kc_confidence_f64(const uint32_t *d_meta, int64_t n_groups, int32_t numeric,
 int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_t n_seq, float *d_sum, void *stream);
 
 /*
+ * K3b — likelihood-weighted vote (NEW feature, self-defined: DESIGN.md §5).  Candidate weight
+ * w_c = kexp(seq_logprob[record][c] - max_k seq_logprob[record][k]); class weight = sum of its cells' weights
+ * (fp32, ascending candidate order); the heaviest class wins, ties -> first seen.
+ *   d_codes int32[n_records*n_fields][n] as kc_vote_i32; d_seq_logprob float32[n_records][n] (e.g. kc_logprob_sum_f32)
+ *   d_weight float32[n_groups]: winning class weight / total voting weight (0 if nothing voted)
+ */
+int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int64_t n_records, int32_t n_fields,
+                         int32_t n, const int32_t *d_none_code, int32_t *d_win_code, uint32_t *d_meta, float *d_weight,
+                         void *stream);
+
+/*
  * End-to-end entry with HOST buffers (the call a k_llms binding makes for a batch of records of one
  * flat schema): chunked, double-buffered H2D -> K1/K2 -> D2H on internal streams of `device`.
  * Either half may be absent (n_vote_fields == 0 or n_num_fields == 0).  Blocks until results are in

@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 
 EXPORTS = (
     "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64",
-    "kc_confidence_f64", "kc_logprob_sum_f32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
+    "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
 
@@ -58,12 +58,14 @@ def load() -> ctypes.CDLL:
     lib.kc_numeric_f64.argtypes = [vp, i64, i32, f64, f64, vp, vp, vp]
     lib.kc_confidence_f64.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.kc_logprob_sum_f32.argtypes = [vp, vp, i64, vp, vp]
+    lib.kc_weighted_vote_i32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int, vp]
     lib.kc_host_alloc.argtypes = [c.c_uint64]
     lib.kc_host_alloc.restype = vp
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
+                 "kc_weighted_vote_i32",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -148,6 +150,27 @@ def logprob_sum(logprobs, offsets, stream=None):
     check(load().kc_logprob_sum_f32(logprobs.data_ptr(), offsets.data_ptr(), out.numel(), out.data_ptr(),
                                     _stream_ptr(torch, stream)))
     return out
+
+
+def weighted_vote(codes, seq_logprob, none_code=None, stream=None):
+    """K3b: likelihood-weighted vote.  codes int32 [R, F, n], seq_logprob float32 [R, n] (cuda).
+    Returns (win_code int32 [R*F], meta int32 [R*F], weight float32 [R*F])."""
+    torch = _require_cuda()
+    assert codes.is_cuda and codes.dtype == torch.int32 and codes.dim() == 3 and codes.is_contiguous()
+    R, F, n = codes.shape
+    assert seq_logprob.is_cuda and seq_logprob.dtype == torch.float32 and tuple(seq_logprob.shape) == (R, n)
+    assert seq_logprob.is_contiguous()
+    win = torch.empty(R * F, dtype=torch.int32, device=codes.device)
+    meta = torch.empty(R * F, dtype=torch.int32, device=codes.device)
+    weight = torch.empty(R * F, dtype=torch.float32, device=codes.device)
+    nc = None
+    if none_code is not None:
+        assert none_code.is_cuda and none_code.dtype == torch.int32 and none_code.numel() == F
+        nc = none_code.data_ptr()
+    _bind(torch, codes)
+    check(load().kc_weighted_vote_i32(codes.data_ptr(), seq_logprob.data_ptr(), R, F, n, nc, win.data_ptr(), meta.data_ptr(),
+                                      weight.data_ptr(), _stream_ptr(torch, stream)))
+    return win, meta, weight
 
 
 def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0, out=None):

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "kc_common.cuh"
+#include "kc_vote.cuh"
 
 namespace kc {
 
@@ -88,6 +89,99 @@ __global__ void __launch_bounds__(256) logprob_sum_kernel(const float *__restric
 #pragma unroll
         for (int st = 16; st >= 1; st >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, st));
         if (lane == 0) out[s] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- K3b: likelihood-weighted vote (self-defined spec)
+
+// exp(x) for x <= 0, built only from single IEEE fp32 operations in a fixed order so that the C oracle
+// (oracle/consensus_oracle.c: ko_exp_f32) reproduces it bit for bit: t = x*log2(e); k = floor(t + 0.5); f = t - k;
+// 2^f by a degree-5 polynomial (Horner, separate multiply and add); scale by 2^k through the exponent field.
+__device__ __forceinline__ float kexp(float x) {
+    x = x < -87.0f ? -87.0f : x;
+    const float t = __fmul_rn(x, 1.44269504f);
+    const float k = floorf(__fadd_rn(t, 0.5f));
+    const float f = __fadd_rn(t, -k);
+    float p = 0.00133336f;
+    p = __fadd_rn(__fmul_rn(p, f), 0.00961813f);
+    p = __fadd_rn(__fmul_rn(p, f), 0.05550411f);
+    p = __fadd_rn(__fmul_rn(p, f), 0.24022651f);
+    p = __fadd_rn(__fmul_rn(p, f), 0.69314718f);
+    p = __fadd_rn(__fmul_rn(p, f), 1.0f);
+    return __fmul_rn(p, __int_as_float(((int)k + 127) << 23));
+}
+
+// One thread per group.  Candidate weight w_c = kexp(s_c - max_k s_k) with s = seq_logprob[record]; class weight =
+// sum of its cells' weights in ascending candidate order (fp32); the heaviest class wins, ties -> first seen.
+template <int NP>
+__global__ void __launch_bounds__(128) weighted_vote_kernel(const int32_t *__restrict__ codes, const float *__restrict__ seq_lp,
+                                                            int64_t n_groups, int n, FieldMap fm, bool has_nc,
+                                                            int32_t *__restrict__ win, uint32_t *__restrict__ meta,
+                                                            float *__restrict__ weight) {
+    using M = typename MaskOf<NP>::type;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const int64_t rec = g / fm.n_fields;
+        const uint32_t field = (uint32_t)(g - rec * fm.n_fields);
+        const int32_t nc = has_nc ? __ldg(fm.none_code + field) : KC_CODE_NONE;
+        int32_t x[NP];
+        float w[NP];
+        float smax = -3.0e38f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            int32_t c = (i < n) ? __ldg(codes + g * n + i) : KC_CODE_ABSENT;
+            const float s = (i < n) ? __ldg(seq_lp + rec * n + i) : -3.0e38f;
+            w[i] = s;
+            smax = (i < n && s > smax) ? s : smax;
+            c = (c == KC_CODE_NONE) ? nc : c;           // None votes as none_code where it is >= 0
+            x[i] = c < KC_CODE_NONE ? KC_CODE_NONE : c;  // absent cells never vote
+        }
+        M live = 0;
+        int present = 0;
+        float total = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            w[i] = kexp(__fadd_rn(w[i], -smax));
+            const bool absent = (i >= n) || __ldg(codes + g * n + (i < n ? i : 0)) < KC_CODE_NONE;
+            present += absent ? 0 : 1;
+            if (x[i] >= 0) {
+                live |= M(1) << i;
+                total = __fadd_rn(total, w[i]);
+            }
+        }
+        const int voters = popc_m(live);
+        float best_w = -1.0f;
+        int best_idx = 0, best_cnt = 0;
+        int32_t best_code = KC_CODE_NONE;
+        bool tie = false;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if ((live >> i) & 1) {
+                const int32_t c = x[i];
+                M eq = 0;
+                float cw = 0.0f;
+#pragma unroll
+                for (int j = i; j < NP; ++j) {
+                    const bool e = x[j] == c;
+                    eq |= e ? (M(1) << j) : M(0);
+                    cw = e ? __fadd_rn(cw, w[j]) : cw;
+                }
+                if (cw > best_w) {
+                    best_w = cw;
+                    best_idx = i;
+                    best_cnt = popc_m(eq);
+                    best_code = c;
+                    tie = false;
+                } else if (cw == best_w) {
+                    tie = true;
+                }
+                live &= ~eq;
+            }
+        }
+        win[g] = best_code;
+        meta[g] = pack_meta(best_idx, best_cnt, voters, present,
+                            voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
+        weight[g] = voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
     }
 }
 

@@ -436,6 +436,33 @@ int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_
     return KC_OK;
 }
 
+int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int64_t n_records, int32_t n_fields,
+                         int32_t n, const int32_t *d_none_code, int32_t *d_win_code, uint32_t *d_meta, float *d_weight,
+                         void *stream) {
+    if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_weighted_vote_i32: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
+    if (n_records < 0 || n_fields < 1) return fail(KC_EINVAL, "kc_weighted_vote_i32: bad sizes");
+    if (n_records == 0) return KC_OK;
+    if (!d_codes || !d_seq_logprob || !d_win_code || !d_meta || !d_weight) return fail(KC_EINVAL, "kc_weighted_vote_i32: NULL buffer");
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int64_t G = n_records * n_fields;
+    const int threads = 128;
+    const int grid = (int)std::min<int64_t>((G + threads - 1) / threads, (int64_t)info.sm_count * 8);
+    const kc::FieldMap fm = make_field_map(d_none_code, n_fields);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define KC_WV(NP) kc::weighted_vote_kernel<NP><<<grid, threads, 0, st>>>(d_codes, d_seq_logprob, G, n, fm, d_none_code != nullptr, d_win_code, d_meta, d_weight)
+    if (n <= 2) KC_WV(2);
+    else if (n <= 4) KC_WV(4);
+    else if (n <= 8) KC_WV(8);
+    else if (n <= 16) KC_WV(16);
+    else if (n <= 32) KC_WV(32);
+    else KC_WV(64);
+#undef KC_WV
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
 void *kc_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -42,6 +42,9 @@ def lib() -> ctypes.CDLL:
         _lib.ko_numeric_f64.restype = None
         _lib.ko_logprob_sum_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p]
         _lib.ko_logprob_sum_f32.restype = None
+        _lib.ko_weighted_vote_i32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p,
+                                              c.c_void_p, c.c_void_p]
+        _lib.ko_weighted_vote_i32.restype = None
         for name in ("ko_np_sum", "ko_np_mean", "ko_np_median_sorted", "ko_np_std"):
             f = getattr(_lib, name)
             f.argtypes = [c.c_void_p, c.c_int]
@@ -82,6 +85,21 @@ def logprob_sum(logprobs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
     out = np.empty(len(offsets) - 1, dtype=np.float32)
     lib().ko_logprob_sum_f32(_ptr(logprobs), _ptr(offsets), len(out), _ptr(out))
     return out
+
+
+def weighted_vote(codes: np.ndarray, seq_logprob: np.ndarray, none_code: np.ndarray | None = None):
+    """codes int32 [R, F, n], seq_logprob float32 [R, n] -> (win int32 [R*F], meta uint32 [R*F], weight float32 [R*F])."""
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    seq_logprob = np.ascontiguousarray(seq_logprob, dtype=np.float32)
+    R, F, n = codes.shape
+    win = np.empty(R * F, dtype=np.int32)
+    meta = np.empty(R * F, dtype=np.uint32)
+    weight = np.empty(R * F, dtype=np.float32)
+    if none_code is not None:
+        none_code = np.ascontiguousarray(none_code, dtype=np.int32)
+    lib().ko_weighted_vote_i32(_ptr(codes), _ptr(seq_logprob), R, F, n, _ptr(none_code) if none_code is not None else None,
+                               _ptr(win), _ptr(meta), _ptr(weight))
+    return win, meta, weight
 
 
 def meta_fields(meta: np.ndarray):

@@ -240,3 +240,84 @@ void ko_logprob_sum_f32(const float *lp, const int64_t *offsets, int64_t n_seq, 
         out[s] = lane[0];
     }
 }
+
+/* ------------------------------------------------------------------ K3b oracle: likelihood-weighted vote (self-defined) */
+
+/* exp(x), x <= 0, from single fp32 operations in a fixed order (mirrors kc::kexp; compiled with -ffp-contract=off). */
+float ko_exp_f32(float x) {
+    if (x < -87.0f) x = -87.0f;
+    volatile float t = x * 1.44269504f;
+    volatile float th = t + 0.5f;
+    float k = floorf(th);
+    volatile float f = t - k;
+    volatile float p = 0.00133336f;
+    p = p * f; p = p + 0.00961813f;
+    p = p * f; p = p + 0.05550411f;
+    p = p * f; p = p + 0.24022651f;
+    p = p * f; p = p + 0.69314718f;
+    p = p * f; p = p + 1.0f;
+    union { int32_t i; float f; } sc;
+    sc.i = ((int32_t)k + 127) << 23;
+    volatile float r = p * sc.f;
+    return r;
+}
+
+void ko_weighted_vote_i32(const int32_t *codes, const float *seq_lp, int64_t n_records, int32_t n_fields, int32_t n,
+                          const int32_t *none_code, int32_t *win_code, uint32_t *meta, float *weight) {
+    for (int64_t r = 0; r < n_records; r++) {
+        float smax = -3.0e38f, w[MAXN];
+        for (int c = 0; c < n; c++)
+            if (seq_lp[r * n + c] > smax) smax = seq_lp[r * n + c];
+        for (int c = 0; c < n; c++) {
+            volatile float d = seq_lp[r * n + c] - smax;
+            w[c] = ko_exp_f32(d);
+        }
+        for (int32_t f = 0; f < n_fields; f++) {
+            int64_t g = r * n_fields + f;
+            int32_t nc = none_code ? none_code[f] : -1;
+            int32_t cls_code[MAXN];
+            int cls_count[MAXN], cls_first[MAXN], n_cls = 0, present = 0, voters = 0;
+            float cls_w[MAXN];
+            volatile float total = 0.0f;
+            for (int c = 0; c < n; c++) {
+                int32_t v = codes[g * n + c];
+                if (v < KC_CODE_NONE) continue;
+                present++;
+                if (v == KC_CODE_NONE) {
+                    if (nc < 0) continue;
+                    v = nc;
+                }
+                voters++;
+                total = total + w[c];
+                int k = 0;
+                while (k < n_cls && cls_code[k] != v) k++;
+                if (k == n_cls) {
+                    cls_code[k] = v;
+                    cls_count[k] = 0;
+                    cls_first[k] = c;
+                    cls_w[k] = 0.0f;
+                    n_cls++;
+                }
+                cls_count[k]++;
+                volatile float acc = cls_w[k] + w[c];
+                cls_w[k] = acc;
+            }
+            if (voters == 0) {
+                win_code[g] = KC_CODE_NONE;
+                meta[g] = KC_META_PACK(0, 0, 0, present, 0);
+                weight[g] = 0.0f;
+                continue;
+            }
+            int best = 0, ties = 0;
+            for (int k = 1; k < n_cls; k++)
+                if (cls_w[k] > cls_w[best]) best = k;
+            for (int k = 0; k < n_cls; k++)
+                if (k != best && cls_w[k] == cls_w[best]) ties = 1;
+            win_code[g] = cls_code[best];
+            meta[g] = KC_META_PACK(cls_first[best], cls_count[best], voters, present,
+                                   KC_FLAG_HAS_VALUE | (ties ? KC_FLAG_TIE : 0));
+            volatile float q = cls_w[best] / total;
+            weight[g] = q;
+        }
+    }
+}

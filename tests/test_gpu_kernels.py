@@ -225,3 +225,45 @@ def test_s32_full_size_properties():
     ev, enm = OC.numeric(vals[sel].cpu().numpy().reshape(-1, n))
     assert np.array_equal(value.view(N, 8)[sel].cpu().numpy().reshape(-1).view(np.uint64), ev.view(np.uint64))
     assert np.array_equal(nmeta.view(N, 8)[sel].cpu().numpy().reshape(-1).view(np.uint32), enm)
+
+
+@pytest.mark.parametrize("n", [2, 3, 8, 16, 32, 64])
+def test_weighted_vote_matches_oracle(n):
+    """K3b (self-defined spec): bit-exact against the C oracle, incl. the class weights."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(40 + n)
+    R, F = 3001, 5
+    codes = random_codes(rng, R * F, n, 4, p_agree=0.5).reshape(R, F, n)
+    lp = (-rng.exponential(6.0, (R, n))).astype(np.float32)
+    lp[rng.random((R, n)) < 0.02] = -500.0  # hopeless candidates (weight underflows to the clamp)
+    none_code = np.array([-1, 0, -1, 2, -1], dtype=np.int32)
+    for nc in (None, none_code):
+        ew, em, ewt = OC.weighted_vote(codes, lp, nc)
+        win, meta, wt = K.weighted_vote(torch.from_numpy(codes).cuda(), torch.from_numpy(lp).cuda(),
+                                        torch.from_numpy(nc).cuda() if nc is not None else None)
+        assert np.array_equal(win.cpu().numpy(), ew)
+        assert np.array_equal(meta.cpu().numpy().view(np.uint32), em)
+        assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
+
+
+def test_config4_logprob_pipeline_n32():
+    """BASELINE config 4 shape (n=32, ragged per-token logprobs): K3 sums -> K3b weighted vote, against the oracle,
+    plus the fp64 deviation of the fp32 likelihood sums (reported, since fp32 cannot hold 1e-6 at |sum| ~ 40)."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(4)
+    R, F, n = 4096, 8, 32
+    lens = rng.integers(8, 65, R * n)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    lp = (-rng.exponential(1.0, offsets[-1])).astype(np.float32)
+    codes = random_codes(rng, R * F, n, 6, p_absent=0.0).reshape(R, F, n)
+    sums = K.logprob_sum(torch.from_numpy(lp).cuda(), torch.from_numpy(offsets).cuda())
+    exp_sums = OC.logprob_sum(lp, offsets)
+    assert np.array_equal(sums.cpu().numpy().view(np.uint32), exp_sums.view(np.uint32))
+    win, meta, wt = K.weighted_vote(torch.from_numpy(codes).cuda(), sums.view(R, n))
+    ew, em, ewt = OC.weighted_vote(codes, exp_sums.reshape(R, n))
+    assert np.array_equal(win.cpu().numpy(), ew) and np.array_equal(meta.cpu().numpy().view(np.uint32), em)
+    assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
+    ref64 = np.add.reduceat(lp.astype(np.float64), offsets[:-1])
+    assert np.max(np.abs(exp_sums - ref64)) < 1e-4
