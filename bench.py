@@ -133,7 +133,7 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is pure Python and absent on the GPU box; this arm runs the oracle port of its per-record path"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -340,9 +340,31 @@ def run_gpu_arm(args):
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
                                  "pipeline_chunks": chunks}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """NCCL and friends print to fd 1 (e.g. "NCCL version ..."); the contract is ONE JSON line on stdout.  Point fd 1
+    at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -365,6 +387,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    _capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
