@@ -187,7 +187,7 @@ def run_gpu_arm(args):
     import torch
     from k_llms_b200 import _native as K
     from k_llms_b200 import synth
-    from k_llms_b200.distributed import OutputLayout, ShardedConsensus
+    from k_llms_b200.distributed import FusedShardedConsensus, OutputLayout, ShardedConsensus
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,10 +215,23 @@ def run_gpu_arm(args):
     codes, none_code, vals = synth.s32_torch(N, n, 20260921 + 2 + rank, dev)  # §8d: seed 20260921 + cfg, per-rank shard
     c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
     layout = OutputLayout(N, 24, 8)
-    chunks = args.chunks if world > 1 else 1  # pipeline depth of compute vs all-gather (meaningless on one GPU)
+    # N > 1: reassembly is fused into the kernels (multimem.st through NVSwitch) when the multicast mapping exists,
+    # else the pipelined NCCL all-gather (--reassembly nccl forces it).
+    fused = None
+    if world > 1 and args.reassembly in ("auto", "fused"):
+        try:
+            fused = FusedShardedConsensus(layout, dev)
+            if not fused.available():
+                fused = None
+        except Exception as exc:  # symmetric memory unavailable on this stack
+            print(f"fused reassembly unavailable: {exc}", file=sys.stderr)
+            fused = None
+        if fused is None and args.reassembly == "fused":
+            raise RuntimeError("--reassembly fused requested but no multicast mapping is available")
+    chunks = args.chunks if (world > 1 and fused is None) else 1  # NCCL path: pipeline depth of compute vs all-gather
     while N % chunks:
         chunks -= 1
-    sharded = ShardedConsensus(layout, dev, chunks=chunks)
+    sharded = ShardedConsensus(layout, dev, chunks=chunks) if fused is None else None
     R = N // chunks
     lib = K.load()
     K.check(lib.kc_set_device(local_rank))
@@ -239,10 +252,28 @@ def run_gpu_arm(args):
             e[2].record()
             kernel_events.append(e)
 
+    def fused_launch(win_p, vmeta_p, value_p, nmeta_p):
+        if timing[0]:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+        K.check(lib.kc_vote_i32_ex(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win_p, vmeta_p, K.OUT_MULTIMEM, sp))
+        if timing[0]:
+            e[1].record()
+        K.check(lib.kc_numeric_f64_ex(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value_p, nmeta_p, K.OUT_MULTIMEM, sp))
+        if timing[0]:
+            e[2].record()
+            kernel_events.append(e)
+
+    def one_step():
+        if fused is not None:
+            fused.step(fused_launch)
+        else:
+            sharded.step(compute)
+
     timing = [False]
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
-        sharded.step(compute)
+        one_step()
     barrier()
 
     # --- timed: exactly K steps; per-kernel events on the launching stream ride along
@@ -253,7 +284,7 @@ def run_gpu_arm(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(K_steps):
-        sharded.step(compute)
+        one_step()
     stop.record()
     barrier()
     t_wall1 = time.time()
@@ -265,7 +296,7 @@ def run_gpu_arm(args):
     compute_ms = max_over_ranks(vote_ms + num_ms)
     value_rps = world * N / (ms_step / 1e3)
     gather_ms = 0.0
-    if dist is not None:  # the all-gather alone (no compute to hide behind), for the record
+    if dist is not None and fused is None:  # the all-gather alone (no compute to hide behind), for the record
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -274,7 +305,10 @@ def run_gpu_arm(args):
         g1.record()
         barrier()
         gather_ms = max_over_ranks(g0.elapsed_time(g1) / 5)
-    win, vmeta, value, nmeta = [torch.cat([sharded.my_views(c)[k] for c in range(chunks)]) for k in range(4)]
+    if fused is not None:
+        win, vmeta, value, nmeta = fused.rank_views(rank)
+    else:
+        win, vmeta, value, nmeta = [torch.cat([sharded.my_views(c)[k] for c in range(chunks)]) for k in range(4)]
 
     # --- end to end through the host-buffer C-ABI entry (rank-local shard, pinned host memory)
     e2e = None
@@ -334,12 +368,17 @@ def run_gpu_arm(args):
                 "config": {"workload": f"S32: {N} records/GPU x 32 fields (16 str-enum + 8 bool as int32 codes, 6 int + 2 float as f64), "
                                        f"n={n}, p_agree=0.8, p_none=0.05; {world} GPU(s), {world * N} records total",
                            "l2": f"inputs are {(bytes_vote + bytes_num) / 1e9:.2f} GB per step per GPU, > 126 MB L2: no flush needed",
-                           "step": "K1 vote + K2 numeric" + (" + NCCL all-gather of packed outputs" if world > 1 else ""),
-                           "parallelism": f"records sharded {world}-way, all-gather reassembly" if world > 1 else "single GPU"},
+                           "step": "K1 vote + K2 numeric" + ("" if world == 1 else
+                                   (" with results multimem.st-replicated to every GPU through NVSwitch + one cross-GPU barrier"
+                                    if fused is not None else " + pipelined NCCL all-gather of packed outputs")),
+                           "parallelism": (f"records sharded {world}-way; reassembly "
+                                           + ("fused into the kernels (NVSwitch multicast)" if fused is not None else "NCCL all-gather"))
+                                          if world > 1 else "single GPU"},
                 "e2e": e2e, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
-                                 "pipeline_chunks": chunks}}
+                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else "fused-multimem" if fused is not None else "nccl"),
+                                 "nvlink_floor_ms": (world - 1) * layout.nbytes / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -376,7 +415,8 @@ def main():
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--chunks", type=int, default=8, help="N>1: pipeline chunks of compute vs all-gather")
+    ap.add_argument("--chunks", type=int, default=8, help="N>1, NCCL reassembly: pipeline chunks of compute vs all-gather")
+    ap.add_argument("--reassembly", default="auto", choices=["auto", "fused", "nccl"])
     ap.add_argument("--cpu-records-per-core", type=int, default=1500)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

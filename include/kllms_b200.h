@@ -105,6 +105,20 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
                    uint32_t *d_meta, void *stream);
 
 /*
+ * Fused compute + reassembly for multi-GPU batches.  With out_mode == KC_OUT_MULTIMEM the output pointers are
+ * NVSwitch MULTICAST addresses (a CUDA multicast object bound on every GPU of the group, e.g. torch symmetric
+ * memory's multicast_ptr + this rank's slot offset): results are written with `multimem.st`, so the switch replicates
+ * every store into all GPUs' copies of the buffer — the all-gather of the output columns happens inside the
+ * producing kernel instead of a separate NCCL collective.  The caller runs a cross-GPU barrier before reading.
+ */
+#define KC_OUT_LOCAL 0u
+#define KC_OUT_MULTIMEM 1u
+int kc_vote_i32_ex(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                   int32_t *d_win_code, uint32_t *d_meta, uint32_t out_mode, void *stream);
+int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                      uint32_t *d_meta, uint32_t out_mode, void *stream);
+
+/*
  * Confidences from result words, bit-exact with Python's round(x, 5) (cu:982,1178,1187,1219):
  *   vote    (numeric == 0): round(pvf * (support / present), 5)          cu:973,982
  *   numeric (numeric == 1): round(support / nn, 5); SINGLE: pvf * (1/present) unrounded (cu:1086,1444)

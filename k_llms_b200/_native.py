@@ -21,9 +21,10 @@ CODE_NONE, CODE_ABSENT = -1, -2
 F64_NONE_BITS = 0x7FF8C0DE00000000
 F64_ABSENT_BITS = 0x7FF8C0DF00000000
 FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
+OUT_LOCAL, OUT_MULTIMEM = 0, 1
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -56,6 +57,8 @@ def load() -> ctypes.CDLL:
     lib.kc_set_device.argtypes = [c.c_int]
     lib.kc_vote_i32.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.kc_numeric_f64.argtypes = [vp, i64, i32, f64, f64, vp, vp, vp]
+    lib.kc_vote_i32_ex.argtypes = [vp, i64, i32, vp, i32, vp, vp, c.c_uint32, vp]
+    lib.kc_numeric_f64_ex.argtypes = [vp, i64, i32, f64, f64, vp, vp, c.c_uint32, vp]
     lib.kc_confidence_f64.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.kc_logprob_sum_f32.argtypes = [vp, vp, i64, vp, vp]
     lib.kc_weighted_vote_i32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
@@ -65,7 +68,7 @@ def load() -> ctypes.CDLL:
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib

@@ -146,6 +146,22 @@ __device__ __forceinline__ void stg_stream_f64(void *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// Result stores.  mc == true: `p` is an NVSwitch MULTICAST address (CUDA multicast object mapped on every GPU of
+// the group); multimem.st makes the switch replicate the store into each GPU's copy of the buffer — the all-gather
+// of the outputs happens inside the producing kernel, tile by tile, instead of in a separate collective.
+__device__ __forceinline__ void store_out_u32(void *p, uint32_t v, bool mc) {
+    if (mc)
+        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void store_out_f64(void *p, double v, bool mc) {
+    if (mc)
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ int4 lds_v4(uint32_t addr) {
     int4 r;
     asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));

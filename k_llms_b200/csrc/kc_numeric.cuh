@@ -397,7 +397,7 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 template <int NP, int T, bool PREFETCH>
 __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restrict__ vals, int64_t n_groups, int n,
                                                            double rel_eps, double abs_eps, double *__restrict__ out_value,
-                                                           uint32_t *__restrict__ out_meta) {
+                                                           uint32_t *__restrict__ out_meta, bool mc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
     const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
@@ -430,8 +430,8 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
             double v;
             uint32_t m;
             numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-            stg_stream_f64(out_value + g, v);
-            stg_stream_u32(out_meta + g, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
 #pragma unroll
             for (int q = 0; q < NP / 2; ++q) cur[q] = nxt[q];
         } else {
@@ -457,8 +457,8 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
             double v;
             uint32_t m;
             numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-            stg_stream_f64(out_value + g, v);
-            stg_stream_u32(out_meta + g, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
         }
     }
 }
@@ -474,7 +474,7 @@ template <int N, int WARPS, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,
                                                                  double *__restrict__ out_value,
-                                                                 uint32_t *__restrict__ out_meta) {
+                                                                 uint32_t *__restrict__ out_meta, bool mc) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
@@ -549,8 +549,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const
             double v;
             uint32_t m;
             numeric_core<N, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-            stg_stream_f64(out_value + g, v);
-            stg_stream_u32(out_meta + g, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
         }
         if (++stage == STAGES) {
             stage = 0;

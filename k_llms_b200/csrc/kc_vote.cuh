@@ -206,7 +206,7 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ codes, int6
 template <int NP, bool VEC, bool HAS_NC, bool PREFETCH>
 __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restrict__ codes, int64_t n_groups, int n,
                                                           FieldMap fm, int32_t *__restrict__ win,
-                                                          uint32_t *__restrict__ meta) {
+                                                          uint32_t *__restrict__ meta, bool mc) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t f = 0, fstep = 0;
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
         int32_t w;
         uint32_t m;
         vote_core<NP, HAS_NC>(raw, row_min<NP>(raw), nc, w, m);
-        stg_stream_u32(win + g, (uint32_t)w);
-        stg_stream_u32(meta + g, m);
+        store_out_u32(win + g, (uint32_t)w, mc);
+        store_out_u32(meta + g, m, mc);
         if constexpr (PREFETCH) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) raw[i] = nxt[i];
@@ -258,7 +258,7 @@ struct Swizzle {  // TMA swizzle mode for a row of ROW_BYTES (rows wider than 12
 template <int N, int WARPS, int STAGES, bool HAS_NC>
 __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t n_groups,
                                                               FieldMap fm, int32_t *__restrict__ win,
-                                                              uint32_t *__restrict__ meta) {
+                                                              uint32_t *__restrict__ meta, bool mc) {
     constexpr int ROW_BYTES = N * 4;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_const
             int32_t w;
             uint32_t m;
             vote_core<N, HAS_NC>(raw, lo, nc, w, m);
-            stg_stream_u32(win + g, (uint32_t)w);
-            stg_stream_u32(meta + g, m);
+            store_out_u32(win + g, (uint32_t)w, mc);
+            store_out_u32(meta + g, m, mc);
         }
     }
 }

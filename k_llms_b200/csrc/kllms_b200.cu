@@ -131,7 +131,7 @@ kc::FieldMap make_field_map(const int32_t *none_code, int n_fields) {
 
 template <int N, int WARPS, int STAGES, bool HAS_NC>
 int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool mc) {
     auto kernel = kc::vote_tma_kernel<N, WARPS, STAGES, HAS_NC>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 4 + 1024;
     // a slab starts on a record boundary so that (g - g0) % n_fields == g % n_fields
@@ -144,7 +144,7 @@ int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code
         int grid = 0;
         rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
         if (rc) return rc;
-        kernel<<<grid, WARPS * 32, smem, st>>>(map, (uint32_t)gs, make_field_map(none_code, n_fields), win + g0, meta + g0);
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, (uint32_t)gs, make_field_map(none_code, n_fields), win + g0, meta + g0, mc);
         KC_CUDA(cudaGetLastError());
     }
     return KC_OK;
@@ -152,16 +152,16 @@ int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code
 
 template <int N, int WARPS, int STAGES>
 int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool mc) {
     if (none_code && n_fields < 60000)
-        return launch_vote_tma_nc<N, WARPS, STAGES, true>(codes, G, none_code, n_fields, win, meta, st);
+        return launch_vote_tma_nc<N, WARPS, STAGES, true>(codes, G, none_code, n_fields, win, meta, st, mc);
     if (none_code) return fail(KC_EINVAL, "kc_vote_i32: more than 60000 fields with none_code is not supported");
-    return launch_vote_tma_nc<N, WARPS, STAGES, false>(codes, G, nullptr, 1, win, meta, st);
+    return launch_vote_tma_nc<N, WARPS, STAGES, false>(codes, G, nullptr, 1, win, meta, st, mc);
 }
 
 template <int NP, bool VEC>
 int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *none_code, int n_fields, int32_t *win,
-                       uint32_t *meta, cudaStream_t st) {
+                       uint32_t *meta, cudaStream_t st, bool mc) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -173,13 +173,13 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     constexpr bool kCanPrefetch = VEC && NP >= 4 && NP <= 16;
     if (kCanPrefetch && prefetch) {
         if (none_code)
-            kc::vote_direct_kernel<NP, VEC, true, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+            kc::vote_direct_kernel<NP, VEC, true, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
         else
-            kc::vote_direct_kernel<NP, VEC, false, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+            kc::vote_direct_kernel<NP, VEC, false, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
     } else if (none_code) {
-        kc::vote_direct_kernel<NP, VEC, true, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+        kc::vote_direct_kernel<NP, VEC, true, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
     } else {
-        kc::vote_direct_kernel<NP, VEC, false, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta);
+        kc::vote_direct_kernel<NP, VEC, false, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
     }
     KC_CUDA(cudaGetLastError());
     return KC_OK;
@@ -189,7 +189,7 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
 
 template <int N, int WARPS, int STAGES, int MIN_CTAS = 1>
 int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool mc) {
     auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES, MIN_CTAS>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
@@ -200,7 +200,7 @@ int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs
         int grid = 0;
         rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
         if (rc) return rc;
-        kernel<<<grid, WARPS * 32, smem, st>>>(map, gs, rel_eps, abs_eps, value + g0, meta + g0);
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, gs, rel_eps, abs_eps, value + g0, meta + g0, mc);
         KC_CUDA(cudaGetLastError());
     }
     return KC_OK;
@@ -208,7 +208,7 @@ int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs
 
 template <int NP, int T>
 int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, double abs_eps, double *value,
-                          uint32_t *meta, cudaStream_t st) {
+                          uint32_t *meta, cudaStream_t st, bool mc) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -222,7 +222,7 @@ int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, 
         if (per_sm < 1) return fail(KC_ECUDA, "numeric_direct_kernel<%d> does not fit", NP);
         const int64_t blocks = (G + T - 1) / T;
         const int grid = (int)std::min<int64_t>(blocks, (int64_t)info.sm_count * per_sm);
-        kernel<<<grid, T, smem, st>>>(vals, G, n, rel_eps, abs_eps, value, meta);
+        kernel<<<grid, T, smem, st>>>(vals, G, n, rel_eps, abs_eps, value, meta, mc);
         KC_CUDA(cudaGetLastError());
         return KC_OK;
     };
@@ -319,6 +319,13 @@ int kc_set_device(int device) {
 
 int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
                 int32_t *d_win_code, uint32_t *d_meta, void *stream) {
+    return kc_vote_i32_ex(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, KC_OUT_LOCAL, stream);
+}
+
+int kc_vote_i32_ex(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                   int32_t *d_win_code, uint32_t *d_meta, uint32_t out_mode, void *stream) {
+    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_vote_i32_ex: unknown out_mode %u", out_mode);
+    const bool mc = out_mode == KC_OUT_MULTIMEM;
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_vote_i32: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_groups < 0) return fail(KC_EINVAL, "kc_vote_i32: negative n_groups");
     if (n_groups == 0) return KC_OK;
@@ -330,43 +337,50 @@ int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32
     // measured on B200 (profiles/README.md): the direct front-end wins up to n = 16, the TMA pipeline from n = 32
     if (force_direct() || (!force_tma() && n <= 16)) {
         switch (n) {
-            case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 8: return launch_vote_direct<8, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 16: return launch_vote_direct<16, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 32: return launch_vote_direct<32, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-            case 64: return launch_vote_direct<64, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+            case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 8: return launch_vote_direct<8, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 16: return launch_vote_direct<16, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 32: return launch_vote_direct<32, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            case 64: return launch_vote_direct<64, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
             default: break;
         }
     } else
     switch (n) {
-        case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 8: return launch_vote_tma<8, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+        case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+        case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+        case 8: return launch_vote_tma<8, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         case 16: {
             static const int cfg = [] { const char *e = getenv("KC_VOTE_CFG"); return e ? atoi(e) : 0; }();
-            if (cfg == 1) return launch_vote_tma<16, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-            if (cfg == 2) return launch_vote_tma<16, 4, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-            if (cfg == 3) return launch_vote_tma<16, 16, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-            if (cfg == 4) return launch_vote_tma<16, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-            if (cfg == 5) return launch_vote_tma<16, 8, 8>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-            return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+            if (cfg == 1) return launch_vote_tma<16, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            if (cfg == 2) return launch_vote_tma<16, 4, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            if (cfg == 3) return launch_vote_tma<16, 16, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            if (cfg == 4) return launch_vote_tma<16, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            if (cfg == 5) return launch_vote_tma<16, 8, 8>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+            return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         }
-        case 32: return launch_vote_tma<32, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
-        case 64: return launch_vote_tma<64, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 32: return launch_vote_tma<32, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+        case 64: return launch_vote_tma<64, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         default: break;
     }
-    if (n < 4) return launch_vote_direct<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-    if (n < 8) return launch_vote_direct<8, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-    if (n < 16) return launch_vote_direct<16, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-    if (n < 32) return launch_vote_direct<32, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
-    return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 4) return launch_vote_direct<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+    if (n < 8) return launch_vote_direct<8, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+    if (n < 16) return launch_vote_direct<16, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+    if (n < 32) return launch_vote_direct<32, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+    return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
 }
 
 int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
                    uint32_t *d_meta, void *stream) {
+    return kc_numeric_f64_ex(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, KC_OUT_LOCAL, stream);
+}
+
+int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                      uint32_t *d_meta, uint32_t out_mode, void *stream) {
+    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_numeric_f64_ex: unknown out_mode %u", out_mode);
+    const bool mc = out_mode == KC_OUT_MULTIMEM;
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_numeric_f64: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_groups < 0) return fail(KC_EINVAL, "kc_numeric_f64: negative n_groups");
     if (!(rel_eps >= 0.0) || !(abs_eps >= 0.0)) return fail(KC_EINVAL, "kc_numeric_f64: rel_eps/abs_eps must be >= 0");
@@ -378,32 +392,32 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
     // and at n = 64 (register pressure)
     if (!force_direct() && (force_tma() || n == 16 || n == 32))
         switch (n) {
-            case 4: return launch_numeric_tma<4, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-            case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 4: return launch_numeric_tma<4, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+            case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 16: {
                 static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
-                if (cfg == 1) return launch_numeric_tma<16, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 4) return launch_numeric_tma<16, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 5) return launch_numeric_tma<16, 4, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 6) return launch_numeric_tma<16, 8, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 7) return launch_numeric_tma<16, 2, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 8) return launch_numeric_tma<16, 8, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 9) return launch_numeric_tma<16, 4, 1, 8>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                if (cfg == 10) return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-                return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+                if (cfg == 1) return launch_numeric_tma<16, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 4) return launch_numeric_tma<16, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 5) return launch_numeric_tma<16, 4, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 6) return launch_numeric_tma<16, 8, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 7) return launch_numeric_tma<16, 2, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 8) return launch_numeric_tma<16, 8, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 9) return launch_numeric_tma<16, 4, 1, 8>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                if (cfg == 10) return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             }
-            case 32: return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
-            case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st);
+            case 32: return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+            case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             default: break;
         }
-    if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n <= 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n <= 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n <= 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    if (n <= 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
-    return launch_numeric_direct<64, 64>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st);
+    if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
+    if (n <= 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
+    if (n <= 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
+    if (n <= 16) return launch_numeric_direct<16, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
+    if (n <= 32) return launch_numeric_direct<32, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
+    return launch_numeric_direct<64, 64>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
 }
 
 int kc_confidence_f64(const uint32_t *d_meta, int64_t n_groups, int32_t numeric, const double *d_pvf, double *d_conf,

@@ -85,3 +85,46 @@ class ShardedConsensus:
         for w in works:
             w.wait()
         return self.gathered
+
+
+class FusedShardedConsensus:
+    """Fused compute + reassembly over NVSwitch multicast (no NCCL collective on the data path).
+
+    The gathered buffer [world][nbytes] is torch symmetric memory with a multicast mapping; every rank's kernels store
+    their results to the MULTICAST address of the rank's slot with `multimem.st` (kc_*_ex, KC_OUT_MULTIMEM), so the
+    switch replicates each store into all GPUs' copies while the kernel is still computing the next groups.  One
+    cross-GPU barrier (symmetric-memory signal pads) closes the step.  Requires NVLS-capable hardware (B200 + NVSwitch);
+    `available()` says whether the multicast mapping exists — callers fall back to ShardedConsensus (NCCL) otherwise.
+    """
+
+    def __init__(self, layout: OutputLayout, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        assert dist.is_initialized(), "FusedShardedConsensus needs an initialised process group"
+        self.layout, self.device = layout, device
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.flat = symm_mem.empty(self.world * layout.nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.flat, self.group)
+        self.gathered = self.flat.view(self.world, layout.nbytes)
+        self.mc_ptr = int(self.handle.multicast_ptr or 0)
+
+    def available(self) -> bool:
+        return self.mc_ptr != 0
+
+    def slot_pointers(self, multicast: bool = True):
+        """(win, vote_meta, value, num_meta) raw addresses of THIS rank's slot, in the multicast or the local mapping."""
+        base = (self.mc_ptr if multicast else self.flat.data_ptr()) + self.rank * self.layout.nbytes
+        gv, gx = self.layout.gv, self.layout.gx
+        return base, base + gv * 4, base + gv * 8, base + gv * 8 + gx * 8
+
+    def rank_views(self, r: int):
+        return self.layout.views(self.gathered[r])
+
+    def step(self, launch: Callable):
+        """launch(win_ptr, vmeta_ptr, value_ptr, nmeta_ptr) enqueues the kernels with KC_OUT_MULTIMEM on the current
+        stream; the barrier afterwards makes every rank's stores visible everywhere."""
+        launch(*self.slot_pointers(multicast=True))
+        self.handle.barrier(channel=0)
+        return self.gathered
