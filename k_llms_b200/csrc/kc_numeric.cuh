@@ -17,6 +17,7 @@
 // the (rare) offending run repairs it.  Non-finite cells get keys above every finite key and sort to the end.
 #pragma once
 
+#include <type_traits>
 #include <utility>
 
 #include "kc_common.cuh"
@@ -58,10 +59,17 @@ struct SwzRow {  // this thread's row of a TMA-swizzled tile
     __device__ __forceinline__ uint32_t addr(uint32_t elem) const {
         return base + Swizzle<ROW_BYTES>::apply(row_off + elem * 8u);
     }
+    __device__ __forceinline__ uint32_t addr_mad(uint32_t elem) const { return addr(elem); }
 };
 struct PlaneRow {  // [cell][thread] plane: pitch = threads*8 bytes, a multiple of 128 => bank depends on tid only
     uint32_t base, pitch;
     __device__ __forceinline__ uint32_t addr(uint32_t elem) const { return base + elem * pitch; }
+    // same address as one IMAD (FMA pipe) instead of shift + add on the busier ALU pipe
+    __device__ __forceinline__ uint32_t addr_mad(uint32_t elem) const {
+        uint32_t a;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(elem), "r"(pitch), "r"(base));
+        return a;
+    }
 };
 
 // ---------------------------------------------------------------- numpy reductions over sorted row memory
@@ -96,6 +104,38 @@ __device__ __forceinline__ double np_sum(F f, int n) {
 template <typename Row>
 __device__ __forceinline__ double np_mean(const Row &xs, int s, int len) {
     return __ddiv_rn(np_sum([&](int i) { return lds_f64(xs.addr(s + i)); }, len), (double)len);
+}
+
+// The same sum for groups of at most 16 cells, without data-dependent loops: fewer than 8 terms -> up to 7
+// predicated adds; otherwise 8 accumulators (two terms each only when all 16 cells are in the cluster), the tree, and
+// up to 7 predicated tail adds.
+template <typename Row>
+__device__ __forceinline__ double np_mean16(const Row &xs, int s, int len) {
+    const uint32_t a0 = xs.addr_mad((uint32_t)s);
+    const uint32_t pitch = xs.addr(1) - xs.addr(0);
+    double res;
+    if (len < 8) {
+        res = -0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < len) res = __dadd_rn(res, lds_f64(a0 + j * pitch));
+    } else {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = lds_f64(a0 + j * pitch);
+        int tail = 8;
+        if (len >= 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], lds_f64(a0 + (8 + j) * pitch));
+            tail = 16;
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (tail + j < len) res = __dadd_rn(res, lds_f64(a0 + (tail + j) * pitch));
+    }
+    return __ddiv_rn(__dadd_rn(0.0, res), (double)len);
 }
 
 template <typename Row>
@@ -262,44 +302,37 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     constexpr uint32_t IDX = N - 1;
     const double qnan = __longlong_as_double(0x7FF8000000000000LL);
 
-    // A. keys, non-finite mask, and the None / absent census.  t is a bijective, order-preserving image of the
-    //    high word; the two tags are adjacent high words, so u = t - T_NONE is 0 (None) or 1 (absent) for tagged
-    //    cells and one packed counter (tagged << 16 | absent) takes a single predicated add per cell.
-    constexpr uint32_t T_NONE = (kNoneHi ^ 0x80000000u) - 0x00100000u;
+    // A. keys and the cell census.  t is a bijective, order-preserving image of the high word; z = t - 0xFFE00000 is
+    //    < 0x200000 exactly for non-finite cells, and the two tags are adjacent high words, so u = z - Z_NONE is
+    //    0 (None) or 1 (absent) for tagged cells.  One packed counter (tagged << 16 | nonfinite << 8 | absent) takes
+    //    a single add per cell.
+    constexpr uint32_t Z_NONE = ((kNoneHi ^ 0x80000000u) - 0x00100000u) - kKeyNonFinite;
     static_assert(kAbsentHi == kNoneHi + 1, "tags must be adjacent high words");
     uint32_t key[N];
-    M nf = 0;
     uint32_t census = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t s = (uint32_t)((int32_t)hi[i] >> 31);
         const uint32_t t = (hi[i] ^ (s | 0x80000000u)) - 0x00100000u;  // monotone in the value; non-finite -> >= 0xFFE00000
-        key[i] = (t & ~IDX) | (uint32_t)i;
-        nf |= (t >= kKeyNonFinite) ? (M(1) << i) : M(0);
-        const uint32_t u = t - T_NONE;
-        census += (u < 2u) ? (u + 0x10000u) : 0u;
+        key[i] = (t | IDX) - (IDX - (uint32_t)i);                       // (t & ~IDX) | i
+        const uint32_t z = t - kKeyNonFinite;
+        const uint32_t u = z - Z_NONE;
+        const uint32_t tagged_inc = (u < 2u) ? (u + 0x10100u) : 0x100u;
+        census += (z < 0x00200000u) ? tagged_inc : 0u;
     }
-    const int m = N - popc_m(nf);                                // finite cells (cu:1105-1114)
-    const int present = N - (int)(census & 0xFFFFu);             // len(values) at this node
-    const int nn = N - (int)(census >> 16);                      // non-None cells == `total` (cu:1100)
+    const int m = N - (int)((census >> 8) & 0xFFu);   // finite cells (cu:1105-1114)
+    const int present = N - (int)(census & 0xFFu);    // len(values) at this node
+    const int nn = N - (int)(census >> 16);           // non-None cells == `total` (cu:1100)
     if (nn == 0) {
         value = qnan;
         meta = pack_meta(0, 0, 0, present, 0);
         return;
     }
-    if (nn == 1) {  // cu:1085-1086: the original object, whatever it is
-        M fin = ~nf;
-        if constexpr (N < 32) fin &= (M(1) << N) - 1;
-        int idx;
-        if (m == 1) {
-            idx = ffs_m(fin) - 1;
-        } else {  // the lone non-None cell is itself not a finite number: find the non-finite cell that is not a tag
-            idx = 0;
-            for (M w = nf; w; w &= w - 1) {
-                const int i = ffs_m(w) - 1;
-                const uint32_t h = lds_u32x2(row.addr(i)).y;
-                if (h != kNoneHi && h != kAbsentHi) idx = i;
-            }
+    if (nn == 1) {  // cu:1085-1086: the original object, whatever it is (rare: scan row memory for the untagged cell)
+        int idx = 0;
+        for (int i = 0; i < N; ++i) {
+            const uint32_t h = lds_u32x2(row.addr(i)).y;
+            if (h != kNoneHi && h != kAbsentHi) idx = i;
         }
         value = lds_f64(row.addr(idx));
         meta = pack_meta(idx, 1, 1, present, KC_FLAG_HAS_VALUE | KC_FLAG_SINGLE);
@@ -315,7 +348,7 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     sort_keys<N>(key);
     double xs[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) xs[k] = lds_f64(row.addr(key[k] & IDX));
+    for (int k = 0; k < N; ++k) xs[k] = lds_f64(row.addr_mad(key[k] & IDX));
 
     // Keys drop low mantissa bits: values that differ only there may be swapped.  (NaN compares false; a -inf in
     // the non-finite tail can raise a false alarm, which only costs the repair call.)
@@ -382,7 +415,10 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     uint32_t flags = KC_FLAG_HAS_VALUE;
     int support = top;
     if (n_top == 1) {
-        value = np_mean(row, top_s, top);  // cu:1174-1178 / 1183-1187
+        if constexpr (N <= 16 && std::is_same<Row, PlaneRow>::value)
+            value = np_mean16(row, top_s, top);  // cu:1174-1178 / 1183-1187
+        else
+            value = np_mean(row, top_s, top);
     } else {
         const TieResult tr = numeric_tie<M, Row>(row, starts, m, top, rel_eps, abs_eps);
         value = tr.value;
@@ -529,7 +565,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const
             hi[2 * q + 1] = (uint32_t)v4.w;
             sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
             sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
-            touch |= (uint32_t)v4.y | (uint32_t)v4.w;
+            touch |= (uint32_t)v4.w;  // one word of every LDS.128 is enough to depend on all of them
         }
         // the tile is in registers (touch depends on every LDS, and a warp instruction issues only when all lanes'
         // operands are ready): hand the stage back
