@@ -313,9 +313,10 @@ def run_gpu_arm(args):
     # --- end to end through the host-buffer C-ABI entry (rank-local shard, pinned host memory)
     e2e = None
     if not args.no_e2e:
-        h_codes = K.pinned_empty((N, 24, n), np.int32)
+        # compact host cells: votes only need equality inside a group, so int8 codes are lossless (kc_consensus_host_i8)
+        h_codes = K.pinned_empty((N, 24, n), np.int8 if args.e2e_cells == "i8" else np.int32)
         h_vals = K.pinned_empty((N, 8, n), np.float64)
-        h_codes[...] = codes.cpu().numpy()
+        h_codes[...] = codes.cpu().numpy().astype(h_codes.dtype)
         h_vals[...] = vals.cpu().numpy()
         h_none = none_code.cpu().numpy()
         out = {"win_code": K.pinned_empty((N, 24), np.int32), "vote_meta": K.pinned_empty((N, 24), np.uint32),
@@ -335,7 +336,8 @@ def run_gpu_arm(args):
         assert np.array_equal(out["value"].reshape(-1).view(np.uint64), value.cpu().numpy().view(np.uint64))
         e2e = {"value": world * N / (e2e_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(h_codes.nbytes + h_vals.nbytes),
                "d2h_bytes_per_step": int(sum(a.nbytes for a in out.values())), "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "path": "kc_consensus_host (C ABI): pinned host buffers -> chunked H2D -> K1/K2 -> D2H on 3 streams, per rank"}
+               "path": f"kc_consensus_host{'_i8' if args.e2e_cells == 'i8' else ''} (C ABI): pinned host buffers ({h_codes.dtype} vote cells, "
+                       "f64 numeric cells) -> chunked H2D -> K1/K2 -> D2H on 3 streams, per rank"}
 
     clocks = None
     if sampler is not None:
@@ -415,6 +417,7 @@ def main():
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-cells", default="i8", choices=["i8", "i32"], help="host encoding of vote cells for the e2e leg")
     ap.add_argument("--chunks", type=int, default=8, help="N>1, NCCL reassembly: pipeline chunks of compute vs all-gather")
     ap.add_argument("--reassembly", default="auto", choices=["auto", "fused", "nccl"])
     ap.add_argument("--cpu-records-per-core", type=int, default=1500)

@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM = 0, 1
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -63,12 +63,14 @@ def load() -> ctypes.CDLL:
     lib.kc_logprob_sum_f32.argtypes = [vp, vp, i64, vp, vp]
     lib.kc_weighted_vote_i32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int, vp]
+    lib.kc_consensus_host_i8.argtypes = lib.kc_consensus_host.argtypes
+    lib.kc_vote_i8.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.kc_host_alloc.argtypes = [c.c_uint64]
     lib.kc_host_alloc.restype = vp
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -113,6 +115,21 @@ def vote(codes, none_code=None, stream=None) -> Tuple["torch.Tensor", "torch.Ten
         nc_ptr = none_code.data_ptr()
     _bind(torch, codes)
     check(load().kc_vote_i32(codes.data_ptr(), G, n, nc_ptr, nf, win.data_ptr(), meta.data_ptr(), _stream_ptr(torch, stream)))
+    return win, meta
+
+
+def vote_i8(codes, none_code=None, stream=None):
+    """K1 on compact int8 cells (cuda int8 [G, n])."""
+    torch = _require_cuda()
+    assert codes.is_cuda and codes.dtype == torch.int8 and codes.dim() == 2 and codes.is_contiguous()
+    G, n = codes.shape
+    win = torch.empty(G, dtype=torch.int32, device=codes.device)
+    meta = torch.empty(G, dtype=torch.int32, device=codes.device)
+    nf, nc_ptr = 0, None
+    if none_code is not None:
+        nf, nc_ptr = none_code.numel(), none_code.data_ptr()
+    _bind(torch, codes)
+    check(load().kc_vote_i8(codes.data_ptr(), G, n, nc_ptr, nf, win.data_ptr(), meta.data_ptr(), _stream_ptr(torch, stream)))
     return win, meta
 
 
@@ -184,7 +201,7 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     lib = load()
     N = n = Fv = Fx = 0
     if codes is not None:
-        assert codes.dtype == np.int32 and codes.ndim == 3 and codes.flags.c_contiguous
+        assert codes.dtype in (np.int32, np.int8) and codes.ndim == 3 and codes.flags.c_contiguous
         N, Fv, n = codes.shape
     if vals is not None:
         assert vals.dtype == np.float64 and vals.ndim == 3 and vals.flags.c_contiguous
@@ -201,8 +218,9 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
         assert none_code.size == Fv
     p = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
     ms = ctypes.c_float(0.0)
-    check(lib.kc_consensus_host(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
-                                p(value), p(nmeta), device, ctypes.addressof(ms)))
+    entry = lib.kc_consensus_host_i8 if (codes is not None and codes.dtype == np.int8) else lib.kc_consensus_host
+    check(entry(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
+                p(value), p(nmeta), device, ctypes.addressof(ms)))
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
 
 

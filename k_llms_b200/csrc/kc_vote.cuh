@@ -241,6 +241,68 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
     }
 }
 
+// ---------------------------------------------------------------- compact cells (int8)
+
+// Votes only need equality INSIDE a group, so a group can always be re-coded with local codes 0..n-1 (< 64): one
+// byte per cell (-1 None, -2 absent) is a lossless input format at a quarter of the bytes — what the end-to-end host
+// path ships over PCIe.  A row of n = 16 cells is ONE 16-byte load per thread (a warp reads 512 contiguous bytes).
+template <int NP, bool VEC>
+__device__ __forceinline__ void load_row_i8(const int8_t *__restrict__ codes, int64_t g, int n, int32_t (&raw)[NP]) {
+    if constexpr (VEC && NP >= 4) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(codes + g * NP);
+        uint32_t w[NP / 4];
+        if constexpr (NP >= 16) {
+#pragma unroll
+            for (int q = 0; q < NP / 16; ++q) {
+                const int4 t = ldg_nc_v4(reinterpret_cast<const int4 *>(p) + q);
+                w[4 * q + 0] = (uint32_t)t.x;
+                w[4 * q + 1] = (uint32_t)t.y;
+                w[4 * q + 2] = (uint32_t)t.z;
+                w[4 * q + 3] = (uint32_t)t.w;
+            }
+        } else if constexpr (NP == 8) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+            w[0] = t.x;
+            w[1] = t.y;
+        } else {
+            w[0] = __ldg(p);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) raw[i] = (int32_t)(int8_t)(w[i / 4] >> (8 * (i % 4)));
+    } else {
+        const int8_t *p = codes + g * n;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) raw[i] = (i < n) ? (int32_t)__ldg(p + i) : KC_CODE_ABSENT;
+    }
+}
+
+template <int NP, bool VEC, bool HAS_NC>
+__global__ void __launch_bounds__(256) vote_i8_kernel(const int8_t *__restrict__ codes, int64_t n_groups, int n, FieldMap fm,
+                                                      int32_t *__restrict__ win, uint32_t *__restrict__ meta, bool mc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t f = 0, fstep = 0;
+    if constexpr (HAS_NC) {
+        f = (uint32_t)(g % fm.n_fields);
+        fstep = (uint32_t)(stride % fm.n_fields);
+    }
+    for (; g < n_groups; g += stride) {
+        int32_t raw[NP];
+        load_row_i8<NP, VEC>(codes, g, n, raw);
+        int32_t nc = KC_CODE_NONE;
+        if constexpr (HAS_NC) {
+            nc = __ldg(fm.none_code + f);
+            f += fstep;
+            f = f >= fm.n_fields ? f - fm.n_fields : f;
+        }
+        int32_t w;
+        uint32_t m;
+        vote_core<NP, HAS_NC>(raw, row_min<NP>(raw), nc, w, m);
+        store_out_u32(win + g, (uint32_t)w, mc);
+        store_out_u32(meta + g, m, mc);
+    }
+}
+
 // ---------------------------------------------------------------- TMA front-end
 
 template <int ROW_BYTES>

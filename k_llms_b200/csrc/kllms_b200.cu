@@ -185,6 +185,23 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     return KC_OK;
 }
 
+template <int NP, bool VEC>
+int launch_vote_i8(const int8_t *codes, int64_t G, int n, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
+                   cudaStream_t st) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((G + threads - 1) / threads, (int64_t)info.sm_count * 8);
+    const kc::FieldMap fm = make_field_map(none_code, n_fields);
+    if (none_code)
+        kc::vote_i8_kernel<NP, VEC, true><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, false);
+    else
+        kc::vote_i8_kernel<NP, VEC, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, false);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
 // ---------------------------------------------------------------- K2 launchers
 
 template <int N, int WARPS, int STAGES, int MIN_CTAS = 1>
@@ -372,6 +389,31 @@ int kc_vote_i32_ex(const int32_t *d_codes, int64_t n_groups, int32_t n, const in
     return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
 }
 
+int kc_vote_i8(const int8_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+               int32_t *d_win_code, uint32_t *d_meta, void *stream) {
+    if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_vote_i8: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
+    if (n_groups < 0) return fail(KC_EINVAL, "kc_vote_i8: negative n_groups");
+    if (n_groups == 0) return KC_OK;
+    if (!d_codes || !d_win_code || !d_meta) return fail(KC_EINVAL, "kc_vote_i8: NULL buffer");
+    if (d_none_code && n_fields < 1) return fail(KC_EINVAL, "kc_vote_i8: none_code given but n_fields=%d", n_fields);
+    if (!d_none_code) n_fields = 1;
+    if (!aligned16(d_codes)) return fail(KC_EINVAL, "kc_vote_i8: d_codes must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (n) {
+        case 4: return launch_vote_i8<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 8: return launch_vote_i8<8, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 16: return launch_vote_i8<16, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 32: return launch_vote_i8<32, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        case 64: return launch_vote_i8<64, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+        default: break;
+    }
+    if (n < 4) return launch_vote_i8<4, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 8) return launch_vote_i8<8, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 16) return launch_vote_i8<16, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    if (n < 32) return launch_vote_i8<32, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+    return launch_vote_i8<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st);
+}
+
 int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
                    uint32_t *d_meta, void *stream) {
     return kc_numeric_f64_ex(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, KC_OUT_LOCAL, stream);
@@ -492,10 +534,32 @@ void kc_host_free(void *p) {
 
 // ---------------------------------------------------------------- end-to-end with host buffers
 
+static int consensus_host_impl(const void *h_codes_v, int code_bytes, int32_t n_vote_fields, const int32_t *h_none_code,
+                               const double *h_vals, int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps,
+                               double abs_eps, int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value,
+                               uint32_t *h_num_meta, int device, float *device_ms);
+
 int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
                       int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
                       int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device,
                       float *device_ms) {
+    return consensus_host_impl(h_codes, 4, n_vote_fields, h_none_code, h_vals, n_num_fields, n_records, n, rel_eps, abs_eps,
+                               h_win_code, h_vote_meta, h_value, h_num_meta, device, device_ms);
+}
+
+int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int32_t *h_none_code, const double *h_vals,
+                         int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
+                         int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device,
+                         float *device_ms) {
+    return consensus_host_impl(h_codes, 1, n_vote_fields, h_none_code, h_vals, n_num_fields, n_records, n, rel_eps, abs_eps,
+                               h_win_code, h_vote_meta, h_value, h_num_meta, device, device_ms);
+}
+
+static int consensus_host_impl(const void *h_codes_v, int code_bytes, int32_t n_vote_fields, const int32_t *h_none_code,
+                               const double *h_vals, int32_t n_num_fields, int64_t n_records, int32_t n, double rel_eps,
+                               double abs_eps, int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value,
+                               uint32_t *h_num_meta, int device, float *device_ms) {
+    const uint8_t *h_codes = static_cast<const uint8_t *>(h_codes_v);
     if (device_ms) *device_ms = 0.0f;
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_consensus_host: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_records < 0 || n_vote_fields < 0 || n_num_fields < 0) return fail(KC_EINVAL, "kc_consensus_host: negative size");
@@ -520,13 +584,13 @@ int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32
         cx.device = device;
     }
     // chunk: ~48 MiB of input per stream buffer keeps H2D, kernels and D2H of neighbouring chunks overlapped
-    const size_t rec_in = (size_t)n * ((size_t)n_vote_fields * 4 + (size_t)n_num_fields * 8);
+    const size_t rec_in = (size_t)n * ((size_t)n_vote_fields * code_bytes + (size_t)n_num_fields * 8);
     int64_t chunk = std::max<int64_t>(1024, (int64_t)((48u << 20) / std::max<size_t>(rec_in, 1)));
     chunk = std::min<int64_t>(chunk, n_records);
     chunk = (chunk + 255) / 256 * 256;
     for (int s = 0; s < HostCtx::kStreams && !rc; ++s) {
         if (n_vote_fields) {
-            rc = cx.codes[s].reserve((size_t)chunk * n_vote_fields * n * 4);
+            rc = cx.codes[s].reserve((size_t)chunk * n_vote_fields * n * code_bytes);
             if (!rc) rc = cx.win[s].reserve((size_t)chunk * n_vote_fields * 4);
             if (!rc) rc = cx.vmeta[s].reserve((size_t)chunk * n_vote_fields * 4);
         }
@@ -564,9 +628,12 @@ int kc_consensus_host(const int32_t *h_codes, int32_t n_vote_fields, const int32
         cudaError_t e = cudaSuccess;
         if (n_vote_fields) {
             const int64_t G = nr * n_vote_fields;
-            e = cudaMemcpyAsync(cx.codes[s].as<int32_t>(), h_codes + r0 * n_vote_fields * n, (size_t)G * n * 4, cudaMemcpyHostToDevice, st);
+            e = cudaMemcpyAsync(cx.codes[s].p, h_codes + (size_t)r0 * n_vote_fields * n * code_bytes, (size_t)G * n * code_bytes,
+                                cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) {
-                rc = kc_vote_i32(cx.codes[s].as<int32_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st);
+                rc = code_bytes == 1
+                         ? kc_vote_i8(cx.codes[s].as<int8_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st)
+                         : kc_vote_i32(cx.codes[s].as<int32_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st);
                 if (rc) break;
                 e = cudaMemcpyAsync(h_win_code + r0 * n_vote_fields, cx.win[s].as<int32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
             }

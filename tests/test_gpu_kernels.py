@@ -267,3 +267,31 @@ def test_config4_logprob_pipeline_n32():
     assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
     ref64 = np.add.reduceat(lp.astype(np.float64), offsets[:-1])
     assert np.max(np.abs(exp_sums - ref64)) < 1e-4
+
+
+@pytest.mark.parametrize("n", [3, 4, 8, 16, 32, 64])
+def test_vote_i8_equals_i32(n):
+    """Compact int8 cells are a lossless input format: same outputs as the int32 path and as the oracle."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(900 + n)
+    F = 5
+    codes = random_codes(rng, F * 2003, n, 7)
+    none_code = np.array([-1, 0, 3, -1, -1], dtype=np.int32)
+    for nc in (None, none_code):
+        ew, em = OC.vote(codes, nc)
+        d_nc = torch.from_numpy(nc).cuda() if nc is not None else None
+        win, meta = K.vote_i8(torch.from_numpy(codes.astype(np.int8)).cuda(), d_nc)
+        assert np.array_equal(win.cpu().numpy(), ew)
+        assert np.array_equal(meta.cpu().numpy().view(np.uint32), em)
+
+
+def test_host_entry_int8_cells():
+    from k_llms_b200 import _native as K
+    from k_llms_b200 import synth
+    codes, none_code, vals = synth.s32_numpy(50_003, 16, 9)
+    a = K.consensus_host(codes, none_code, vals)
+    b = K.consensus_host(codes.astype(np.int8), none_code, vals)
+    for k in ("win_code", "vote_meta", "num_meta"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(a["value"].view(np.uint64), b["value"].view(np.uint64))
