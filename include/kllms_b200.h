@@ -172,6 +172,23 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
                          int32_t *h_win_code, uint32_t *h_vote_meta, double *h_value, uint32_t *h_num_meta, int device,
                          float *device_ms);
 
+/*
+ * H1 — native columnariser / decoder for FLAT records: for each record, n candidate JSON texts in ->
+ * consensus JSON text + likelihoods JSON text out, multi-threaded on the host with K1/K2 in between.  Replaces, for such
+ * records, the Python around the hot path: _safe_parse_content (consolidation.py:25-38), the dict part of
+ * recursive_list_alignments (consensus_utils.py:516-548: keys sorted, missing -> None), the dispatcher
+ * (consensus_utils.py:1376-1454), sanitize_value (:925-933) and _format_consensus_content (consolidation.py:41-60).
+ *   texts   [n_records * n] candidate contents (record-major); lens [n_records * n] byte lengths or NULL (NUL-terminated)
+ *   out_content / out_likelihoods [n_records] malloc'ed NUL-terminated strings (free with kc_free_strings), byte-identical
+ *           to the reference's json.dumps output; out_status [n_records]: 0 = consolidated here, 1 = not expressible as
+ *           scalar groups (nested values, multi-word strings, non-ASCII, empty content, ...) -> caller uses the Python path
+ *   threads <= 0: all hardware threads.  Blocks until done.
+ */
+int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, double rel_eps,
+                        double abs_eps, int device, int32_t threads, char **out_content, char **out_likelihoods,
+                        uint8_t *out_status);
+void kc_free_strings(char **arr, int64_t count);
+
 void *kc_host_alloc(uint64_t bytes); /* page-locked host memory, NULL on failure */
 void kc_host_free(void *p);
 

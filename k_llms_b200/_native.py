@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM = 0, 1
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -65,12 +65,16 @@ def load() -> ctypes.CDLL:
     lib.kc_consensus_host.argtypes = [vp, i32, vp, vp, i32, i64, i32, f64, f64, vp, vp, vp, vp, c.c_int, vp]
     lib.kc_consensus_host_i8.argtypes = lib.kc_consensus_host.argtypes
     lib.kc_vote_i8.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
+    lib.kc_consolidate_json.argtypes = [vp, vp, i64, i32, f64, f64, c.c_int, i32, vp, vp, vp]
+    lib.kc_consolidate_json.restype = c.c_int
+    lib.kc_free_strings.argtypes = [vp, i64]
+    lib.kc_free_strings.restype = None
     lib.kc_host_alloc.argtypes = [c.c_uint64]
     lib.kc_host_alloc.restype = vp
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -222,6 +226,35 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     check(entry(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
                 p(value), p(nmeta), device, ctypes.addressof(ms)))
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
+
+
+def consolidate_json(records, rel_eps: float = 0.03, abs_eps: float = 1e-6, device: int = 0, threads: int = 0):
+    """H1: native consolidation of FLAT records.  records: list of lists of n candidate content strings.
+    Returns a list of (content_str, likelihoods_json_str) or None where the record needs the Python path."""
+    lib = load()
+    R = len(records)
+    if R == 0:
+        return []
+    n = len(records[0])
+    assert all(len(r) == n for r in records), "every record needs the same number of candidates"
+    blobs = [t.encode("utf-8") for r in records for t in r]
+    texts = (ctypes.c_char_p * (R * n))(*blobs)
+    lens = (ctypes.c_int64 * (R * n))(*[len(b) for b in blobs])
+    out_c = (ctypes.c_void_p * R)()
+    out_l = (ctypes.c_void_p * R)()
+    status = (ctypes.c_uint8 * R)()
+    check(lib.kc_consolidate_json(ctypes.cast(texts, ctypes.c_void_p), ctypes.cast(lens, ctypes.c_void_p), R, n, float(rel_eps),
+                                  float(abs_eps), device, threads, ctypes.cast(out_c, ctypes.c_void_p),
+                                  ctypes.cast(out_l, ctypes.c_void_p), ctypes.cast(status, ctypes.c_void_p)))
+    res = []
+    for i in range(R):
+        if status[i] == 0:
+            res.append((ctypes.string_at(out_c[i]).decode("ascii"), ctypes.string_at(out_l[i]).decode("ascii")))
+        else:
+            res.append(None)
+    lib.kc_free_strings(ctypes.cast(out_c, ctypes.c_void_p), R)
+    lib.kc_free_strings(ctypes.cast(out_l, ctypes.c_void_p), R)
+    return res
 
 
 def pinned_empty(shape, dtype):

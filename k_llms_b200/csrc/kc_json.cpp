@@ -1,0 +1,668 @@
+// kc_json.cpp — H1: native host columnariser / decoder.
+//
+// kc_consolidate_json(): for every record, n candidate JSON texts in -> consensus JSON text + likelihoods JSON text out,
+// with only the CUDA kernels in between.  It does, in C++ and multi-threaded, what the reference does per request in
+// Python around the hot path:
+//     _safe_parse_content            consolidation.py:25-38   (json.loads, or {"text": content})
+//     recursive_list_alignments      consensus_utils.py:516-548 (dict part: every candidate gets every key, keys SORTED)
+//     consensus_values dispatcher    consensus_utils.py:1376-1454 (flat records: scalar fields only)
+//     sanitize_value / `v or False`  consensus_utils.py:925-933, 956   -> local dictionary codes (int8 cells)
+//     _format_consensus_content      consolidation.py:41-60   (json.dumps of the consensus; {"text": s} -> s)
+// Records it cannot express as scalar groups (nested dicts / lists, multi-word strings that need the similarity medoid,
+// non-ASCII text, mixed-type bool groups) are NOT guessed at: they get status 1 and the Python path handles them.
+//
+// Text formats follow CPython exactly: float -> float.__repr__ (shortest round-trip digits, exponent form outside
+// 1e-4 <= |x| < 1e16, always a fractional part), json.dumps separators ", " / ": " and ensure_ascii escaping.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <vector>
+
+#include "../../include/kllms_b200.h"
+
+namespace {
+
+enum TokType : uint8_t { T_MISSING = 0, T_NULL, T_TRUE, T_FALSE, T_INT, T_FLOAT, T_STR, T_NESTED };
+
+struct Tok {
+    TokType type = T_MISSING;
+    double num = 0.0;      // T_INT / T_FLOAT value (strtod: correctly rounded, like float(int) / float(text))
+    std::string text;      // T_STR: unescaped value; T_INT: canonical decimal digits (Python str(int))
+};
+
+struct Candidate {
+    std::vector<std::pair<std::string, Tok>> items;  // in text order; later duplicates override earlier ones
+    bool ok = true;                                  // false: not a flat ASCII JSON object
+};
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+// str.split() / str.strip() whitespace within ASCII: \t \n \v \f \r, \x1c-\x1f and space
+inline bool is_py_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+
+struct Scanner {
+    const char *p, *end;
+    bool non_ascii = false;
+    void ws() {
+        while (p < end && is_ws(*p)) ++p;
+    }
+    bool lit(const char *s) {
+        const size_t n = strlen(s);
+        if ((size_t)(end - p) >= n && memcmp(p, s, n) == 0) {
+            p += n;
+            return true;
+        }
+        return false;
+    }
+    bool string(std::string &out) {  // at opening quote
+        ++p;
+        out.clear();
+        while (p < end) {
+            const unsigned char c = (unsigned char)*p;
+            if (c == '"') {
+                ++p;
+                return true;
+            }
+            if (c < 0x20) return false;  // json.loads(strict=True) rejects raw control characters
+            if (c >= 0x80) non_ascii = true;
+            if (c != '\\') {
+                out.push_back((char)c);
+                ++p;
+                continue;
+            }
+            if (++p >= end) return false;
+            switch (*p++) {
+                case '"': out.push_back('"'); break;
+                case '\\': out.push_back('\\'); break;
+                case '/': out.push_back('/'); break;
+                case 'b': out.push_back('\b'); break;
+                case 'f': out.push_back('\f'); break;
+                case 'n': out.push_back('\n'); break;
+                case 'r': out.push_back('\r'); break;
+                case 't': out.push_back('\t'); break;
+                case 'u': {
+                    if (end - p < 4) return false;
+                    unsigned v = 0;
+                    for (int i = 0; i < 4; ++i) {
+                        const char h = p[i];
+                        v <<= 4;
+                        if (h >= '0' && h <= '9') v |= (unsigned)(h - '0');
+                        else if (h >= 'a' && h <= 'f') v |= (unsigned)(h - 'a' + 10);
+                        else if (h >= 'A' && h <= 'F') v |= (unsigned)(h - 'A' + 10);
+                        else return false;
+                    }
+                    p += 4;
+                    if (v >= 0x80) non_ascii = true;  // parity for non-ASCII text is unpinned: hand the record to Python
+                    out.push_back((char)(v & 0x7F));
+                    break;
+                }
+                default: return false;
+            }
+        }
+        return false;
+    }
+    bool skip_nested() {  // at '{' or '[': skip a balanced value
+        int depth = 0;
+        std::string tmp;
+        while (p < end) {
+            const char c = *p;
+            if (c == '"') {
+                if (!string(tmp)) return false;
+                continue;
+            }
+            if (c == '{' || c == '[') ++depth;
+            if (c == '}' || c == ']') {
+                --depth;
+                if (depth == 0) {
+                    ++p;
+                    return true;
+                }
+            }
+            ++p;
+        }
+        return false;
+    }
+    bool number(Tok &t) {
+        const char *s = p;
+        if (p < end && *p == '-') ++p;
+        if (p >= end) return false;
+        if (*p == '0') {
+            ++p;
+        } else if (*p >= '1' && *p <= '9') {
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        } else {
+            return false;
+        }
+        bool is_float = false;
+        if (p < end && *p == '.') {
+            ++p;
+            if (p >= end || *p < '0' || *p > '9') return false;
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+            is_float = true;
+        }
+        if (p < end && (*p == 'e' || *p == 'E')) {
+            const char *q = p + 1;
+            if (q < end && (*q == '+' || *q == '-')) ++q;
+            if (q < end && *q >= '0' && *q <= '9') {
+                while (q < end && *q >= '0' && *q <= '9') ++q;
+                p = q;
+                is_float = true;
+            }
+        }
+        std::string txt(s, p);
+        t.num = strtod(txt.c_str(), nullptr);
+        if (is_float) {
+            t.type = T_FLOAT;
+        } else {
+            t.type = T_INT;
+            size_t i = 0;  // canonical str(int): no "-0", no other normalisation needed (JSON forbids leading zeros)
+            if (txt == "-0") txt = "0";
+            (void)i;
+            t.text = std::move(txt);
+        }
+        return true;
+    }
+    bool value(Tok &t) {
+        ws();
+        if (p >= end) return false;
+        const char c = *p;
+        if (c == '"') {
+            t.type = T_STR;
+            return string(t.text);
+        }
+        if (c == '{' || c == '[') {
+            t.type = T_NESTED;
+            return skip_nested();
+        }
+        if (lit("true")) { t.type = T_TRUE; return true; }
+        if (lit("false")) { t.type = T_FALSE; return true; }
+        if (lit("null")) { t.type = T_NULL; return true; }
+        if (lit("NaN")) { t.type = T_FLOAT; t.num = NAN; return true; }
+        if (lit("Infinity")) { t.type = T_FLOAT; t.num = INFINITY; return true; }
+        if (lit("-Infinity")) { t.type = T_FLOAT; t.num = -INFINITY; return true; }
+        return number(t);
+    }
+};
+
+// json.loads(text) for a flat object; anything else that json.loads would ACCEPT (top-level list, number, ...) is
+// reported through `not_object`; a parse failure means the reference wraps the text (consolidation.py:37-38).
+bool parse_object(const char *s, size_t len, Candidate &out, bool &not_object, bool &non_ascii) {
+    Scanner sc{s, s + len};
+    not_object = false;
+    sc.ws();
+    if (sc.p >= sc.end) return false;
+    if (*sc.p != '{') {
+        Tok t;
+        const bool ok = sc.value(t);
+        sc.ws();
+        if (ok && sc.p == sc.end) not_object = true;
+        non_ascii = sc.non_ascii;
+        return ok && sc.p == sc.end;
+    }
+    ++sc.p;
+    sc.ws();
+    if (sc.p < sc.end && *sc.p == '}') {
+        ++sc.p;
+    } else {
+        for (;;) {
+            sc.ws();
+            if (sc.p >= sc.end || *sc.p != '"') return false;
+            std::string key;
+            if (!sc.string(key)) return false;
+            sc.ws();
+            if (sc.p >= sc.end || *sc.p != ':') return false;
+            ++sc.p;
+            Tok t;
+            if (!sc.value(t)) return false;
+            out.items.emplace_back(std::move(key), std::move(t));
+            sc.ws();
+            if (sc.p < sc.end && *sc.p == ',') {
+                ++sc.p;
+                continue;
+            }
+            if (sc.p < sc.end && *sc.p == '}') {
+                ++sc.p;
+                break;
+            }
+            return false;
+        }
+    }
+    sc.ws();
+    non_ascii = sc.non_ascii;
+    return sc.p == sc.end;
+}
+
+// ---------------------------------------------------------------- CPython text formats
+
+// float.__repr__: shortest round-trip digits; fixed notation for -4 <= exponent10 < 16, else d[.ddd]e+XX.
+void py_float_repr(double x, std::string &out) {
+    if (std::isnan(x)) { out += "nan"; return; }
+    if (std::isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+    char buf[40];
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);  // shortest digits: d[.ddd]e+XX
+    std::string_view sv(buf, (size_t)(r.ptr - buf));
+    size_t i = 0;
+    if (sv[i] == '-') { out.push_back('-'); ++i; }
+    const size_t epos = sv.find('e');
+    std::string digits;
+    for (size_t k = i; k < epos; ++k)
+        if (sv[k] != '.') digits.push_back(sv[k]);
+    const int exp10 = atoi(std::string(sv.substr(epos + 1)).c_str());
+    const int decpt = exp10 + 1;  // position of the decimal point relative to the digit string
+    const int nd = (int)digits.size();
+    if (decpt > 16 || decpt < -3) {
+        out.push_back(digits[0]);
+        if (nd > 1) {
+            out.push_back('.');
+            out.append(digits, 1, std::string::npos);
+        }
+        out.push_back('e');
+        const int e = decpt - 1;
+        out.push_back(e < 0 ? '-' : '+');
+        const int ae = e < 0 ? -e : e;
+        if (ae < 10) out.push_back('0');
+        out += std::to_string(ae);
+    } else if (decpt <= 0) {
+        out += "0.";
+        out.append((size_t)(-decpt), '0');
+        out += digits;
+    } else if (decpt >= nd) {
+        out += digits;
+        out.append((size_t)(decpt - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, 0, (size_t)decpt);
+        out.push_back('.');
+        out.append(digits, (size_t)decpt, std::string::npos);
+    }
+}
+
+// json.dumps float: repr, but NaN / Infinity / -Infinity spelled the JSON way
+void json_float(double x, std::string &out) {
+    if (std::isnan(x)) out += "NaN";
+    else if (std::isinf(x)) out += x < 0 ? "-Infinity" : "Infinity";
+    else py_float_repr(x, out);
+}
+
+// json.dumps(str) with ensure_ascii=True (input is ASCII)
+void json_string(const std::string &s, std::string &out) {
+    static const char *hex = "0123456789abcdef";
+    out.push_back('"');
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\n': out += "\\n"; break;
+            case '\r': out += "\\r"; break;
+            case '\t': out += "\\t"; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if (c < 0x20) {
+                    out += "\\u00";
+                    out.push_back(hex[c >> 4]);
+                    out.push_back(hex[c & 15]);
+                } else {
+                    out.push_back((char)c);
+                }
+        }
+    }
+    out.push_back('"');
+}
+
+// str(v) as Python prints the value (for the enum-likeness test and for sanitising)
+void py_str(const Tok &t, std::string &out) {
+    switch (t.type) {
+        case T_TRUE: out += "True"; break;
+        case T_FALSE: out += "False"; break;
+        case T_INT: out += t.text; break;
+        case T_FLOAT: py_float_repr(t.num, out); break;
+        case T_STR: out += t.text; break;
+        default: break;
+    }
+}
+
+int word_count(const std::string &s) {  // len(s.strip().split())
+    int n = 0;
+    bool in = false;
+    for (unsigned char c : s) {
+        const bool sp = is_py_space(c);
+        if (!sp && !in) ++n;
+        in = !sp;
+    }
+    return n;
+}
+
+void sanitize(const std::string &s, std::string &out) {  // consensus_utils.py:925-933 on ASCII
+    out.clear();
+    for (unsigned char c : s) {
+        if (c >= 'A' && c <= 'Z') c = (unsigned char)(c + 32);
+        if ((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9')) out.push_back((char)c);
+    }
+}
+
+void json_value(const Tok &t, std::string &out) {
+    switch (t.type) {
+        case T_TRUE: out += "true"; break;
+        case T_FALSE: out += "false"; break;
+        case T_INT: out += t.text; break;
+        case T_FLOAT: json_float(t.num, out); break;
+        case T_STR: json_string(t.text, out); break;
+        default: out += "null"; break;
+    }
+}
+
+// ---------------------------------------------------------------- per-record plan
+
+enum GroupKind : uint8_t { G_ALLNULL = 0, G_VOTE_STR, G_VOTE_BOOL, G_NUMERIC };
+
+struct Group {
+    GroupKind kind;
+    std::string key;
+    std::vector<Tok> cells;  // n tokens (T_MISSING / T_NULL count as None)
+    int64_t row = -1;        // row in the vote / numeric cell matrix
+};
+
+struct Record {
+    uint8_t status = 0;  // 0 native, 1 needs the Python path
+    std::vector<Group> groups;
+};
+
+const double kF64None = [] { const uint64_t b = KC_F64_NONE_BITS; double d; memcpy(&d, &b, 8); return d; }();
+
+void plan_record(const char *const *texts, const int64_t *lens, int n, Record &rec) {
+    std::vector<Candidate> cands((size_t)n);
+    for (int c = 0; c < n; ++c) {
+        const char *s = texts[c];
+        const size_t len = lens ? (size_t)lens[c] : strlen(s);
+        if (len == 0) {  // `if choice.message.content:` drops empty contents, changing n (consolidation.py:92): Python path
+            rec.status = 1;
+            return;
+        }
+        bool not_object = false, non_ascii = false;
+        Candidate cand;
+        const bool ok = parse_object(s, len, cand, not_object, non_ascii);
+        for (size_t i = 0; i < len && !non_ascii; ++i)
+            if ((unsigned char)s[i] >= 0x80) non_ascii = true;
+        if (non_ascii || (ok && not_object)) {
+            rec.status = 1;
+            return;
+        }
+        if (!ok) {  // {"text": content}
+            cand.items.clear();
+            Tok t;
+            t.type = T_STR;
+            t.text.assign(s, len);
+            cand.items.emplace_back("text", std::move(t));
+        }
+        cands[(size_t)c] = std::move(cand);
+    }
+    std::vector<std::string> keys;
+    for (auto &c : cands)
+        for (auto &kv : c.items) keys.push_back(kv.first);
+    std::sort(keys.begin(), keys.end());  // code-point order == byte order for ASCII (consensus_utils.py:521-522)
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    for (auto &key : keys) {
+        if (key.find("reasoning___") != std::string::npos || key.find("source___") != std::string::npos) continue;  // cu:1292
+        Group g;
+        g.key = key;
+        g.cells.resize((size_t)n);
+        for (int c = 0; c < n; ++c)
+            for (auto &kv : cands[(size_t)c].items)
+                if (kv.first == key) g.cells[(size_t)c] = kv.second;  // later duplicates win, like dict construction
+        const Tok *first = nullptr;
+        for (auto &t : g.cells)
+            if (t.type > T_NULL) {
+                first = &t;
+                break;
+            }
+        if (!first) {
+            g.kind = G_ALLNULL;
+        } else if (first->type == T_NESTED) {
+            rec.status = 1;
+            return;
+        } else if (first->type == T_STR || first->type == T_TRUE || first->type == T_FALSE) {
+            std::string tmp;
+            for (auto &t : g.cells) {
+                if (t.type <= T_NULL) continue;
+                if (t.type == T_NESTED) {  // str(dict) is almost never enum-like: leave it to Python
+                    rec.status = 1;
+                    return;
+                }
+                tmp.clear();
+                py_str(t, tmp);
+                if (word_count(tmp) >= 3) {  // not enum-like -> similarity medoid (host)
+                    rec.status = 1;
+                    return;
+                }
+            }
+            if (first->type == T_STR) {
+                g.kind = G_VOTE_STR;
+            } else {
+                for (auto &t : g.cells)  // `v or False` on non-bool values compares Python objects: Python path
+                    if (t.type != T_MISSING && t.type != T_NULL && t.type != T_TRUE && t.type != T_FALSE) {
+                        rec.status = 1;
+                        return;
+                    }
+                g.kind = G_VOTE_BOOL;
+            }
+        } else {
+            g.kind = G_NUMERIC;
+        }
+        rec.groups.push_back(std::move(g));
+    }
+}
+
+void encode_vote(const Group &g, int n, int8_t *cells) {
+    std::vector<std::string> seen;
+    std::string tmp, san;
+    for (int c = 0; c < n; ++c) {
+        const Tok &t = g.cells[(size_t)c];
+        if (g.kind == G_VOTE_BOOL) {
+            cells[c] = (t.type == T_TRUE) ? 1 : 0;  // None and False -> False (cu:956)
+            continue;
+        }
+        if (t.type <= T_NULL) {
+            cells[c] = KC_CODE_NONE;
+            continue;
+        }
+        tmp.clear();
+        py_str(t, tmp);
+        sanitize(tmp, san);
+        size_t k = 0;
+        while (k < seen.size() && seen[k] != san) ++k;
+        if (k == seen.size()) seen.push_back(san);
+        cells[c] = (int8_t)k;
+    }
+}
+
+void encode_numeric(const Group &g, int n, double *cells) {
+    for (int c = 0; c < n; ++c) {
+        const Tok &t = g.cells[(size_t)c];
+        if (t.type <= T_NULL) cells[c] = kF64None;
+        else if (t.type == T_INT || t.type == T_FLOAT) cells[c] = t.num;  // non-finite values are dropped by the kernel
+        else cells[c] = NAN;                                               // bool / str / nested: counted, never clustered
+    }
+}
+
+// CPython round(x, 5) on the host (same algorithm as kc::py_round5): exact value * 1e5, half-even, one division
+double py_round5(double x) {
+    if (!(x > 0.0) || !std::isfinite(x)) return x;
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    const int biased = (int)((bits >> 52) & 0x7FF);
+    uint64_t mant = bits & 0xFFFFFFFFFFFFFull;
+    int exp2;
+    if (biased == 0) exp2 = -1074;
+    else { mant |= 1ull << 52; exp2 = biased - 1075; }
+    if (exp2 >= 0) return x;
+    const int sh = -exp2;
+    if (sh >= 128) return 0.0;
+    const unsigned __int128 prod = (unsigned __int128)mant * 100000u;
+    unsigned __int128 q = prod >> sh;
+    const unsigned __int128 rem = prod - (q << sh);
+    const unsigned __int128 half = (unsigned __int128)1 << (sh - 1);
+    if (rem > half || (rem == half && (q & 1))) ++q;
+    return (double)(uint64_t)q / 100000.0;
+}
+
+void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, std::string &content,
+                 std::string &lik) {
+    content = "{";
+    lik = "{";
+    bool first = true;
+    const Tok *single_text = nullptr;
+    for (const Group &g : rec.groups) {
+        if (!first) {
+            content += ", ";
+            lik += ", ";
+        }
+        first = false;
+        json_string(g.key, content);
+        json_string(g.key, lik);
+        content += ": ";
+        lik += ": ";
+        double conf = 0.0;
+        Tok value;  // T_MISSING == None
+        if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) {
+            const uint32_t m = vmeta[g.row];
+            const uint32_t idx = KC_META_IDX(m), support = KC_META_SUPPORT(m), present = KC_META_PRESENT(m);
+            if (g.kind == G_VOTE_BOOL) {
+                value.type = (g.cells[idx].type == T_TRUE) ? T_TRUE : T_FALSE;  // the processed key (cu:958)
+            } else {
+                value = g.cells[idx];  // first original whose sanitised form wins (cu:971)
+            }
+            conf = py_round5(1.0 * ((double)support / (double)present));
+        } else if (g.kind == G_NUMERIC) {
+            const uint32_t m = nmeta[g.row];
+            const uint32_t idx = KC_META_IDX(m), support = KC_META_SUPPORT(m), nn = KC_META_NN(m), present = KC_META_PRESENT(m);
+            const uint32_t flags = KC_META_FLAGS(m);
+            if (flags & KC_FLAG_HAS_VALUE) {
+                if (flags & KC_FLAG_SINGLE) {
+                    value = g.cells[idx];
+                    conf = 1.0 * (1.0 / (double)present) * (1.0 / 1.0);
+                } else {
+                    value.type = T_FLOAT;
+                    value.num = nvalue[g.row];
+                    conf = py_round5((double)support / (double)nn);
+                }
+            } else if (flags & KC_FLAG_NO_FINITE) {
+                conf = 1.0 * ((double)nn / (double)present);
+            } else {
+                conf = present == 0 ? 1.0 : 0.0;
+            }
+        }  // G_ALLNULL: None, 0.0 (cu:1401-1402)
+        json_value(value, content);
+        json_float(conf, lik);
+        if (rec.groups.size() == 1 && g.key == "text" && value.type == T_STR) single_text = &g.cells[KC_META_IDX(vmeta[g.row])];
+    }
+    content += "}";
+    lik += "}";
+    (void)n;
+    if (single_text) content = single_text->text;  // {"text": s} -> s (consolidation.py:55-57)
+}
+
+char *dup_string(const std::string &s) {
+    char *p = (char *)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+template <typename F>
+void parallel_for(int64_t n, int threads, F fn) {
+    std::atomic<int64_t> next{0};
+    const int64_t grain = 256;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int64_t b = next.fetch_add(grain);
+                if (b >= n) return;
+                const int64_t e = std::min(n, b + grain);
+                for (int64_t i = b; i < e; ++i) fn(i);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, double rel_eps,
+                        double abs_eps, int device, int32_t threads, char **out_content, char **out_likelihoods,
+                        uint8_t *out_status) {
+    if (n < 2 || n > KC_MAX_CANDIDATES || n_records < 0 || !texts || !out_content || !out_likelihoods || !out_status)
+        return KC_EINVAL;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<Record> recs((size_t)n_records);
+    parallel_for(n_records, threads, [&](int64_t r) { plan_record(texts + r * n, lens ? lens + r * n : nullptr, n, recs[(size_t)r]); });
+
+    int64_t gv = 0, gx = 0;
+    for (auto &rec : recs) {
+        if (rec.status) continue;
+        for (auto &g : rec.groups) {
+            if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) g.row = gv++;
+            else if (g.kind == G_NUMERIC) g.row = gx++;
+        }
+    }
+    int8_t *h_codes = gv ? (int8_t *)kc_host_alloc((uint64_t)gv * n) : nullptr;
+    double *h_vals = gx ? (double *)kc_host_alloc((uint64_t)gx * n * 8) : nullptr;
+    int32_t *h_win = gv ? (int32_t *)kc_host_alloc((uint64_t)gv * 4) : nullptr;
+    uint32_t *h_vmeta = gv ? (uint32_t *)kc_host_alloc((uint64_t)gv * 4) : nullptr;
+    double *h_value = gx ? (double *)kc_host_alloc((uint64_t)gx * 8) : nullptr;
+    uint32_t *h_nmeta = gx ? (uint32_t *)kc_host_alloc((uint64_t)gx * 4) : nullptr;
+    int rc = KC_OK;
+    if ((gv && (!h_codes || !h_win || !h_vmeta)) || (gx && (!h_vals || !h_value || !h_nmeta))) rc = KC_ENOMEM;
+    if (!rc) {
+        parallel_for(n_records, threads, [&](int64_t r) {
+            const Record &rec = recs[(size_t)r];
+            if (rec.status) return;
+            for (auto &g : rec.groups) {
+                if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) encode_vote(g, n, h_codes + g.row * n);
+                else if (g.kind == G_NUMERIC) encode_numeric(g, n, h_vals + g.row * n);
+            }
+        });
+        // one "field" per group: the two halves are independent calls of the host-buffer entry
+        if (gv) rc = kc_consensus_host_i8(h_codes, 1, nullptr, nullptr, 0, gv, n, rel_eps, abs_eps, h_win, h_vmeta, nullptr, nullptr, device, nullptr);
+        if (!rc && gx) rc = kc_consensus_host_i8(nullptr, 0, nullptr, h_vals, 1, gx, n, rel_eps, abs_eps, nullptr, nullptr, h_value, h_nmeta, device, nullptr);
+    }
+    if (!rc) {
+        parallel_for(n_records, threads, [&](int64_t r) {
+            const Record &rec = recs[(size_t)r];
+            out_status[r] = rec.status;
+            out_content[r] = nullptr;
+            out_likelihoods[r] = nullptr;
+            if (rec.status) return;
+            std::string content, lik;
+            emit_record(rec, n, h_vmeta, h_value, h_nmeta, content, lik);
+            out_content[r] = dup_string(content);
+            out_likelihoods[r] = dup_string(lik);
+        });
+    }
+    kc_host_free(h_codes);
+    kc_host_free(h_vals);
+    kc_host_free(h_win);
+    kc_host_free(h_vmeta);
+    kc_host_free(h_value);
+    kc_host_free(h_nmeta);
+    return rc;
+}
+
+void kc_free_strings(char **arr, int64_t count) {
+    if (!arr) return;
+    for (int64_t i = 0; i < count; ++i) {
+        free(arr[i]);
+        arr[i] = nullptr;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""GPU parity for H1 (native JSON in -> consensus JSON out): byte-identical to the reference's client order
+(align + consensus + json.dumps), which the object-level oracle restates (oracle/consensus_py.client_order)."""
+import json
+import random
+
+import pytest
+
+from oracle import consensus_py as O
+from tests.helpers import raising_embeddings
+
+pytestmark = pytest.mark.gpu
+
+WORDS = ["alpha", "Bravo", "charlie", "DELTA", "echo", "fox-trot", "golf", "Hotel", "", "a b", "x\ty", 'q"uote', "back\\slash", "nl\n"]
+
+
+def _expected(texts):
+    from k_llms_b200.utils.consolidation import _format_consensus_content, _safe_parse_content
+    contents = [_safe_parse_content(t) for t in texts if t]
+    value, conf = O.client_order(contents, embed=raising_embeddings)
+    return _format_consensus_content(value), json.dumps(conf)
+
+
+def _random_record(rng, n):
+    n_fields = rng.randrange(1, 7)
+    kinds = [rng.choice(["str", "bool", "int", "float", "near", "big", "mixnum"]) for _ in range(n_fields)]
+    truth = {}
+    for f, k in enumerate(kinds):
+        truth[f] = {"str": lambda: rng.choice(WORDS), "bool": lambda: rng.random() < 0.5,
+                    "int": lambda: rng.randrange(-50, 10 ** rng.randrange(1, 8)), "float": lambda: rng.uniform(-1e3, 1e5),
+                    "near": lambda: rng.choice([1.0, 100.0, 1e-5, 1e16, 123456789.125, 0.0, -0.0]),
+                    "big": lambda: rng.choice([10 ** 30, 2 ** 63, -(10 ** 25), 10 ** 400]),
+                    "mixnum": lambda: rng.choice([1, 1.0, 2, 2.5])}[k]()
+    texts = []
+    for _ in range(n):
+        d = {}
+        for f, k in enumerate(kinds):
+            r = rng.random()
+            if r < 0.08:
+                continue  # key missing
+            v = truth[f]
+            if r < 0.3:
+                v = {"str": lambda: rng.choice(WORDS).upper(), "bool": lambda: rng.random() < 0.5,
+                     "int": lambda: rng.randrange(0, 1000), "float": lambda: rng.uniform(0, 10),
+                     "near": lambda: truth[f] * rng.choice([1.02, 0.97, 1.05, 10.0]) if isinstance(truth[f], float) else 3.0,
+                     "big": lambda: rng.choice([10 ** 30 + 1, 7]), "mixnum": lambda: rng.choice([True, "1", None, 3])}[k]()
+            if r > 0.93:
+                v = None
+            d[f"k{f}" if rng.random() > 0.02 else "reasoning___why"] = v
+        t = json.dumps(d)
+        if rng.random() < 0.03:
+            t = t.replace(", ", " ,\n ")  # odd whitespace
+        texts.append(t)
+    return texts
+
+
+def test_native_json_matches_reference_client_order():
+    from k_llms_b200 import _native as K
+    rng = random.Random(2024)
+    records = []
+    for _ in range(3000):
+        n = rng.choice([2, 3, 5, 8, 16])
+        records.append((n, _random_record(rng, n)))
+    specials = [
+        ['{"a": 1}', 'not json', '{"a": 1}'],                    # one candidate falls back to {"text": ...}
+        ['Yes', 'yes', 'No'],                                    # free text: wrapper and unwrapping
+        ['{"a": 1, "a": 2}', '{"a": 2}', '{"a": 1}'],            # duplicate keys: last one wins
+        ['{}', '{}'], ['{"x": null}', '{"x": null}'],
+        ['{"a": NaN, "b": Infinity}', '{"a": 1.5, "b": 2}', '{"a": 1.5, "b": 2}'],
+        ['{"f": 1e400}', '{"f": 3}', '{"f": 3}'], ['{"f": 1E5}', '{"f": 100000.0}', '{"f": 1e+5}'],
+        ['{"s": "a\\u0041b"}', '{"s": "aAb"}'], ['{"v": 0.1}', '{"v": 0.1}', '{"v": 0.30000000000000004}'],
+        ['{"t": true, "u": "true"}', '{"t": null, "u": true}', '{"t": false, "u": "TRUE!"}'],
+    ]
+    for s in specials:
+        records.append((len(s), s))
+    by_n = {}
+    for n, texts in records:
+        by_n.setdefault(n, []).append(texts)
+    native_count = 0
+    for n, recs in by_n.items():
+        out = K.consolidate_json(recs)
+        assert len(out) == len(recs)
+        for texts, got in zip(recs, out):
+            if got is None:
+                continue  # handed to the Python path by design (nested / multi-word / mixed bool groups ...)
+            native_count += 1
+            exp = _expected(texts)
+            assert got[0] == exp[0], (texts, got, exp)
+            assert got[1] == exp[1], (texts, got, exp)
+    assert native_count > 2500
+
+
+def test_native_json_declines_what_it_cannot_express():
+    from k_llms_b200 import _native as K
+    recs = [['{"a": {"b": 1}}', '{"a": {"b": 1}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": "x"}'],
+            ['{"a": "caf\\u00e9"}', '{"a": "cafe"}'], ['[1, 2]', '{"a": 1}'], ['', '{"a": 1}'], ['{"a": true}', '{"a": 1}']]
+    assert K.consolidate_json(recs) == [None] * len(recs)
+    ok = K.consolidate_json([['{"a": "x"}', '{"a": "X!"}']])
+    assert ok == [('{"a": "x"}', '{"a": 1.0}')]
