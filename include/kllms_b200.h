@@ -182,7 +182,7 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
  *   out_content / out_likelihoods [n_records] malloc'ed NUL-terminated strings (free with kc_free_strings), byte-identical
  *           to the reference's json.dumps output; out_status [n_records]: 0 = consolidated here, 1 = not expressible as
  *           scalar groups (nested values, multi-word strings, non-ASCII, empty content, ...) -> caller uses the Python path
- *   threads <= 0: all hardware threads.  Blocks until done.
+ *   threads <= 0: min(32, hardware threads).  Blocks until done; callers are serialised (one staging pool per process).
  */
 int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, double rel_eps,
                         double abs_eps, int device, int32_t threads, char **out_content, char **out_likelihoods,

@@ -17,11 +17,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -33,20 +36,60 @@ namespace {
 
 enum TokType : uint8_t { T_MISSING = 0, T_NULL, T_TRUE, T_FALSE, T_INT, T_FLOAT, T_STR, T_NESTED };
 
+// A token is a VIEW into the candidate text (no copies): strings keep their raw inner span and an "has escapes" flag
+// and are unescaped only where the value is needed; numbers keep their text span and the strtod value.
 struct Tok {
     TokType type = T_MISSING;
-    double num = 0.0;      // T_INT / T_FLOAT value (strtod: correctly rounded, like float(int) / float(text))
-    std::string text;      // T_STR: unescaped value; T_INT: canonical decimal digits (Python str(int))
+    bool esc = false;
+    const char *p = nullptr;
+    uint32_t len = 0;
+    double num = 0.0;  // T_INT / T_FLOAT (strtod: correctly rounded, like float(int) / float(text))
 };
 
-struct Candidate {
-    std::vector<std::pair<std::string, Tok>> items;  // in text order; later duplicates override earlier ones
-    bool ok = true;                                  // false: not a flat ASCII JSON object
+struct Item {
+    std::string_view key;
+    Tok tok;
 };
 
 inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
 // str.split() / str.strip() whitespace within ASCII: \t \n \v \f \r, \x1c-\x1f and space
 inline bool is_py_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+
+// raw inner span of a JSON string -> value (ASCII only; \uXXXX above 0x7F never gets here)
+void unescape(const char *p, uint32_t len, std::string &out) {
+    out.clear();
+    const char *e = p + len;
+    while (p < e) {
+        if (*p != '\\') {
+            out.push_back(*p++);
+            continue;
+        }
+        ++p;
+        switch (*p++) {
+            case 'b': out.push_back('\b'); break;
+            case 'f': out.push_back('\f'); break;
+            case 'n': out.push_back('\n'); break;
+            case 'r': out.push_back('\r'); break;
+            case 't': out.push_back('\t'); break;
+            case 'u': {
+                unsigned v = 0;
+                for (int i = 0; i < 4; ++i) {
+                    const char h = p[i];
+                    v = (v << 4) | (unsigned)(h <= '9' ? h - '0' : (h | 0x20) - 'a' + 10);
+                }
+                p += 4;
+                out.push_back((char)(v & 0x7F));
+                break;
+            }
+            default: out.push_back(p[-1]); break;  // \" \\ \/
+        }
+    }
+}
+
+inline void tok_string(const Tok &t, std::string &out) {  // value of a T_STR token
+    if (t.esc) unescape(t.p, t.len, out);
+    else out.assign(t.p, t.len);
+}
 
 struct Scanner {
     const char *p, *end;
@@ -54,68 +97,62 @@ struct Scanner {
     void ws() {
         while (p < end && is_ws(*p)) ++p;
     }
-    bool lit(const char *s) {
-        const size_t n = strlen(s);
+    bool lit(const char *s, size_t n) {
         if ((size_t)(end - p) >= n && memcmp(p, s, n) == 0) {
             p += n;
             return true;
         }
         return false;
     }
-    bool string(std::string &out) {  // at opening quote
+    // at the opening quote: validates, reports the raw inner span
+    bool string(const char *&sp, uint32_t &slen, bool &esc) {
         ++p;
-        out.clear();
+        sp = p;
+        esc = false;
         while (p < end) {
             const unsigned char c = (unsigned char)*p;
             if (c == '"') {
+                slen = (uint32_t)(p - sp);
                 ++p;
                 return true;
             }
             if (c < 0x20) return false;  // json.loads(strict=True) rejects raw control characters
             if (c >= 0x80) non_ascii = true;
             if (c != '\\') {
-                out.push_back((char)c);
                 ++p;
                 continue;
             }
+            esc = true;
             if (++p >= end) return false;
-            switch (*p++) {
-                case '"': out.push_back('"'); break;
-                case '\\': out.push_back('\\'); break;
-                case '/': out.push_back('/'); break;
-                case 'b': out.push_back('\b'); break;
-                case 'f': out.push_back('\f'); break;
-                case 'n': out.push_back('\n'); break;
-                case 'r': out.push_back('\r'); break;
-                case 't': out.push_back('\t'); break;
-                case 'u': {
-                    if (end - p < 4) return false;
-                    unsigned v = 0;
-                    for (int i = 0; i < 4; ++i) {
-                        const char h = p[i];
-                        v <<= 4;
-                        if (h >= '0' && h <= '9') v |= (unsigned)(h - '0');
-                        else if (h >= 'a' && h <= 'f') v |= (unsigned)(h - 'a' + 10);
-                        else if (h >= 'A' && h <= 'F') v |= (unsigned)(h - 'A' + 10);
-                        else return false;
-                    }
-                    p += 4;
-                    if (v >= 0x80) non_ascii = true;  // parity for non-ASCII text is unpinned: hand the record to Python
-                    out.push_back((char)(v & 0x7F));
-                    break;
+            const char k = *p++;
+            if (k == 'u') {
+                if (end - p < 4) return false;
+                unsigned v = 0;
+                for (int i = 0; i < 4; ++i) {
+                    const char h = p[i];
+                    v <<= 4;
+                    if (h >= '0' && h <= '9') v |= (unsigned)(h - '0');
+                    else if (h >= 'a' && h <= 'f') v |= (unsigned)(h - 'a' + 10);
+                    else if (h >= 'A' && h <= 'F') v |= (unsigned)(h - 'A' + 10);
+                    else return false;
                 }
-                default: return false;
+                p += 4;
+                if (v >= 0x80) non_ascii = true;  // parity for non-ASCII text is unpinned: hand the record to Python
+            } else if (!(k == '"' || k == '\\' || k == '/' || k == 'b' || k == 'f' || k == 'n' || k == 'r' || k == 't')) {
+                return false;
             }
         }
         return false;
     }
     bool skip_nested() {  // at '{' or '[': skip a balanced value
         int depth = 0;
-        std::string tmp;
         while (p < end) {
             const char c = *p;
             if (c == '"') {
-                if (!string(tmp)) return false;
+                const char *sp;
+                uint32_t sl;
+                bool esc;
+                if (!string(sp, sl, esc)) return false;
                 continue;
             }
             if (c == '{' || c == '[') ++depth;
@@ -157,16 +194,16 @@ struct Scanner {
                 is_float = true;
             }
         }
-        std::string txt(s, p);
-        t.num = strtod(txt.c_str(), nullptr);
-        if (is_float) {
-            t.type = T_FLOAT;
+        t.p = s;
+        t.len = (uint32_t)(p - s);
+        t.type = is_float ? T_FLOAT : T_INT;
+        if (t.len < 40) {  // strtod needs a terminated buffer
+            char buf[40];
+            memcpy(buf, s, t.len);
+            buf[t.len] = 0;
+            t.num = strtod(buf, nullptr);
         } else {
-            t.type = T_INT;
-            size_t i = 0;  // canonical str(int): no "-0", no other normalisation needed (JSON forbids leading zeros)
-            if (txt == "-0") txt = "0";
-            (void)i;
-            t.text = std::move(txt);
+            t.num = strtod(std::string(s, t.len).c_str(), nullptr);
         }
         return true;
     }
@@ -176,27 +213,29 @@ struct Scanner {
         const char c = *p;
         if (c == '"') {
             t.type = T_STR;
-            return string(t.text);
+            return string(t.p, t.len, t.esc);
         }
         if (c == '{' || c == '[') {
             t.type = T_NESTED;
             return skip_nested();
         }
-        if (lit("true")) { t.type = T_TRUE; return true; }
-        if (lit("false")) { t.type = T_FALSE; return true; }
-        if (lit("null")) { t.type = T_NULL; return true; }
-        if (lit("NaN")) { t.type = T_FLOAT; t.num = NAN; return true; }
-        if (lit("Infinity")) { t.type = T_FLOAT; t.num = INFINITY; return true; }
-        if (lit("-Infinity")) { t.type = T_FLOAT; t.num = -INFINITY; return true; }
+        if (c == 't' && lit("true", 4)) { t.type = T_TRUE; return true; }
+        if (c == 'f' && lit("false", 5)) { t.type = T_FALSE; return true; }
+        if (c == 'n' && lit("null", 4)) { t.type = T_NULL; return true; }
+        if (c == 'N' && lit("NaN", 3)) { t.type = T_FLOAT; t.num = NAN; return true; }
+        if (c == 'I' && lit("Infinity", 8)) { t.type = T_FLOAT; t.num = INFINITY; return true; }
+        if (c == '-' && lit("-Infinity", 9)) { t.type = T_FLOAT; t.num = -INFINITY; return true; }
         return number(t);
     }
 };
 
 // json.loads(text) for a flat object; anything else that json.loads would ACCEPT (top-level list, number, ...) is
 // reported through `not_object`; a parse failure means the reference wraps the text (consolidation.py:37-38).
-bool parse_object(const char *s, size_t len, Candidate &out, bool &not_object, bool &non_ascii) {
+// `odd` is set for things this fast path does not model (escaped keys): the record goes to the Python path.
+bool parse_object(const char *s, size_t len, std::vector<Item> &out, bool &not_object, bool &non_ascii, bool &odd) {
     Scanner sc{s, s + len};
     not_object = false;
+    out.clear();
     sc.ws();
     if (sc.p >= sc.end) return false;
     if (*sc.p != '{') {
@@ -215,14 +254,18 @@ bool parse_object(const char *s, size_t len, Candidate &out, bool &not_object, b
         for (;;) {
             sc.ws();
             if (sc.p >= sc.end || *sc.p != '"') return false;
-            std::string key;
-            if (!sc.string(key)) return false;
+            const char *kp;
+            uint32_t kl;
+            bool kesc;
+            if (!sc.string(kp, kl, kesc)) return false;
+            if (kesc) odd = true;
             sc.ws();
             if (sc.p >= sc.end || *sc.p != ':') return false;
             ++sc.p;
-            Tok t;
-            if (!sc.value(t)) return false;
-            out.items.emplace_back(std::move(key), std::move(t));
+            Item it;
+            it.key = std::string_view(kp, kl);
+            if (!sc.value(it.tok)) return false;
+            out.push_back(it);
             sc.ws();
             if (sc.p < sc.end && *sc.p == ',') {
                 ++sc.p;
@@ -293,7 +336,7 @@ void json_float(double x, std::string &out) {
 }
 
 // json.dumps(str) with ensure_ascii=True (input is ASCII)
-void json_string(const std::string &s, std::string &out) {
+void json_string(std::string_view s, std::string &out) {
     static const char *hex = "0123456789abcdef";
     out.push_back('"');
     for (unsigned char c : s) {
@@ -318,14 +361,29 @@ void json_string(const std::string &s, std::string &out) {
     out.push_back('"');
 }
 
+// str(int) of a JSON integer token: the digits as written (JSON forbids leading zeros), except "-0" -> "0"
+void int_text(const Tok &t, std::string &out) {
+    if (t.len == 2 && t.p[0] == '-' && t.p[1] == '0') out += "0";
+    else out.append(t.p, t.len);
+}
+
 // str(v) as Python prints the value (for the enum-likeness test and for sanitising)
 void py_str(const Tok &t, std::string &out) {
     switch (t.type) {
         case T_TRUE: out += "True"; break;
         case T_FALSE: out += "False"; break;
-        case T_INT: out += t.text; break;
+        case T_INT: int_text(t, out); break;
         case T_FLOAT: py_float_repr(t.num, out); break;
-        case T_STR: out += t.text; break;
+        case T_STR: {
+            if (t.esc) {
+                std::string tmp;
+                unescape(t.p, t.len, tmp);
+                out += tmp;
+            } else {
+                out.append(t.p, t.len);
+            }
+            break;
+        }
         default: break;
     }
 }
@@ -353,9 +411,14 @@ void json_value(const Tok &t, std::string &out) {
     switch (t.type) {
         case T_TRUE: out += "true"; break;
         case T_FALSE: out += "false"; break;
-        case T_INT: out += t.text; break;
+        case T_INT: int_text(t, out); break;
         case T_FLOAT: json_float(t.num, out); break;
-        case T_STR: json_string(t.text, out); break;
+        case T_STR: {
+            std::string tmp;
+            tok_string(t, tmp);
+            json_string(tmp, out);
+            break;
+        }
         default: out += "null"; break;
     }
 }
@@ -366,20 +429,24 @@ enum GroupKind : uint8_t { G_ALLNULL = 0, G_VOTE_STR, G_VOTE_BOOL, G_NUMERIC };
 
 struct Group {
     GroupKind kind;
-    std::string key;
-    std::vector<Tok> cells;  // n tokens (T_MISSING / T_NULL count as None)
-    int64_t row = -1;        // row in the vote / numeric cell matrix
+    std::string_view key;
+    int64_t row = -1;  // row in the vote / numeric cell matrix
 };
 
 struct Record {
-    uint8_t status = 0;  // 0 native, 1 needs the Python path
+    uint8_t status = 0;        // 0 native, 1 needs the Python path
     std::vector<Group> groups;
+    std::vector<Tok> cells;    // groups.size() * n tokens, group-major (T_MISSING / T_NULL count as None)
 };
 
 const double kF64None = [] { const uint64_t b = KC_F64_NONE_BITS; double d; memcpy(&d, &b, 8); return d; }();
 
 void plan_record(const char *const *texts, const int64_t *lens, int n, Record &rec) {
-    std::vector<Candidate> cands((size_t)n);
+    thread_local std::vector<std::vector<Item>> cands;
+    thread_local std::vector<std::string_view> keys;
+    thread_local std::string tmp;
+    if ((int)cands.size() < n) cands.resize((size_t)n);
+    static const char kTextKey[] = "text";
     for (int c = 0; c < n; ++c) {
         const char *s = texts[c];
         const size_t len = lens ? (size_t)lens[c] : strlen(s);
@@ -387,68 +454,82 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
             rec.status = 1;
             return;
         }
-        bool not_object = false, non_ascii = false;
-        Candidate cand;
-        const bool ok = parse_object(s, len, cand, not_object, non_ascii);
-        for (size_t i = 0; i < len && !non_ascii; ++i)
-            if ((unsigned char)s[i] >= 0x80) non_ascii = true;
-        if (non_ascii || (ok && not_object)) {
+        bool not_object = false, non_ascii = false, odd = false;
+        std::vector<Item> &items = cands[(size_t)c];
+        const bool ok = parse_object(s, len, items, not_object, non_ascii, odd);
+        if (!ok || !non_ascii)  // a failed parse may have stopped early: look at every byte
+            for (size_t i = 0; i < len && !non_ascii; ++i)
+                if ((unsigned char)s[i] >= 0x80) non_ascii = true;
+        if (non_ascii || odd || (ok && not_object)) {
             rec.status = 1;
             return;
         }
-        if (!ok) {  // {"text": content}
-            cand.items.clear();
-            Tok t;
-            t.type = T_STR;
-            t.text.assign(s, len);
-            cand.items.emplace_back("text", std::move(t));
+        if (!ok) {  // {"text": content}: the whole text is the (already unescaped) value
+            items.clear();
+            Item it;
+            it.key = std::string_view(kTextKey, 4);
+            it.tok.type = T_STR;
+            it.tok.p = s;
+            it.tok.len = (uint32_t)len;
+            items.push_back(it);
         }
-        cands[(size_t)c] = std::move(cand);
+        // sort by key; of duplicates the LAST one in the text wins (dict construction)
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.key < b.key; });
     }
-    std::vector<std::string> keys;
-    for (auto &c : cands)
-        for (auto &kv : c.items) keys.push_back(kv.first);
+    keys.clear();
+    for (int c = 0; c < n; ++c)
+        for (auto &it : cands[(size_t)c]) keys.push_back(it.key);
     std::sort(keys.begin(), keys.end());  // code-point order == byte order for ASCII (consensus_utils.py:521-522)
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    rec.groups.clear();
+    rec.cells.clear();
+    rec.cells.reserve(keys.size() * (size_t)n);
+    std::vector<size_t> cursor((size_t)n, 0);
     for (auto &key : keys) {
-        if (key.find("reasoning___") != std::string::npos || key.find("source___") != std::string::npos) continue;  // cu:1292
+        const size_t base = rec.cells.size();
+        rec.cells.resize(base + (size_t)n);
+        for (int c = 0; c < n; ++c) {  // merge: both sides are sorted by key
+            auto &items = cands[(size_t)c];
+            size_t &k = cursor[(size_t)c];
+            while (k < items.size() && items[k].key == key) rec.cells[base + (size_t)c] = items[k++].tok;
+        }
+        if (key.find("reasoning___") != std::string_view::npos || key.find("source___") != std::string_view::npos) {  // cu:1292
+            rec.cells.resize(base);
+            continue;
+        }
         Group g;
         g.key = key;
-        g.cells.resize((size_t)n);
-        for (int c = 0; c < n; ++c)
-            for (auto &kv : cands[(size_t)c].items)
-                if (kv.first == key) g.cells[(size_t)c] = kv.second;  // later duplicates win, like dict construction
+        const Tok *cells = &rec.cells[base];
         const Tok *first = nullptr;
-        for (auto &t : g.cells)
-            if (t.type > T_NULL) {
-                first = &t;
-                break;
-            }
+        for (int c = 0; c < n && !first; ++c)
+            if (cells[c].type > T_NULL) first = &cells[c];
         if (!first) {
             g.kind = G_ALLNULL;
         } else if (first->type == T_NESTED) {
             rec.status = 1;
             return;
         } else if (first->type == T_STR || first->type == T_TRUE || first->type == T_FALSE) {
-            std::string tmp;
-            for (auto &t : g.cells) {
+            for (int c = 0; c < n; ++c) {
+                const Tok &t = cells[c];
                 if (t.type <= T_NULL) continue;
                 if (t.type == T_NESTED) {  // str(dict) is almost never enum-like: leave it to Python
                     rec.status = 1;
                     return;
                 }
-                tmp.clear();
-                py_str(t, tmp);
-                if (word_count(tmp) >= 3) {  // not enum-like -> similarity medoid (host)
-                    rec.status = 1;
-                    return;
+                if (t.type == T_STR) {  // numbers and bools print as one word
+                    tmp.clear();
+                    py_str(t, tmp);
+                    if (word_count(tmp) >= 3) {  // not enum-like -> similarity medoid (host)
+                        rec.status = 1;
+                        return;
+                    }
                 }
             }
             if (first->type == T_STR) {
                 g.kind = G_VOTE_STR;
             } else {
-                for (auto &t : g.cells)  // `v or False` on non-bool values compares Python objects: Python path
-                    if (t.type != T_MISSING && t.type != T_NULL && t.type != T_TRUE && t.type != T_FALSE) {
+                for (int c = 0; c < n; ++c)  // `v or False` on non-bool values compares Python objects: Python path
+                    if (cells[c].type > T_FALSE) {
                         rec.status = 1;
                         return;
                     }
@@ -457,16 +538,17 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
         } else {
             g.kind = G_NUMERIC;
         }
-        rec.groups.push_back(std::move(g));
+        rec.groups.push_back(g);
     }
 }
 
-void encode_vote(const Group &g, int n, int8_t *cells) {
-    std::vector<std::string> seen;
-    std::string tmp, san;
+void encode_vote(GroupKind kind, const Tok *toks, int n, int8_t *cells) {
+    thread_local std::vector<std::string> seen;
+    thread_local std::string tmp, san;
+    size_t n_seen = 0;
     for (int c = 0; c < n; ++c) {
-        const Tok &t = g.cells[(size_t)c];
-        if (g.kind == G_VOTE_BOOL) {
+        const Tok &t = toks[c];
+        if (kind == G_VOTE_BOOL) {
             cells[c] = (t.type == T_TRUE) ? 1 : 0;  // None and False -> False (cu:956)
             continue;
         }
@@ -478,15 +560,18 @@ void encode_vote(const Group &g, int n, int8_t *cells) {
         py_str(t, tmp);
         sanitize(tmp, san);
         size_t k = 0;
-        while (k < seen.size() && seen[k] != san) ++k;
-        if (k == seen.size()) seen.push_back(san);
+        while (k < n_seen && seen[k] != san) ++k;
+        if (k == n_seen) {
+            if (seen.size() <= n_seen) seen.emplace_back();
+            seen[n_seen++] = san;
+        }
         cells[c] = (int8_t)k;
     }
 }
 
-void encode_numeric(const Group &g, int n, double *cells) {
+void encode_numeric(const Tok *toks, int n, double *cells) {
     for (int c = 0; c < n; ++c) {
-        const Tok &t = g.cells[(size_t)c];
+        const Tok &t = toks[c];
         if (t.type <= T_NULL) cells[c] = kF64None;
         else if (t.type == T_INT || t.type == T_FLOAT) cells[c] = t.num;  // non-finite values are dropped by the kernel
         else cells[c] = NAN;                                               // bool / str / nested: counted, never clustered
@@ -520,7 +605,9 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
     lik = "{";
     bool first = true;
     const Tok *single_text = nullptr;
-    for (const Group &g : rec.groups) {
+    for (size_t gi = 0; gi < rec.groups.size(); ++gi) {
+        const Group &g = rec.groups[gi];
+        const Tok *cells = &rec.cells[gi * (size_t)n];
         if (!first) {
             content += ", ";
             lik += ", ";
@@ -536,9 +623,9 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
             const uint32_t m = vmeta[g.row];
             const uint32_t idx = KC_META_IDX(m), support = KC_META_SUPPORT(m), present = KC_META_PRESENT(m);
             if (g.kind == G_VOTE_BOOL) {
-                value.type = (g.cells[idx].type == T_TRUE) ? T_TRUE : T_FALSE;  // the processed key (cu:958)
+                value.type = (cells[idx].type == T_TRUE) ? T_TRUE : T_FALSE;  // the processed key (cu:958)
             } else {
-                value = g.cells[idx];  // first original whose sanitised form wins (cu:971)
+                value = cells[idx];  // first original whose sanitised form wins (cu:971)
             }
             conf = py_round5(1.0 * ((double)support / (double)present));
         } else if (g.kind == G_NUMERIC) {
@@ -547,7 +634,7 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
             const uint32_t flags = KC_META_FLAGS(m);
             if (flags & KC_FLAG_HAS_VALUE) {
                 if (flags & KC_FLAG_SINGLE) {
-                    value = g.cells[idx];
+                    value = cells[idx];
                     conf = 1.0 * (1.0 / (double)present) * (1.0 / 1.0);
                 } else {
                     value.type = T_FLOAT;
@@ -562,12 +649,11 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
         }  // G_ALLNULL: None, 0.0 (cu:1401-1402)
         json_value(value, content);
         json_float(conf, lik);
-        if (rec.groups.size() == 1 && g.key == "text" && value.type == T_STR) single_text = &g.cells[KC_META_IDX(vmeta[g.row])];
+        if (rec.groups.size() == 1 && g.key == "text" && value.type == T_STR) single_text = &cells[KC_META_IDX(vmeta[g.row])];
     }
     content += "}";
     lik += "}";
-    (void)n;
-    if (single_text) content = single_text->text;  // {"text": s} -> s (consolidation.py:55-57)
+    if (single_text) tok_string(*single_text, content);  // {"text": s} -> s (consolidation.py:55-57)
 }
 
 char *dup_string(const std::string &s) {
@@ -602,10 +688,15 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
                         uint8_t *out_status) {
     if (n < 2 || n > KC_MAX_CANDIDATES || n_records < 0 || !texts || !out_content || !out_likelihoods || !out_status)
         return KC_EINVAL;
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads <= 0) threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));  // parsing saturates memory / malloc beyond ~32
+    const bool timing = getenv("KC_JSON_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     std::vector<Record> recs((size_t)n_records);
     parallel_for(n_records, threads, [&](int64_t r) { plan_record(texts + r * n, lens ? lens + r * n : nullptr, n, recs[(size_t)r]); });
 
+    const auto t1 = now();
     int64_t gv = 0, gx = 0;
     for (auto &rec : recs) {
         if (rec.status) continue;
@@ -614,27 +705,47 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
             else if (g.kind == G_NUMERIC) g.row = gx++;
         }
     }
-    int8_t *h_codes = gv ? (int8_t *)kc_host_alloc((uint64_t)gv * n) : nullptr;
-    double *h_vals = gx ? (double *)kc_host_alloc((uint64_t)gx * n * 8) : nullptr;
-    int32_t *h_win = gv ? (int32_t *)kc_host_alloc((uint64_t)gv * 4) : nullptr;
-    uint32_t *h_vmeta = gv ? (uint32_t *)kc_host_alloc((uint64_t)gv * 4) : nullptr;
-    double *h_value = gx ? (double *)kc_host_alloc((uint64_t)gx * 8) : nullptr;
-    uint32_t *h_nmeta = gx ? (uint32_t *)kc_host_alloc((uint64_t)gx * 4) : nullptr;
+    // page-locked staging buffers are expensive to create: keep them (grow-only) across calls
+    static std::mutex pool_mu;
+    static struct { void *p = nullptr; size_t cap = 0; } pool[6];
+    std::lock_guard<std::mutex> pool_lock(pool_mu);  // also serialises callers (one staging pool per process)
+    auto pinned = [&](int slot, size_t bytes) -> void * {
+        if (bytes == 0) return nullptr;
+        if (pool[slot].cap < bytes) {
+            kc_host_free(pool[slot].p);
+            pool[slot].cap = bytes + bytes / 4;
+            pool[slot].p = kc_host_alloc(pool[slot].cap);
+            if (!pool[slot].p) pool[slot].cap = 0;
+        }
+        return pool[slot].p;
+    };
+    int8_t *h_codes = (int8_t *)pinned(0, (size_t)gv * n);
+    double *h_vals = (double *)pinned(1, (size_t)gx * n * 8);
+    int32_t *h_win = (int32_t *)pinned(2, (size_t)gv * 4);
+    uint32_t *h_vmeta = (uint32_t *)pinned(3, (size_t)gv * 4);
+    double *h_value = (double *)pinned(4, (size_t)gx * 8);
+    uint32_t *h_nmeta = (uint32_t *)pinned(5, (size_t)gx * 4);
+    const auto t2 = now();
+    auto t3 = t2, t4 = t2;
     int rc = KC_OK;
     if ((gv && (!h_codes || !h_win || !h_vmeta)) || (gx && (!h_vals || !h_value || !h_nmeta))) rc = KC_ENOMEM;
     if (!rc) {
         parallel_for(n_records, threads, [&](int64_t r) {
             const Record &rec = recs[(size_t)r];
             if (rec.status) return;
-            for (auto &g : rec.groups) {
-                if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) encode_vote(g, n, h_codes + g.row * n);
-                else if (g.kind == G_NUMERIC) encode_numeric(g, n, h_vals + g.row * n);
+            for (size_t gi = 0; gi < rec.groups.size(); ++gi) {
+                const Group &g = rec.groups[gi];
+                const Tok *toks = &rec.cells[gi * (size_t)n];
+                if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) encode_vote(g.kind, toks, n, h_codes + g.row * n);
+                else if (g.kind == G_NUMERIC) encode_numeric(toks, n, h_vals + g.row * n);
             }
         });
+        t3 = now();
         // one "field" per group: the two halves are independent calls of the host-buffer entry
         if (gv) rc = kc_consensus_host_i8(h_codes, 1, nullptr, nullptr, 0, gv, n, rel_eps, abs_eps, h_win, h_vmeta, nullptr, nullptr, device, nullptr);
         if (!rc && gx) rc = kc_consensus_host_i8(nullptr, 0, nullptr, h_vals, 1, gx, n, rel_eps, abs_eps, nullptr, nullptr, h_value, h_nmeta, device, nullptr);
     }
+    t4 = now();
     if (!rc) {
         parallel_for(n_records, threads, [&](int64_t r) {
             const Record &rec = recs[(size_t)r];
@@ -648,12 +759,10 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
             out_likelihoods[r] = dup_string(lik);
         });
     }
-    kc_host_free(h_codes);
-    kc_host_free(h_vals);
-    kc_host_free(h_win);
-    kc_host_free(h_vmeta);
-    kc_host_free(h_value);
-    kc_host_free(h_nmeta);
+    const auto t5 = now();
+    if (timing)
+        fprintf(stderr, "kc_consolidate_json: parse+plan %.1f ms, rows+alloc %.1f ms, encode %.1f ms, gpu %.1f ms, emit %.1f ms (%d threads)\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), threads);
     return rc;
 }
 

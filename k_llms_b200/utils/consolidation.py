@@ -177,3 +177,41 @@ async def async_consolidate_parsed_chat_completions(
     content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
                                                   async_get_openai_embeddings_from_text, client)
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=False)
+
+
+def consolidate_contents_batch(records: List[List[str]], consensus_settings: ConsensusSettings = ConsensusSettings(),
+                               get_openai_embeddings_from_text: Optional[SYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE] = None,
+                               client: Any = None, device: int = 0):
+    """Batched consolidation of raw contents (new; the reference has no batch dimension): for every record, the n
+    `choice.message.content` strings in -> (consensus content string, likelihoods) out, exactly what the per-request
+    functions above put into choices[0] and `likelihoods`.
+
+    Flat records go through the native path (kc_consolidate_json: C++ parse/encode/decode + K1/K2, no Python objects);
+    records it declines (nested values, multi-word strings, non-ASCII, ...) take the regular Python + GPU path."""
+    from .. import _native
+    default_eps = (consensus_settings.rel_eps, consensus_settings.abs_eps)
+    native: List[Any] = [None] * len(records)
+    if not consensus_settings.allow_none_as_candidate:
+        by_n: dict = {}
+        for i, texts in enumerate(records):
+            if len(texts) >= 2:
+                by_n.setdefault(len(texts), []).append(i)
+        for n, idxs in by_n.items():
+            if n > _native.MAX_CANDIDATES:
+                continue
+            outs = _native.consolidate_json([records[i] for i in idxs], default_eps[0], default_eps[1], device)
+            for i, o in zip(idxs, outs):
+                native[i] = o
+    results = []
+    embed = get_openai_embeddings_from_text if get_openai_embeddings_from_text is not None else (lambda texts: [[0.0] for _ in texts])
+    for texts, nat in zip(records, native):
+        if nat is not None:
+            results.append((nat[0], json.loads(nat[1])))
+            continue
+        contents = [_safe_parse_content(t) for t in texts if t]
+        if len(contents) == 1:  # single choice: nothing to consolidate (consolidation.py:85-87)
+            results.append((texts[0], None))
+            continue
+        value, likelihoods = _consensus_sync(contents, consensus_settings, embed, client)
+        results.append((_format_consensus_content(value), likelihoods))
+    return results

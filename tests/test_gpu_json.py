@@ -96,3 +96,25 @@ def test_native_json_declines_what_it_cannot_express():
     assert K.consolidate_json(recs) == [None] * len(recs)
     ok = K.consolidate_json([['{"a": "x"}', '{"a": "X!"}']])
     assert ok == [('{"a": "x"}', '{"a": 1.0}')]
+
+
+def test_batch_helper_mixes_native_and_python_paths():
+    from k_llms_b200.utils.consolidation import consolidate_contents_batch
+    records = [
+        ['{"a": "x", "n": 5}', '{"a": "X!", "n": 5}', '{"a": "y", "n": 50}'],                 # native
+        ['{"a": {"b": [1, 2]}}', '{"a": {"b": [1, 2]}}', '{"a": {"b": [2, 1]}}'],               # nested + list alignment: Python path
+        ['{"t": "the big cat"}', '{"t": "the big cat"}', '{"t": "the big dog"}'],               # multi-word: medoid on the host
+        ['Yes', 'yes', 'No'],
+    ]
+    out = consolidate_contents_batch(records)
+    for texts, (content, lik) in zip(records, out):
+        exp_content, exp_lik = _expected_full(texts)
+        assert content == exp_content and lik == exp_lik, (texts, content, lik, exp_content, exp_lik)
+
+
+def _expected_full(texts):
+    """Expected output through the golden-pinned Python product path (align incl. lists + consensus)."""
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings
+    from k_llms_b200.utils.consolidation import _consensus_sync, _format_consensus_content, _safe_parse_content
+    value, lik = _consensus_sync([_safe_parse_content(t) for t in texts], ConsensusSettings(), raising_embeddings, None)
+    return _format_consensus_content(value), lik

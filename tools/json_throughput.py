@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--records", type=int, default=20000)
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--py-records", type=int, default=300)
+    ap.add_argument("--threads", type=int, default=0)
     args = ap.parse_args()
     recs = make_texts(args.records, args.n, 11)
     nbytes = sum(len(t) for r in recs for t in r)
@@ -53,7 +54,7 @@ def main():
     best = None
     for _ in range(3):
         t0 = time.perf_counter()
-        K.check(lib.kc_consolidate_json(cast(texts), cast(lens), R, n, 0.03, 1e-6, 0, 0, cast(out_c), cast(out_l), cast(status)))
+        K.check(lib.kc_consolidate_json(cast(texts), cast(lens), R, n, 0.03, 1e-6, 0, args.threads, cast(out_c), cast(out_l), cast(status)))
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         first = ctypes.string_at(out_c[0]).decode()
