@@ -189,6 +189,10 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
                         uint8_t *out_status);
 void kc_free_strings(char **arr, int64_t count);
 
+/* Host helper: unit-cost edit distance of two byte strings (python-Levenshtein `distance`, consensus_utils.py:759),
+ * used by the host similarity medoid / list alignment.  -1 on bad arguments. */
+int32_t kc_levenshtein(const char *a, int32_t alen, const char *b, int32_t blen);
+
 void *kc_host_alloc(uint64_t bytes); /* page-locked host memory, NULL on failure */
 void kc_host_free(void *p);
 

@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM = 0, 1
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -67,6 +67,8 @@ def load() -> ctypes.CDLL:
     lib.kc_vote_i8.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.kc_consolidate_json.argtypes = [vp, vp, i64, i32, f64, f64, c.c_int, i32, vp, vp, vp]
     lib.kc_consolidate_json.restype = c.c_int
+    lib.kc_levenshtein.argtypes = [c.c_char_p, i32, c.c_char_p, i32]
+    lib.kc_levenshtein.restype = i32
     lib.kc_free_strings.argtypes = [vp, i64]
     lib.kc_free_strings.restype = None
     lib.kc_host_alloc.argtypes = [c.c_uint64]
@@ -74,7 +76,7 @@ def load() -> ctypes.CDLL:
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -226,6 +228,12 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     check(entry(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
                 p(value), p(nmeta), device, ctypes.addressof(ms)))
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
+
+
+def levenshtein(a: str, b: str) -> int:
+    """Edit distance through the native library (code points must be Latin-1; callers pass normalised ASCII)."""
+    ba, bb = a.encode("latin-1"), b.encode("latin-1")
+    return int(load().kc_levenshtein(ba, len(ba), bb, len(bb)))
 
 
 def consolidate_json(records, rel_eps: float = 0.03, abs_eps: float = 1e-6, device: int = 0, threads: int = 0):

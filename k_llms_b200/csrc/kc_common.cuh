@@ -29,8 +29,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 // make mbarrier.init visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -92,20 +90,6 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
-// Same, with a register the issue must wait for (orders the copy after the instructions that produce `dep`).
-__device__ __forceinline__ void tma_load_2d_dep(void *smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1,
-                                                uint64_t *bar, uint64_t policy, uint32_t dep) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 kc_dep;\n\t"
-        "mov.b32 kc_dep, %6;\n\t"
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
-        "[%4], %5;\n\t"
-        "}\n" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy), "r"(dep)
-        : "memory");
-}
-
 // 32-bit shared-space addresses + dependency register.
 __device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar,
                                               uint64_t policy, uint32_t dep) {
@@ -122,28 +106,12 @@ __device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorM
 
 // ---------------------------------------------------------------- global memory: streaming loads / stores
 
-__device__ __forceinline__ int4 ldg_stream_v4(const void *p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
 // read-only path, default L1 allocation: a thread's neighbouring 16-byte pieces share 32-byte sectors, so the
 // second piece should hit L1 instead of going back to L2
 __device__ __forceinline__ int4 ldg_nc_v4(const void *p) {
     int4 r;
     asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
-}
-
-__device__ __forceinline__ void stg_stream_u32(void *p, uint32_t v) {
-    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void stg_stream_f64(void *p, double v) {
-    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // Result stores.  mc == true: `p` is an NVSwitch MULTICAST address (CUDA multicast object mapped on every GPU of

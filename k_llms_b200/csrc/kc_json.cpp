@@ -766,6 +766,32 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
     return rc;
 }
 
+// Unit-cost edit distance of two byte strings (what python-Levenshtein's `distance` returns for the ASCII strings
+// normalize_string() produces, consensus_utils.py:745-761).  Host helper for the similarity medoid / list alignment.
+int32_t kc_levenshtein(const char *a, int32_t alen, const char *b, int32_t blen) {
+    if (alen < 0 || blen < 0 || (!a && alen) || (!b && blen)) return -1;
+    if (alen < blen) {
+        std::swap(a, b);
+        std::swap(alen, blen);
+    }
+    if (blen == 0) return alen;
+    thread_local std::vector<int32_t> row;
+    row.resize((size_t)blen + 1);
+    for (int32_t j = 0; j <= blen; ++j) row[(size_t)j] = j;
+    for (int32_t i = 1; i <= alen; ++i) {
+        int32_t diag = row[0];
+        row[0] = i;
+        const char ca = a[i - 1];
+        for (int32_t j = 1; j <= blen; ++j) {
+            const int32_t up = row[(size_t)j];
+            const int32_t v = std::min(std::min(up + 1, row[(size_t)j - 1] + 1), diag + (ca != b[j - 1] ? 1 : 0));
+            diag = up;
+            row[(size_t)j] = v;
+        }
+    }
+    return row[(size_t)blen];
+}
+
 void kc_free_strings(char **arr, int64_t count) {
     if (!arr) return;
     for (int64_t i = 0; i < count; ++i) {

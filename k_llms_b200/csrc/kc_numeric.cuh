@@ -11,10 +11,10 @@
 // Cost model: the op is HBM-streaming (8n bytes in, 12 out per group) but a 64-bit sort in 32-bit registers is
 // select-bound, so the sort runs on 32-bit KEYS instead: the order-preserving image of each cell's high word
 // with the candidate index in the low log2(n) bits.  A compare-exchange is then one IMNMX pair.  The cells
-// themselves stay in shared memory ("row memory": the thread's row of the TMA tile, or a [cell][thread] plane)
-// and are fetched once in key order.  Keys drop the low mantissa bits, so values that differ only there may
-// come out swapped; the adjacent differences the clustering needs anyway detect that, and a bubble pass on
-// the (rare) offending run repairs it.  Non-finite cells get keys above every finite key and sort to the end.
+// themselves stay in shared memory ("row memory": a [cell][thread] plane) and are fetched once in key order.
+// Keys drop the low mantissa bits, so values that differ only there may come out swapped; a 15-compare
+// sortedness check detects that and a shared-memory insertion sort of the (rare) offending row repairs it.
+// Non-finite cells get keys above every finite key and sort to the end.
 #pragma once
 
 #include <type_traits>
@@ -53,14 +53,6 @@ __device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
     return v;
 }
 
-template <int ROW_BYTES>
-struct SwzRow {  // this thread's row of a TMA-swizzled tile
-    uint32_t base, row_off;
-    __device__ __forceinline__ uint32_t addr(uint32_t elem) const {
-        return base + Swizzle<ROW_BYTES>::apply(row_off + elem * 8u);
-    }
-    __device__ __forceinline__ uint32_t addr_mad(uint32_t elem) const { return addr(elem); }
-};
 struct PlaneRow {  // [cell][thread] plane: pitch = threads*8 bytes, a multiple of 128 => bank depends on tid only
     uint32_t base, pitch;
     __device__ __forceinline__ uint32_t addr(uint32_t elem) const { return base + elem * pitch; }

@@ -27,6 +27,9 @@ except Exception:  # pragma: no cover - depends on the image
 def levenshtein_distance(a: str, b: str) -> int:
     if _lev is not None:
         return _lev(a, b)
+    if a.isascii() and b.isascii():  # always true for normalize_string() output: native C++ DP
+        from .. import _native
+        return _native.levenshtein(a, b)
     if a == b:
         return 0
     if len(a) < len(b):
