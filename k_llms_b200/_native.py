@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM = 0, 1
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -67,6 +67,8 @@ def load() -> ctypes.CDLL:
     lib.kc_vote_i8.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.kc_consolidate_json.argtypes = [vp, vp, i64, i32, f64, f64, c.c_int, i32, vp, vp, vp]
     lib.kc_consolidate_json.restype = c.c_int
+    lib.kc_medoid_str.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    lib.kc_medoid_str.restype = c.c_int
     lib.kc_levenshtein.argtypes = [c.c_char_p, i32, c.c_char_p, i32]
     lib.kc_levenshtein.restype = i32
     lib.kc_free_strings.argtypes = [vp, i64]
@@ -76,7 +78,7 @@ def load() -> ctypes.CDLL:
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -228,6 +230,20 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     check(entry(p(codes), Fv, p(none_code), p(vals), Fx, N, n, float(rel_eps), float(abs_eps), p(win), p(vmeta),
                 p(value), p(nmeta), device, ctypes.addressof(ms)))
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
+
+
+def medoid_str(chars, str_off, grp_off, stream=None):
+    """K4 on device tensors: chars uint8 [C], str_off int32 [S+1], grp_off int32 [G+1] ->
+    (best index int32 [G], mean similarity float64 [G])."""
+    torch = _require_cuda()
+    assert chars.is_cuda and chars.dtype == torch.uint8 and str_off.dtype == torch.int32 and grp_off.dtype == torch.int32
+    G = grp_off.numel() - 1
+    idx = torch.empty(G, dtype=torch.int32, device=chars.device)
+    avg = torch.empty(G, dtype=torch.float64, device=chars.device)
+    _bind(torch, chars)
+    check(load().kc_medoid_str(chars.data_ptr(), str_off.data_ptr(), grp_off.data_ptr(), G, idx.data_ptr(), avg.data_ptr(),
+                               _stream_ptr(torch, stream)))
+    return idx, avg
 
 
 def levenshtein(a: str, b: str) -> int:

@@ -45,6 +45,11 @@ def _fold_non_ascii(s: str) -> str:
     return "".join(ch for ch in unicodedata.normalize("NFKD", s) if not unicodedata.combining(ch))
 
 
+def _normalize(text: str) -> str:
+    """normalize_string (cu:660-673): keep ASCII alphanumerics, lower-case."""
+    return "".join(ch for ch in text if ch.isascii() and ch.isalnum()).lower() if text else ""
+
+
 def sanitize_value(v: Any) -> str:
     """str() -> lower -> drop spaces -> unidecode -> keep [a-zA-Z0-9]  (cu:925-933)."""
     s = str(v).lower().replace(" ", "")
@@ -77,6 +82,13 @@ class _NumLeaf:
         self.row, self.cells, self.pvf = row, cells, pvf
 
 
+class _MedoidLeaf:
+    __slots__ = ("row", "cells", "pvf")
+
+    def __init__(self, row: int, cells: list, pvf: float):
+        self.row, self.cells, self.pvf = row, cells, pvf
+
+
 class _DictNode:
     __slots__ = ("children",)
 
@@ -103,6 +115,8 @@ class Plan:
         self.host_primitive = host_primitive
         self.vote_rows: List[List[int]] = []
         self.num_rows: List[List[float]] = []
+        self.medoid_groups: List[List[str]] = []  # normalised strings of the groups K4 handles
+        self.string_method = "embeddings"         # set by the caller (ConsensusSettings.string_similarity_method)
 
     # -- leaves ---------------------------------------------------------------------------------------
     def _vote(self, values: Sequence[Any], pvf: float) -> _VoteLeaf:
@@ -181,12 +195,27 @@ class Plan:
         sub = pvf * (len(live) / len(values))  # cu:1444
         if len(live) == 1:
             return _Const(live[0], sub * (1 / 1))  # cu:1085-1086
-        value, conf = self.host_primitive(live, sub, embed)  # similarity medoid, cu:1221-1237
+        if self._medoid_on_device(live):
+            self.medoid_groups.append([_normalize(s) for s in live])
+            return _MedoidLeaf(len(self.medoid_groups) - 1, live, sub)
+        value, conf = self.host_primitive(live, sub, embed)  # similarity medoid on the host, cu:1221-1237
         return _Const(value, conf)
+
+    def _medoid_on_device(self, live: Sequence[Any]) -> bool:
+        """K4 takes groups of plain ASCII strings whose every pair is a Levenshtein pair with a <= 64-character side:
+        method 'levenshtein', or 'embeddings' where no two strings are both longer than 50 characters (cu:813 would
+        ask the embeddings service for those)."""
+        if self.string_method not in ("levenshtein", "embeddings") or len(live) > MAX_CANDIDATES:
+            return False
+        if not all(isinstance(v, str) and v.isascii() for v in live):
+            return False
+        if self.string_method == "embeddings" and sum(1 for v in live if len(v) > 50) > 1:
+            return False
+        return sum(1 for v in live if len(_normalize(v)) > 64) <= 1
 
     # -- device ----------------------------------------------------------------------------------------
     def run(self, device=None):
-        """One K1 and one K2 launch over every recorded group; returns numpy result columns."""
+        """One K1, one K2 and one K4 launch over every recorded group; returns numpy result columns."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("k_llms_b200: no CUDA device — the consensus hot path has no CPU fallback")
@@ -201,6 +230,18 @@ class Plan:
             value, meta = _native.numeric(vals, self.rel_eps, self.abs_eps)
             out["num_value"] = value.cpu().numpy()
             out["num_meta"] = meta.cpu().numpy().view(np.uint32)
+        if self.medoid_groups:
+            blobs, str_off, grp_off = [], [0], [0]
+            for grp in self.medoid_groups:
+                for s in grp:
+                    b = s.encode("ascii")
+                    blobs.append(b)
+                    str_off.append(str_off[-1] + len(b))
+                grp_off.append(grp_off[-1] + len(grp))
+            chars = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
+            idx, avg = _native.medoid_str(torch.from_numpy(chars).to(dev), torch.tensor(str_off, dtype=torch.int32, device=dev),
+                                          torch.tensor(grp_off, dtype=torch.int32, device=dev))
+            out["medoid_idx"], out["medoid_avg"] = idx.cpu().numpy(), avg.cpu().numpy()
         return out
 
     # -- epilogue --------------------------------------------------------------------------------------
@@ -219,6 +260,8 @@ class Plan:
         if isinstance(node, _ListNode):
             pairs = [self.materialise(c, res) for c in node.children]
             return [p[0] for p in pairs], [p[1] for p in pairs]
+        if isinstance(node, _MedoidLeaf):  # cu:1233-1237
+            return node.cells[int(res["medoid_idx"][node.row])], round(node.pvf * float(res["medoid_avg"][node.row]), 5)
         if isinstance(node, _VoteLeaf):
             idx, support, _nn, present, flags = self._fields(int(res["vote_meta"][node.row]))
             if not flags & _native.FLAG_HAS_VALUE:  # cannot happen for a planned vote group (>= 1 voter)

@@ -18,6 +18,7 @@
 #include "../../include/kllms_b200.h"
 #include "kc_common.cuh"
 #include "kc_extra.cuh"
+#include "kc_medoid.cuh"
 #include "kc_numeric.cuh"
 #include "kc_vote.cuh"
 
@@ -515,6 +516,24 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
     else if (n <= 32) KC_WV(32);
     else KC_WV(64);
 #undef KC_WV
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
+int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
+                  int32_t *d_best_idx, double *d_best_avg, void *stream) {
+    if (n_groups < 0) return fail(KC_EINVAL, "kc_medoid_str: negative n_groups");
+    if (n_groups == 0) return KC_OK;
+    if (!d_chars || !d_str_off || !d_grp_off || !d_best_idx || !d_best_avg) return fail(KC_EINVAL, "kc_medoid_str: NULL buffer");
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    constexpr int WARPS = 4;  // 9 KB of Peq tables + 8 KB of distances per warp
+    auto kernel = kc::medoid_kernel<WARPS>;
+    const size_t smem = (size_t)WARPS * (32 * kc::kAlphabet * 8 + kc::kMedoidMaxN * kc::kMedoidMaxN * 2);
+    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((n_groups + WARPS - 1) / WARPS, (int64_t)info.sm_count * 3);
+    kernel<<<grid, WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(d_chars, d_str_off, d_grp_off, n_groups, d_best_idx, d_best_avg);
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }

@@ -57,7 +57,9 @@ def _host_primitive(settings: ConsensusSettings):
 
 
 def _plan_for(n: int, settings: ConsensusSettings) -> columnar.Plan:
-    return columnar.Plan(n, settings.allow_none_as_candidate, settings.rel_eps, settings.abs_eps, _host_primitive(settings))
+    plan = columnar.Plan(n, settings.allow_none_as_candidate, settings.rel_eps, settings.abs_eps, _host_primitive(settings))
+    plan.string_method = settings.string_similarity_method if settings.string_consensus_method == "centroid" else "host"
+    return plan
 
 
 def consensus_values(
@@ -70,7 +72,7 @@ def consensus_values(
     """(consensus value, confidence) for one record's n candidate values — cu:1376-1454."""
     plan = _plan_for(len(values), consensus_settings)
     root = plan.add(values, parent_valid_frac, sync_get_openai_embeddings_from_text)
-    res = plan.run() if (plan.vote_rows or plan.num_rows) else {}
+    res = plan.run() if (plan.vote_rows or plan.num_rows or plan.medoid_groups) else {}
     return plan.materialise(root, res)
 
 
@@ -86,7 +88,7 @@ def consensus_values_batch(
     embed = sync_get_openai_embeddings_from_text if sync_get_openai_embeddings_from_text is not None else _no_embeddings
     plan = _plan_for(max((len(r) for r in records), default=1), settings)
     roots = [plan.add(values, parent_valid_frac, embed) for values in records]
-    res = plan.run() if (plan.vote_rows or plan.num_rows) else {}
+    res = plan.run() if (plan.vote_rows or plan.num_rows or plan.medoid_groups) else {}
     return [plan.materialise(root, res) for root in roots]
 
 

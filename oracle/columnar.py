@@ -45,6 +45,8 @@ def lib() -> ctypes.CDLL:
         _lib.ko_weighted_vote_i32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p,
                                               c.c_void_p, c.c_void_p]
         _lib.ko_weighted_vote_i32.restype = None
+        _lib.ko_medoid_str.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p]
+        _lib.ko_medoid_str.restype = None
         for name in ("ko_np_sum", "ko_np_mean", "ko_np_median_sorted", "ko_np_std"):
             f = getattr(_lib, name)
             f.argtypes = [c.c_void_p, c.c_int]
@@ -100,6 +102,29 @@ def weighted_vote(codes: np.ndarray, seq_logprob: np.ndarray, none_code: np.ndar
     lib().ko_weighted_vote_i32(_ptr(codes), _ptr(seq_logprob), R, F, n, _ptr(none_code) if none_code is not None else None,
                                _ptr(win), _ptr(meta), _ptr(weight))
     return win, meta, weight
+
+
+def pack_string_groups(groups):
+    """groups: list of lists of normalised (ASCII) strings -> (chars uint8, str_off int32, grp_off int32)."""
+    blobs, str_off, grp_off = [], [0], [0]
+    for grp in groups:
+        for s in grp:
+            b = s.encode("ascii")
+            blobs.append(b)
+            str_off.append(str_off[-1] + len(b))
+        grp_off.append(grp_off[-1] + len(grp))
+    chars = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
+    return chars, np.asarray(str_off, dtype=np.int32), np.asarray(grp_off, dtype=np.int32)
+
+
+def medoid(groups):
+    """(best index int32 [G], mean similarity float64 [G]) of groups of normalised strings."""
+    chars, str_off, grp_off = pack_string_groups(groups)
+    G = len(groups)
+    idx = np.empty(G, dtype=np.int32)
+    avg = np.empty(G, dtype=np.float64)
+    lib().ko_medoid_str(_ptr(chars), _ptr(str_off), _ptr(grp_off), G, _ptr(idx), _ptr(avg))
+    return idx, avg
 
 
 def meta_fields(meta: np.ndarray):

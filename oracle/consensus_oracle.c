@@ -321,3 +321,59 @@ void ko_weighted_vote_i32(const int32_t *codes, const float *seq_lp, int64_t n_r
         }
     }
 }
+
+/* ------------------------------------------------------------------ K4 oracle: similarity medoid of string groups */
+
+static int edit_distance(const uint8_t *a, int al, const uint8_t *b, int bl) {
+    int prev[2048], cur[2048];
+    if (al > 2047 || bl > 2047) return -1;
+    for (int j = 0; j <= bl; j++) prev[j] = j;
+    for (int i = 1; i <= al; i++) {
+        cur[0] = i;
+        for (int j = 1; j <= bl; j++) {
+            int v = prev[j] + 1;
+            if (cur[j - 1] + 1 < v) v = cur[j - 1] + 1;
+            if (prev[j - 1] + (a[i - 1] != b[j - 1]) < v) v = prev[j - 1] + (a[i - 1] != b[j - 1]);
+            cur[j] = v;
+        }
+        memcpy(prev, cur, sizeof(int) * (size_t)(bl + 1));
+    }
+    return prev[bl];
+}
+
+/* cu:1221-1237 with levenshtein_similarity (cu:745-761) on already normalised strings: sim matrix, np.nanmean per row
+ * (a copy with NaN -> 0 summed in numpy's pairwise order, divided by the count of non-NaN), first argmax. */
+void ko_medoid_str(const uint8_t *chars, const int32_t *str_off, const int32_t *grp_off, int64_t n_groups, int32_t *best_idx,
+                   double *best_avg) {
+    for (int64_t g = 0; g < n_groups; g++) {
+        int s0 = grp_off[g], k = grp_off[g + 1] - s0;
+        double best = -1.0;
+        int bi = 0;
+        for (int i = 0; i < k; i++) {
+            double row[MAXN];
+            int li = str_off[s0 + i + 1] - str_off[s0 + i];
+            for (int j = 0; j < k; j++) {
+                if (j == i) {
+                    row[j] = 0.0;
+                    continue;
+                }
+                int lj = str_off[s0 + j + 1] - str_off[s0 + j];
+                int mx = li > lj ? li : lj;
+                if (mx == 0) {
+                    row[j] = 1.0;
+                    continue;
+                }
+                int d = edit_distance(chars + str_off[s0 + i], li, chars + str_off[s0 + j], lj);
+                double sim = 1.0 - ((double)d / (double)mx);
+                row[j] = sim > 1e-8 ? sim : 1e-8;
+            }
+            double avg = ko_np_sum(row, k) / (double)(k - 1);
+            if (avg > best) {
+                best = avg;
+                bi = i;
+            }
+        }
+        best_idx[g] = bi;
+        best_avg[g] = best;
+    }
+}

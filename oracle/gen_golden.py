@@ -200,6 +200,40 @@ def random_cases(seed: int, count: int) -> list:
     return cases
 
 
+PHRASE_WORDS = ("invoice total due amount net gross payment bank transfer within thirty days from receipt of goods and "
+                "services the a an of to acme corp ltd gmbh street road avenue suite floor new york london paris berlin "
+                "2024 2025 q1 q2 ref no id number 000123 77 ab-12 x y z").split()
+
+
+def phrase_groups(seed: int, count: int) -> list:
+    """Groups of 2..20 multi-word strings (noisy copies of one phrase): inputs of the similarity medoid, cu:1221-1237."""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(count):
+        k = rng.randint(2, 20)
+        base = [rng.choice(PHRASE_WORDS) for _ in range(rng.randint(3, 8))]
+        grp = []
+        for _c in range(k):
+            words, r = list(base), rng.random()
+            if r < 0.35:
+                pass
+            elif r < 0.6:
+                words[rng.randrange(len(words))] = rng.choice(PHRASE_WORDS)
+            elif r < 0.75:
+                words = words[: max(1, len(words) - rng.randint(1, 2))]
+            elif r < 0.9:
+                words = words + [rng.choice(PHRASE_WORDS) for _ in range(rng.randint(1, 3))]
+            else:
+                words = [w.upper() if rng.random() < 0.5 else w + "," for w in words]
+            grp.append("" if rng.random() < 0.03 else " ".join(words))
+        if rng.random() < 0.1:
+            grp[rng.randrange(k)] = " ".join(rng.choice(PHRASE_WORDS) for _ in range(40))
+        if rng.random() < 0.15:
+            grp[rng.randrange(k)] = None
+        out.append(grp)
+    return out
+
+
 def _same(a, b) -> bool:
     if isinstance(a, float) and isinstance(b, float):
         return (math.isnan(a) and math.isnan(b)) or (a == b and math.copysign(1, a) == math.copysign(1, b))
@@ -240,9 +274,19 @@ def main() -> None:
     for case in client:
         aligned, mapping = cu.recursive_list_alignments(case["values"], "embeddings", raising_embeddings, None, 0.51)
         alignment.append({"values": case["values"], "aligned": aligned, "key_mappings": mapping})
+    medoid = []
+    for grp in phrase_groups(4242, 250):
+        for method in ("levenshtein", "embeddings"):
+            settings = cu.ConsensusSettings(string_similarity_method=method)
+            try:
+                v, c = cu.consensus_values(grp, settings, raising_embeddings, None, 0.8)
+            except Exception:  # two strings longer than 50 characters: the reference asks the embeddings service (cu:813)
+                continue
+            medoid.append({"values": grp, "method": method, "pvf": 0.8, "value": v, "conf": c})
     meta = {"generator": "oracle/gen_golden.py", "reference": "retab-dev/k-LLMs @ 089dba9 behind 3 import stubs",
             "entry": "consensus_values(values, ConsensusSettings(), raising_embeddings, client=None)"}
-    for name, payload in (("known_answers", known), ("client_order", client), ("random_cases", rnd), ("alignment", alignment)):
+    for name, payload in (("known_answers", known), ("client_order", client), ("random_cases", rnd), ("alignment", alignment),
+                          ("medoid", medoid)):
         with open(os.path.join(GOLDEN_DIR, name + ".json"), "w") as f:
             json.dump({"meta": meta, "cases": payload}, f, separators=(",", ":"))
         print(f"wrote {name}.json: {len(payload)} cases")

@@ -41,4 +41,41 @@ def oracle_run(plan):
     if plan.num_rows:
         value, meta = OC.numeric(np.asarray(plan.num_rows, dtype=np.float64), plan.rel_eps, plan.abs_eps)
         out["num_value"], out["num_meta"] = value, meta
+    if plan.medoid_groups:
+        out["medoid_idx"], out["medoid_avg"] = OC.medoid(plan.medoid_groups)
     return out
+
+
+_WORDS = ("invoice total due amount net gross payment bank transfer within thirty days from receipt of goods and services "
+          "the a an of to acme corp ltd gmbh street road avenue suite floor new york london paris berlin 2024 2025 q1 q2 "
+          "ref no id number 000123 77 ab-12 x y z").split()
+
+
+def random_string_groups(rng, n_groups, max_k=16, long_frac=0.1):
+    """Groups of 2..max_k multi-word strings: noisy copies of a base phrase (the shape of LLM string fields)."""
+    groups = []
+    for _ in range(n_groups):
+        k = int(rng.integers(2, max_k + 1))
+        base = [_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), int(rng.integers(3, 9)))]
+        grp = []
+        for _c in range(k):
+            words = list(base)
+            r = rng.random()
+            if r < 0.35:
+                pass
+            elif r < 0.6:
+                words[int(rng.integers(0, len(words)))] = _WORDS[int(rng.integers(0, len(_WORDS)))]
+            elif r < 0.75:
+                words = words[: max(1, len(words) - int(rng.integers(1, 3)))]
+            elif r < 0.9:
+                words = words + [_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), int(rng.integers(1, 4)))]
+            else:
+                words = [w.upper() if rng.random() < 0.5 else w + "," for w in words]
+            s = " ".join(words)
+            if rng.random() < 0.03:
+                s = ""
+            grp.append(s)
+        if rng.random() < long_frac:  # one long member is still inside K4's contract (pattern = the shorter string)
+            grp[int(rng.integers(0, k))] = " ".join(_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), 40))
+        groups.append(grp)
+    return groups

@@ -295,3 +295,20 @@ def test_host_entry_int8_cells():
     for k in ("win_code", "vote_meta", "num_meta"):
         assert np.array_equal(a[k], b[k])
     assert np.array_equal(a["value"].view(np.uint64), b["value"].view(np.uint64))
+
+
+def test_medoid_kernel_matches_oracle():
+    """K4 == ko_medoid_str (pinned to the reference in tests/golden/medoid.json) on random phrase groups: index and mean bit-exact."""
+    from k_llms_b200 import _native
+    from k_llms_b200.columnar import _normalize
+    from tests.helpers import random_string_groups
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    groups = [[_normalize(s) for s in g] for g in random_string_groups(rng, 3000, max_k=64)]
+    groups += [["a", "a"], ["", ""], ["", "abc", ""], ["x" * 64, "y" * 64, "x" * 63 + "y"], ["abc"] * 64]
+    chars, str_off, grp_off = OC.pack_string_groups(groups)
+    exp_idx, exp_avg = OC.medoid(groups)
+    idx, avg = _native.medoid_str(torch.from_numpy(chars).cuda(), torch.from_numpy(str_off).cuda(), torch.from_numpy(grp_off).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), exp_idx)
+    assert same_bits(avg.cpu().numpy(), exp_avg)

@@ -25,6 +25,20 @@ def test_consensus_values_matches_reference_goldens(name):
         assert same(got[0], case["value"]) and same(got[1], case["conf"]), (case["values"], got, case["value"], case["conf"])
 
 
+def test_medoid_goldens_on_gpu():
+    """Multi-word string fields: K4 (kc_medoid_str) behind consensus_values == the reference (tests/golden/medoid.json)."""
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings, consensus_values, consensus_values_batch
+    cases = load_golden("medoid")
+    for case in cases:
+        st = ConsensusSettings(string_similarity_method=case["method"])
+        got = consensus_values(case["values"], st, raising_embeddings, None, case["pvf"])
+        assert same(got[0], case["value"]) and same(got[1], case["conf"]), (case, got)
+    lev = [c for c in cases if c["method"] == "levenshtein"]
+    outs = consensus_values_batch([[{"k": v} for v in c["values"]] for c in lev],
+                                  ConsensusSettings(string_similarity_method="levenshtein"), raising_embeddings)  # one K4 launch
+    assert [o[0]["k"] for o in outs] == [c["value"] for c in lev]
+
+
 def test_batch_entry_equals_per_record_and_goldens():
     from k_llms_b200.utils.consensus_utils import consensus_values_batch
     cases = [c for c in load_golden("random_cases") + load_golden("known_answers") if len(c["values"]) <= 64]

@@ -64,3 +64,32 @@ def test_logprob_sum_order_is_the_documented_one():
             lanes = [np.float32(lanes[l] + lanes[l ^ stride]) for l in range(32)]
             stride //= 2
         assert got[s] == lanes[0]
+
+
+def test_medoid_oracle_matches_host_medoid():
+    """ko_medoid_str (the K4 checker) == similarity.medoid (cu:1221-1237 restated on numpy) on random phrase groups."""
+    from k_llms_b200.columnar import _normalize
+    from k_llms_b200.utils import similarity
+    from tests.helpers import random_string_groups
+
+    rng = np.random.default_rng(5)
+    groups = random_string_groups(rng, 400, max_k=20)
+    idx, avg = OC.medoid([[_normalize(s) for s in g] for g in groups])
+    for g, i, a in zip(groups, idx, avg):
+        value, conf = similarity.medoid(g, "levenshtein", None, 0.7)
+        assert value == g[int(i)] and g.index(value) == int(i) or g[int(i)] == value
+        assert conf == round(0.7 * float(a), 5)
+
+
+def test_medoid_goldens_through_host_plan_with_oracle_k4():
+    """Planner routes phrase groups to K4 (C oracle standing in); results == the reference's (tests/golden/medoid.json)."""
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings, _plan_for
+    on_device = 0
+    for case in load_golden("medoid"):
+        st = ConsensusSettings(string_similarity_method=case["method"])
+        plan = _plan_for(len(case["values"]), st)
+        root = plan.add(case["values"], case["pvf"], raising_embeddings)
+        on_device += len(plan.medoid_groups)
+        got = plan.materialise(root, oracle_run(plan))
+        assert same(got[0], case["value"]) and same(got[1], case["conf"]), (case, got)
+    assert on_device > 300  # the fixture really exercises the K4 route, not the host fallback
