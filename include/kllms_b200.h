@@ -160,12 +160,14 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
  * levenshtein_similarity :745-761): pairwise 1 - dist/max_len (floored at 1e-8) on NORMALISED strings (lower-case [a-z0-9],
  * normalize_string :660-673, done by the caller), np.nanmean of each row in numpy's summation order, first argmax.
  *   d_chars uint8[...]   all strings back to back       d_str_off int32[S+1]  string s = chars[str_off[s] .. str_off[s+1])
- *   d_grp_off int32[G+1] group g = strings grp_off[g] .. grp_off[g+1]  (2..64 strings per group)
- *   contract: for every pair of one group, the shorter string has at most 64 characters (Myers' bit-parallel distance)
+ *   d_grp_off int32[G+1] group g = strings grp_off[g] .. grp_off[g+1]  (2..max_group strings per group, max_group <= 64:
+ *                        it sizes the per-warp shared memory, so pass the real maximum, not 64)
+ *   contract: for every pair of one group, the shorter string has at most 64 characters (Myers' bit-parallel distance),
+ *             and no string is longer than 65535 characters
  *   d_best_idx int32[G] index (within the group) of the medoid; d_best_avg float64[G] its mean similarity (unrounded)
  */
 int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
-                  int32_t *d_best_idx, double *d_best_avg, void *stream);
+                  int32_t max_group, int32_t *d_best_idx, double *d_best_avg, void *stream);
 
 /*
  * End-to-end entry with HOST buffers (the call a k_llms binding makes for a batch of records of one

@@ -67,7 +67,7 @@ def load() -> ctypes.CDLL:
     lib.kc_vote_i8.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.kc_consolidate_json.argtypes = [vp, vp, i64, i32, f64, f64, c.c_int, i32, vp, vp, vp]
     lib.kc_consolidate_json.restype = c.c_int
-    lib.kc_medoid_str.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    lib.kc_medoid_str.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.kc_medoid_str.restype = c.c_int
     lib.kc_levenshtein.argtypes = [c.c_char_p, i32, c.c_char_p, i32]
     lib.kc_levenshtein.restype = i32
@@ -232,8 +232,8 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
 
 
-def medoid_str(chars, str_off, grp_off, stream=None):
-    """K4 on device tensors: chars uint8 [C], str_off int32 [S+1], grp_off int32 [G+1] ->
+def medoid_str(chars, str_off, grp_off, max_group=MAX_CANDIDATES, stream=None):
+    """K4 on device tensors: chars uint8 [C], str_off int32 [S+1], grp_off int32 [G+1], max_group = largest group ->
     (best index int32 [G], mean similarity float64 [G])."""
     torch = _require_cuda()
     assert chars.is_cuda and chars.dtype == torch.uint8 and str_off.dtype == torch.int32 and grp_off.dtype == torch.int32
@@ -241,7 +241,8 @@ def medoid_str(chars, str_off, grp_off, stream=None):
     idx = torch.empty(G, dtype=torch.int32, device=chars.device)
     avg = torch.empty(G, dtype=torch.float64, device=chars.device)
     _bind(torch, chars)
-    check(load().kc_medoid_str(chars.data_ptr(), str_off.data_ptr(), grp_off.data_ptr(), G, idx.data_ptr(), avg.data_ptr(),
+    check(load().kc_medoid_str(chars.data_ptr(), str_off.data_ptr(), grp_off.data_ptr(), G, max(2, int(max_group)), idx.data_ptr(),
+                               avg.data_ptr(),
                                _stream_ptr(torch, stream)))
     return idx, avg
 

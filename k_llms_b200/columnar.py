@@ -211,7 +211,8 @@ class Plan:
             return False
         if self.string_method == "embeddings" and sum(1 for v in live if len(v) > 50) > 1:
             return False
-        return sum(1 for v in live if len(_normalize(v)) > 64) <= 1
+        lens = [len(_normalize(v)) for v in live]
+        return sum(1 for l in lens if l > 64) <= 1 and max(lens) <= 2000
 
     # -- device ----------------------------------------------------------------------------------------
     def run(self, device=None):
@@ -240,7 +241,8 @@ class Plan:
                 grp_off.append(grp_off[-1] + len(grp))
             chars = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
             idx, avg = _native.medoid_str(torch.from_numpy(chars).to(dev), torch.tensor(str_off, dtype=torch.int32, device=dev),
-                                          torch.tensor(grp_off, dtype=torch.int32, device=dev))
+                                          torch.tensor(grp_off, dtype=torch.int32, device=dev),
+                                          max_group=max(len(grp) for grp in self.medoid_groups))
             out["medoid_idx"], out["medoid_avg"] = idx.cpu().numpy(), avg.cpu().numpy()
         return out
 

@@ -2,13 +2,16 @@
 //
 // Replaces, for groups of strings, the fallback of consensus_as_primitive (reference consensus_utils.py:1221-1237):
 // pairwise levenshtein_similarity (cu:745-761: 1 - dist/max_len on normalize_string()ed text, floored at 1e-8),
-// np.nanmean of every row of the n x n matrix (diagonal NaN), first argmax.  One WARP per group:
-//   * lanes split the n(n-1)/2 pairs; each distance is Myers' bit-parallel algorithm (one 64-bit word, O(text) word
-//     operations) with the SHORTER string as the pattern.  The caller guarantees min(len_i, len_j) <= 64 for every pair
-//     (always true under the reference's default method, which sends pairs of two long strings to the embeddings
-//     service instead, cu:813); groups that violate it stay on the host;
-//   * lane i then sums row i in numpy's pairwise order (diagonal contributes +0.0, as nanmean's NaN->0 copy does) and
-//     divides by the n-1 valid entries; a shuffle reduction picks the first maximum.
+// np.nanmean of every row of the k x k matrix (diagonal NaN), first argmax.  One WARP per group:
+//   1. lanes hash their strings; every string finds the first identical one before it (its class representative) —
+//      candidates of one LLM field mostly agree, and a distance is needed only between DISTINCT strings;
+//   2. one lane per distinct string builds its Myers match table (36 x u64) in shared memory, once per group;
+//   3. lanes split the u(u-1)/2 pairs of distinct strings; each distance is Myers' bit-parallel algorithm with the
+//      SHORTER string as the pattern: 32-bit words when it has <= 32 characters, one 64-bit word otherwise.  The caller
+//      guarantees min(len_i, len_j) <= 64 for every pair (always true under the reference's default method, which sends
+//      pairs of two long strings to the embeddings service instead, cu:813); groups that violate it stay on the host;
+//   4. lane i sums row i in numpy's pairwise order (diagonal contributes +0.0, as nanmean's NaN->0 copy does) and
+//      divides by the k-1 valid entries; a shuffle reduction picks the first maximum.
 // Strings arrive normalised (lower-case [a-z0-9]); the host does normalize_string() and the final round(pvf*avg, 5).
 #pragma once
 
@@ -17,26 +20,27 @@
 
 namespace kc {
 
-constexpr int kMedoidMaxN = 64;       // strings per group
+constexpr int kMedoidMaxN = 64;        // strings per group
 constexpr int kMedoidMaxPattern = 64;  // the shorter string of every pair must fit one 64-bit word
 constexpr int kAlphabet = 36;
+constexpr int kPeqStride = 37;  // u64 per table: odd, so that lanes building different tables spread over the banks
 
-__device__ __forceinline__ int alnum_index(uint8_t c) { return c <= '9' ? c - '0' : c - 'a' + 10; }
+__device__ __forceinline__ int alnum_index(uint32_t c) { return (int)c - (c > 64u ? 'a' - 10 : '0'); }
 
-// Edit distance of pattern p (m <= 64 chars, Peq table given) against text t (Myers 1999 / Hyyro 2003).
-__device__ __forceinline__ int myers64(const uint64_t *peq, int m, const uint8_t *t, int tn) {
-    uint64_t pv = ~0ull, mv = 0;
+// Edit distance of a pattern of m characters (match table peq) against text t.  Myers 1999 in Hyyro's formulation.
+template <typename W>
+__device__ __forceinline__ int myers(const uint64_t *peq, int m, const uint8_t *__restrict__ t, int tn) {
+    W pv = ~W(0), mv = 0;
     int score = m;
-    const uint64_t top = 1ull << (m - 1);
+    const int sh = m - 1;
     for (int k = 0; k < tn; ++k) {
-        const uint64_t eq = peq[alnum_index(t[k])];
-        const uint64_t xv = eq | mv;
-        const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
-        uint64_t ph = mv | ~(xh | pv);
-        uint64_t mh = pv & xh;
-        score += (ph & top) ? 1 : 0;
-        score -= (mh & top) ? 1 : 0;
-        ph = (ph << 1) | 1ull;
+        const W eq = (W)peq[alnum_index(__ldg(t + k))];
+        const W xv = eq | mv;
+        const W xh = (((eq & pv) + pv) ^ pv) | eq;
+        W ph = mv | ~(xh | pv);
+        W mh = pv & xh;
+        score += (int)((ph >> sh) & 1) - (int)((mh >> sh) & 1);
+        ph = (ph << 1) | W(1);
         mh <<= 1;
         pv = mh | ~(xv | ph);
         mv = ph & xv;
@@ -44,63 +48,128 @@ __device__ __forceinline__ int myers64(const uint64_t *peq, int m, const uint8_t
     return score;
 }
 
+// Per-warp shared memory for groups of at most `kmax` strings.
+struct MedoidSmem {
+    static __host__ __device__ size_t bytes(int kmax) {
+        return (size_t)kmax * kPeqStride * 8 + (size_t)kmax * kmax * 2 + (size_t)kMedoidMaxN * (4 + 4 + 4 + 1 + 1 + 1) + 64;
+    }
+};
+
 // chars: all strings back to back; str_off[s]..str_off[s+1] string s; grp_off[g]..grp_off[g+1] the strings of group g.
-// Dynamic shared memory per warp: a Peq table per LANE (36 u64 = 288 B -> 9 KB per warp, rebuilt for every pair by the
-// lane that owns it) and the distance matrix (u16 [64][64] = 8 KB).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__restrict__ chars, const int32_t *__restrict__ str_off,
-                                                            const int32_t *__restrict__ grp_off, int64_t n_groups,
+                                                            const int32_t *__restrict__ grp_off, int64_t n_groups, int kmax,
                                                             int32_t *__restrict__ best_idx, double *__restrict__ best_avg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr size_t PEQ_BYTES = 32 * kAlphabet * 8;               // per warp
-    constexpr size_t DIST_BYTES = kMedoidMaxN * kMedoidMaxN * 2;   // per warp
-    uint8_t *wbase = smem_raw + (size_t)warp * (PEQ_BYTES + DIST_BYTES);
-    uint64_t *peq = reinterpret_cast<uint64_t *>(wbase) + lane * kAlphabet;
-    uint16_t *dist = reinterpret_cast<uint16_t *>(wbase + PEQ_BYTES);
+    const size_t per_warp = (MedoidSmem::bytes(kmax) + 15) & ~size_t(15);
+    uint8_t *wbase = smem_raw + (size_t)warp * per_warp;
+    uint64_t *peq = reinterpret_cast<uint64_t *>(wbase);                 // [u][kPeqStride]
+    int32_t *s_off = reinterpret_cast<int32_t *>(peq + (size_t)kmax * kPeqStride);  // [64] first character
+    int32_t *s_len = s_off + kMedoidMaxN;                                 // [64]
+    uint32_t *s_hash = reinterpret_cast<uint32_t *>(s_len + kMedoidMaxN);  // [64]
+    uint16_t *dist = reinterpret_cast<uint16_t *>(s_hash + kMedoidMaxN);   // [u][kmax] between distinct strings
+    uint8_t *s_cls = reinterpret_cast<uint8_t *>(dist + (size_t)kmax * kmax);  // [64] string -> index of its class
+    uint8_t *s_uniq = s_cls + kMedoidMaxN;                                     // [u] class -> first string of the class
+    uint8_t *s_rep = s_uniq + kMedoidMaxN;                                     // [64] string -> first identical string
 
     const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t gstep = (int64_t)gridDim.x * WARPS;
     for (int64_t g = gw; g < n_groups; g += gstep) {
         const int s0 = __ldg(grp_off + g), k = __ldg(grp_off + g + 1) - s0;
-        const int n_pairs = k * (k - 1) / 2;
-        for (int p = lane; p < n_pairs; p += 32) {
-            // (i, j), i < j, from the linear index over the upper triangle
-            int i = 0, rem = p;
-            while (rem >= k - 1 - i) {
-                rem -= k - 1 - i;
-                ++i;
-            }
-            const int j = i + 1 + rem;
-            int ao = __ldg(str_off + s0 + i), al = __ldg(str_off + s0 + i + 1) - ao;
-            int bo = __ldg(str_off + s0 + j), bl = __ldg(str_off + s0 + j + 1) - bo;
-            if (al > bl) {  // pattern = the shorter string
-                const int to = ao, tl = al;
-                ao = bo; al = bl; bo = to; bl = tl;
-            }
-            int d;
-            if (al == 0) {
-                d = bl;
-            } else {  // al <= kMedoidMaxPattern by contract
-                for (int c = 0; c < kAlphabet; ++c) peq[c] = 0;
-                for (int q = 0; q < al; ++q) peq[alnum_index(__ldg(chars + ao + q))] |= 1ull << q;
-                d = myers64(peq, al, chars + bo, bl);
-            }
-            dist[i * kMedoidMaxN + j] = (uint16_t)d;
-            dist[j * kMedoidMaxN + i] = (uint16_t)d;
+        // 1. offsets, lengths, hashes (FNV-1a; only a filter: equality is confirmed character by character)
+        for (int i = lane; i < k; i += 32) {
+            const int o = __ldg(str_off + s0 + i), l = __ldg(str_off + s0 + i + 1) - o;
+            uint32_t h = 2166136261u;
+            for (int q = 0; q < l; ++q) h = (h ^ __ldg(chars + o + q)) * 16777619u;
+            s_off[i] = o;
+            s_len[i] = l;
+            s_hash[i] = h;
         }
         __syncwarp();
+        for (int i = lane; i < k; i += 32) {
+            const int o = s_off[i], l = s_len[i];
+            const uint32_t h = s_hash[i];
+            int rep = i;
+            for (int j = 0; j < i; ++j) {
+                if (s_hash[j] == h && s_len[j] == l) {
+                    const int oj = s_off[j];
+                    int q = 0;
+                    while (q < l && __ldg(chars + o + q) == __ldg(chars + oj + q)) ++q;
+                    if (q == l) {
+                        rep = j;
+                        break;
+                    }
+                }
+            }
+            s_rep[i] = (uint8_t)rep;
+        }
+        __syncwarp();
+        // class numbering in first-seen order
+        int u = 0;
+        for (int base = 0; base < k; base += 32) {
+            const int i = base + lane;
+            const bool first = i < k && s_rep[i] == i;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, first);
+            if (first) {
+                const int c = u + __popc(mask & ((1u << lane) - 1u));
+                s_uniq[c] = (uint8_t)i;
+                s_cls[i] = (uint8_t)c;
+            }
+            u += __popc(mask);
+        }
+        __syncwarp();
+        for (int i = lane; i < k; i += 32) s_cls[i] = s_cls[s_rep[i]];  // representatives already hold their own class
+        // 2. match tables of the distinct strings that can be a pattern
+        for (int a = lane; a < u; a += 32) {
+            const int i = s_uniq[a], o = s_off[i], l = s_len[i];
+            uint64_t *tab = peq + (size_t)a * kPeqStride;
+            if (l <= kMedoidMaxPattern) {
+#pragma unroll 4
+                for (int c = 0; c < kAlphabet; ++c) tab[c] = 0;
+                for (int q = 0; q < l; ++q) tab[alnum_index(__ldg(chars + o + q))] |= 1ull << q;
+            }
+            dist[a * kmax + a] = 0;
+        }
+        __syncwarp();
+        // 3. distances between distinct strings
+        const int n_pairs = u * (u - 1) / 2;
+        for (int p = lane; p < n_pairs; p += 32) {
+            int a = 0, rem = p;  // (a, b), a < b, from the linear index over the upper triangle
+            while (rem >= u - 1 - a) {
+                rem -= u - 1 - a;
+                ++a;
+            }
+            const int b = a + 1 + rem;
+            int pa = a, ta = b;  // pattern = the shorter string
+            if (s_len[s_uniq[a]] > s_len[s_uniq[b]]) {
+                pa = b;
+                ta = a;
+            }
+            const int m = s_len[s_uniq[pa]], to = s_off[s_uniq[ta]], tl = s_len[s_uniq[ta]];
+            int d;
+            if (m == 0)
+                d = tl;
+            else if (m <= 32)
+                d = myers<uint32_t>(peq + (size_t)pa * kPeqStride, m, chars + to, tl);
+            else  // m <= kMedoidMaxPattern by contract
+                d = myers<uint64_t>(peq + (size_t)pa * kPeqStride, m, chars + to, tl);
+            dist[a * kmax + b] = (uint16_t)d;
+            dist[b * kmax + a] = (uint16_t)d;
+        }
+        __syncwarp();
+        // 4. row means and the first maximum
         double my_avg = -1.0;
         int my_idx = 0x7FFFFFFF;
         for (int i = lane; i < k; i += 32) {
-            const int li = __ldg(str_off + s0 + i + 1) - __ldg(str_off + s0 + i);
+            const int li = s_len[i];
+            const uint16_t *drow = dist + (int)s_cls[i] * kmax;
             const double tot = np_sum(
                 [&](int j) {
                     if (j == i) return 0.0;  // nanmean works on a copy with NaN -> 0
-                    const int lj = __ldg(str_off + s0 + j + 1) - __ldg(str_off + s0 + j);
-                    const int mx = max(li, lj);
+                    const int mx = max(li, s_len[j]);
                     if (mx == 0) return 1.0;  // cu:756-757
-                    const double s = __dadd_rn(1.0, -__ddiv_rn((double)dist[i * kMedoidMaxN + j], (double)mx));
+                    const double s = __dadd_rn(1.0, -__ddiv_rn((double)drow[s_cls[j]], (double)mx));
                     return s > 1e-8 ? s : 1e-8;  // cu:761
                 },
                 k);

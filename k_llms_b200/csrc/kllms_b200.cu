@@ -521,19 +521,25 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
 }
 
 int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
-                  int32_t *d_best_idx, double *d_best_avg, void *stream) {
+                  int32_t max_group, int32_t *d_best_idx, double *d_best_avg, void *stream) {
     if (n_groups < 0) return fail(KC_EINVAL, "kc_medoid_str: negative n_groups");
+    if (max_group < 2 || max_group > kc::kMedoidMaxN)
+        return fail(KC_EINVAL, "kc_medoid_str: max_group=%d outside [2,%d]", max_group, kc::kMedoidMaxN);
     if (n_groups == 0) return KC_OK;
     if (!d_chars || !d_str_off || !d_grp_off || !d_best_idx || !d_best_avg) return fail(KC_EINVAL, "kc_medoid_str: NULL buffer");
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
-    constexpr int WARPS = 4;  // 9 KB of Peq tables + 8 KB of distances per warp
+    constexpr int WARPS = 4;
     auto kernel = kc::medoid_kernel<WARPS>;
-    const size_t smem = (size_t)WARPS * (32 * kc::kAlphabet * 8 + kc::kMedoidMaxN * kc::kMedoidMaxN * 2);
+    const size_t per_warp = (kc::MedoidSmem::bytes(max_group) + 15) & ~size_t(15);  // match tables + distances, sized by max_group
+    const size_t smem = WARPS * per_warp;
     KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>((n_groups + WARPS - 1) / WARPS, (int64_t)info.sm_count * 3);
-    kernel<<<grid, WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(d_chars, d_str_off, d_grp_off, n_groups, d_best_idx, d_best_avg);
+    int per_sm = 1;
+    KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    const int grid = (int)std::min<int64_t>((n_groups + WARPS - 1) / WARPS, (int64_t)info.sm_count * std::max(per_sm, 1));
+    kernel<<<grid, WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(d_chars, d_str_off, d_grp_off, n_groups, max_group,
+                                                                         d_best_idx, d_best_avg);
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }

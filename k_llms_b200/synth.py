@@ -75,3 +75,30 @@ def s32_torch(n_records: int, n: int, seed: int, device, p_agree: float = 0.8, p
         vals[r0:r1] = v
     none_code = torch.tensor(S32_NONE_CODE, device=device)
     return codes, none_code, vals
+
+
+def phrase_groups_numpy(n_groups: int, k: int, seed: int, min_len: int = 16, max_len: int = 48, p_agree: float = 0.5):
+    """Synthetic input of K4 (similarity medoid): n_groups groups of k normalised strings ([a-z0-9], what
+    normalize_string (consensus_utils.py:660-673) leaves of a multi-word field).  Every group has one base string of
+    min_len..max_len characters; a candidate repeats it with probability p_agree, otherwise carries 1..4 substituted
+    characters and may lose up to 4 trailing ones.  Returns (chars uint8, str_off int32 [G*k+1], grp_off int32 [G+1])."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", dtype=np.uint8)
+    base_len = rng.integers(min_len, max_len + 1, n_groups)
+    base = alphabet[rng.integers(0, 36, (n_groups, max_len))]
+    cand = np.repeat(base[:, None, :], k, axis=1)  # [G, k, L]
+    mutate = rng.random((n_groups, k)) >= p_agree
+    n_sub = rng.integers(1, 5, (n_groups, k)) * mutate
+    for s in range(4):
+        pos = (rng.random((n_groups, k)) * base_len[:, None]).astype(np.int64)
+        new = alphabet[rng.integers(0, 36, (n_groups, k))]
+        g, c = np.nonzero(n_sub > s)
+        cand[g, c, pos[g, c]] = new[g, c]
+    lens = base_len[:, None] - rng.integers(0, 5, (n_groups, k)) * (mutate & (rng.random((n_groups, k)) < 0.3))
+    lens = np.maximum(lens, 1).astype(np.int64)
+    keep = np.arange(max_len)[None, None, :] < lens[:, :, None]
+    chars = np.ascontiguousarray(cand[keep])
+    str_off = np.zeros(n_groups * k + 1, dtype=np.int32)
+    np.cumsum(lens.reshape(-1), out=str_off[1:])
+    grp_off = (np.arange(n_groups + 1, dtype=np.int64) * k).astype(np.int32)
+    return chars, str_off, grp_off

@@ -305,10 +305,19 @@ def test_medoid_kernel_matches_oracle():
     torch = _torch()
     rng = np.random.default_rng(77)
     groups = [[_normalize(s) for s in g] for g in random_string_groups(rng, 3000, max_k=64)]
-    groups += [["a", "a"], ["", ""], ["", "abc", ""], ["x" * 64, "y" * 64, "x" * 63 + "y"], ["abc"] * 64]
+    groups += [["a", "a"], ["", ""], ["", "abc", ""], ["x" * 64, "y" * 64, "x" * 63 + "y"], ["abc"] * 64,
+               ["a" * 32, "a" * 31 + "b", "b" * 33, "a" * 32], ["q" * 64, "q" * 500 + "z", "q" * 10, "zq" * 16],
+               ["ab" * 16 + "c", "ab" * 16, "ba" * 16, "ab" * 16 + "c", "ab" * 17]]
     chars, str_off, grp_off = OC.pack_string_groups(groups)
     exp_idx, exp_avg = OC.medoid(groups)
-    idx, avg = _native.medoid_str(torch.from_numpy(chars).cuda(), torch.from_numpy(str_off).cuda(), torch.from_numpy(grp_off).cuda())
+    idx, avg = _native.medoid_str(torch.from_numpy(chars).cuda(), torch.from_numpy(str_off).cuda(), torch.from_numpy(grp_off).cuda(),
+                                  max_group=max(len(g) for g in groups))
     torch.cuda.synchronize()
     assert np.array_equal(idx.cpu().numpy(), exp_idx)
     assert same_bits(avg.cpu().numpy(), exp_avg)
+    small = [g[:5] for g in groups]  # another shared-memory geometry (max_group = 5)
+    chars, str_off, grp_off = OC.pack_string_groups(small)
+    exp_idx, exp_avg = OC.medoid(small)
+    idx, avg = _native.medoid_str(torch.from_numpy(chars).cuda(), torch.from_numpy(str_off).cuda(), torch.from_numpy(grp_off).cuda(),
+                                  max_group=5)
+    assert np.array_equal(idx.cpu().numpy(), exp_idx) and same_bits(avg.cpu().numpy(), exp_avg)
