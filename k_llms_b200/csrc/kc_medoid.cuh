@@ -10,6 +10,7 @@
 //      SHORTER string as the pattern: 32-bit words when it has <= 32 characters, one 64-bit word otherwise.  The caller
 //      guarantees min(len_i, len_j) <= 64 for every pair (always true under the reference's default method, which sends
 //      pairs of two long strings to the embeddings service instead, cu:813); groups that violate it stay on the host;
+//      the similarity (cu:758-761) is stored once per pair of classes;
 //   4. lane i sums row i in numpy's pairwise order (diagonal contributes +0.0, as nanmean's NaN->0 copy does) and
 //      divides by the k-1 valid entries; a shuffle reduction picks the first maximum.
 // Strings arrive normalised (lower-case [a-z0-9]); the host does normalize_string() and the final round(pvf*avg, 5).
@@ -51,7 +52,7 @@ __device__ __forceinline__ int myers(const uint64_t *peq, int m, const uint8_t *
 // Per-warp shared memory for groups of at most `kmax` strings.
 struct MedoidSmem {
     static __host__ __device__ size_t bytes(int kmax) {
-        return (size_t)kmax * kPeqStride * 8 + (size_t)kmax * kmax * 2 + (size_t)kMedoidMaxN * (4 + 4 + 4 + 1 + 1 + 1) + 64;
+        return (size_t)kmax * kPeqStride * 8 + (size_t)kmax * kmax * 8 + (size_t)kMedoidMaxN * (4 + 4 + 4 + 1 + 1 + 1) + 64;
     }
 };
 
@@ -65,11 +66,11 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
     const size_t per_warp = (MedoidSmem::bytes(kmax) + 15) & ~size_t(15);
     uint8_t *wbase = smem_raw + (size_t)warp * per_warp;
     uint64_t *peq = reinterpret_cast<uint64_t *>(wbase);                 // [u][kPeqStride]
-    int32_t *s_off = reinterpret_cast<int32_t *>(peq + (size_t)kmax * kPeqStride);  // [64] first character
+    double *sim = reinterpret_cast<double *>(peq + (size_t)kmax * kPeqStride);  // [u][kmax] similarity of two classes
+    int32_t *s_off = reinterpret_cast<int32_t *>(sim + (size_t)kmax * kmax);  // [64] first character
     int32_t *s_len = s_off + kMedoidMaxN;                                 // [64]
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(s_len + kMedoidMaxN);  // [64]
-    uint16_t *dist = reinterpret_cast<uint16_t *>(s_hash + kMedoidMaxN);   // [u][kmax] between distinct strings
-    uint8_t *s_cls = reinterpret_cast<uint8_t *>(dist + (size_t)kmax * kmax);  // [64] string -> index of its class
+    uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_hash + kMedoidMaxN);    // [64] string -> index of its class
     uint8_t *s_uniq = s_cls + kMedoidMaxN;                                     // [u] class -> first string of the class
     uint8_t *s_rep = s_uniq + kMedoidMaxN;                                     // [64] string -> first identical string
 
@@ -87,7 +88,29 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
             s_hash[i] = h;
         }
         __syncwarp();
-        for (int i = lane; i < k; i += 32) {
+        bool matched = false;  // every string found its representative through the hash match below
+        if (k <= 32) {
+            const bool live = lane < k;
+            const uint32_t key = live ? (s_hash[lane] ^ ((uint32_t)s_len[lane] * 0x9E3779B1u)) : (0xFFFFFFFFu - lane);
+            const int rep = __ffs(__match_any_sync(0xFFFFFFFFu, key)) - 1;  // lowest lane with the same (hash, length)
+            bool same = true;
+            if (live && rep != lane) {
+                const int o = s_off[lane], orep = s_off[rep], l = s_len[lane];
+                const uint8_t *pa = chars + o, *pb = chars + orep;
+                uint32_t diff = s_len[rep] == l ? 0u : 1u;  // no early exit: equal hashes almost always mean equal strings
+                int q = 0;
+                if (diff == 0) {
+                    for (; q + 4 <= l; q += 4)
+                        diff |= (uint32_t)(__ldg(pa + q) ^ __ldg(pb + q)) | (uint32_t)(__ldg(pa + q + 1) ^ __ldg(pb + q + 1)) |
+                                (uint32_t)(__ldg(pa + q + 2) ^ __ldg(pb + q + 2)) | (uint32_t)(__ldg(pa + q + 3) ^ __ldg(pb + q + 3));
+                    for (; q < l; ++q) diff |= (uint32_t)(__ldg(pa + q) ^ __ldg(pb + q));
+                }
+                same = diff == 0;
+            }
+            matched = __all_sync(0xFFFFFFFFu, same);  // a hash collision sends the group to the exact scan
+            if (matched && live) s_rep[lane] = (uint8_t)rep;
+        }
+        for (int i = lane; i < k && !matched; i += 32) {
             const int o = s_off[i], l = s_len[i];
             const uint32_t h = s_hash[i];
             int rep = i;
@@ -129,7 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
                 for (int c = 0; c < kAlphabet; ++c) tab[c] = 0;
                 for (int q = 0; q < l; ++q) tab[alnum_index(__ldg(chars + o + q))] |= 1ull << q;
             }
-            dist[a * kmax + a] = 0;
+            sim[a * kmax + a] = 1.0;  // identical strings: 1 - 0/max_len, or the empty-pair rule cu:756-757
         }
         __syncwarp();
         // 3. distances between distinct strings
@@ -154,25 +177,20 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
                 d = myers<uint32_t>(peq + (size_t)pa * kPeqStride, m, chars + to, tl);
             else  // m <= kMedoidMaxPattern by contract
                 d = myers<uint64_t>(peq + (size_t)pa * kPeqStride, m, chars + to, tl);
-            dist[a * kmax + b] = (uint16_t)d;
-            dist[b * kmax + a] = (uint16_t)d;
+            // cu:758-761; tl is the longer length (> 0, the strings differ)
+            double sv = __dadd_rn(1.0, -__ddiv_rn((double)d, (double)tl));
+            sv = sv > 1e-8 ? sv : 1e-8;
+            sim[a * kmax + b] = sv;
+            sim[b * kmax + a] = sv;
         }
         __syncwarp();
         // 4. row means and the first maximum
         double my_avg = -1.0;
         int my_idx = 0x7FFFFFFF;
         for (int i = lane; i < k; i += 32) {
-            const int li = s_len[i];
-            const uint16_t *drow = dist + (int)s_cls[i] * kmax;
-            const double tot = np_sum(
-                [&](int j) {
-                    if (j == i) return 0.0;  // nanmean works on a copy with NaN -> 0
-                    const int mx = max(li, s_len[j]);
-                    if (mx == 0) return 1.0;  // cu:756-757
-                    const double s = __dadd_rn(1.0, -__ddiv_rn((double)drow[s_cls[j]], (double)mx));
-                    return s > 1e-8 ? s : 1e-8;  // cu:761
-                },
-                k);
+            const double *srow = sim + (int)s_cls[i] * kmax;
+            const double tot = np_sum([&](int j) { return j == i ? 0.0 : srow[s_cls[j]]; },  // nanmean: NaN -> 0 copy
+                                      k);
             const double avg = __ddiv_rn(tot, (double)(k - 1));
             if (avg > my_avg) {  // first maximum within this lane's rows (ascending i)
                 my_avg = avg;
