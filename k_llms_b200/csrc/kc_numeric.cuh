@@ -21,6 +21,7 @@
 #include <utility>
 
 #include "kc_common.cuh"
+#include "kc_csa.cuh"
 #include "kc_vote.cuh"  // MaskOf, Swizzle, popc_m
 
 namespace kc {
@@ -498,6 +499,236 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
 // conflict-free LDS.128 and copied to a [cell][thread] plane: the data-dependent accesses of the core would
 // bank-conflict on a row-per-thread layout, while in the plane the bank depends on the thread only.  The stage
 // is handed back to the TMA unit right after that copy.
+// ---------------------------------------------------------------- K2 fast path: a strict majority of identical cells
+//
+// Candidates of one field mostly agree bit for bit.  If one value v fills a strict majority of the m finite cells, its
+// cluster is the unique largest one whatever the rest looks like (cu:1145-1187), and if no other finite cell is close
+// to v the cluster is exactly the c copies of v: value = np.mean([v]*c), support = c — no sort, no closeness chain.
+//   1. guess v as the bitwise "at least half" vote over the cells (carry-save adder tree, kc_csa.cuh);
+//   2. verify exactly: c = cells bit-identical to v, 2c > m;
+//   3. the nearest finite cells below and above v are found on the HIGH words only (two unsigned min/max scans; only
+//      groups without negative cells are taken, so raw high words are ordered like the values); each stands for every
+//      double sharing that high word.  They are certified far from v with
+//      fl() monotonicity alone: |v - x| >= fl(v - x_nearest_possible) and tol(x, v) <= max(abs, fl(rel * max(|x|_max,
+//      |v|, 1))) for rel >= 0 (the launcher rejects rel < 0);
+//   4. anything else — no majority, a neighbour within reach, a cell sharing v's high word, a single non-None cell —
+//      is NOT decided here: the caller queues the group for numeric_core (exact, general).
+// Returns true when (value, meta) are final.
+// census += 0x100 for a non-finite cell, += 0x10000 for None, += 0x10001 for absent — as PREDICATED adds (the compiler
+// prefers select + add, two ALU-pipe instructions more per cell)
+__device__ __forceinline__ void census_cell(uint32_t h, uint32_t &census) {
+    asm("{\n\t.reg .pred p, q;\n\t.reg .u32 u, w;\n\t"
+        "setp.ge.u32 p, %1, 0x7FF00000;\n\t"
+        "@p add.u32 %0, %0, 256;\n\t"
+        "sub.u32 u, %1, %2;\n\t"
+        "setp.lt.u32 q, u, 2;\n\t"
+        "add.u32 w, u, 65536;\n\t"
+        "@q add.u32 %0, %0, w;\n\t}"
+        : "+r"(census)
+        : "r"(h), "n"(kNoneHi));
+}
+
+// a cell with v's high word: count it, and collect any difference of its low word
+__device__ __forceinline__ void match_cell(uint32_t h, uint32_t l, uint32_t hv, uint32_t lv, uint32_t &c, uint32_t &bad) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, %2, %4;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "@p lop3.b32 %1, %1, %3, %5, 0xF6;\n\t}"  // bad | (l ^ lv)
+        : "+r"(c), "+r"(bad)
+        : "r"(h), "r"(l), "r"(hv), "r"(lv));
+}
+
+template <int N>
+__device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint32_t (&lo)[N], double rel_eps, double thr,
+                                             double &value, uint32_t &meta) {
+    // Only groups without a negative cell are decided here (raw high words of non-negative doubles are already
+    // ordered like the values; -0.0 counts as negative).  Non-finite <=> hi >= 0x7FF00000.
+    uint32_t any = 0, census = 0;  // census = tagged << 16 | nonfinite << 8 | absent
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        any |= hi[i];
+        census_cell(hi[i], census);
+    }
+    const uint32_t hv = at_least_half(hi), lv = at_least_half(lo);
+    // d = hi - hv as a signed number: < 0 below v, > 0 above (all high words are < 2^31 here).  Unsigned max of d is
+    // the nearest cell below (if any is below), unsigned min of d - 1 the nearest above.
+    uint32_t c = 0, bad = 0, below = 0, above = 0xFFFFFFFFu;
+    const uint32_t neg_hv = 0u - hv, neg_hv1 = ~hv;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        below = max(below, hi[i] + neg_hv);
+        above = min(above, hi[i] + neg_hv1);
+        match_cell(hi[i], lo[i], hv, lv, c, bad);
+    }
+    const uint32_t nonfinite = (census >> 8) & 0xFFu, tagged = census >> 16, absent = census & 0xFFu;
+    // a negative cell / the guess is not a finite value / no strict majority of the finite cells / one non-None cell
+    if ((any & 0x80000000u) != 0 || hv >= 0x7FF00000u || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2))
+        return false;
+    const double v = __hiloint2double((int)hv, (int)lv);
+    // Neighbours: every double with the high word hb is <= (hb, ~0) < v, every one with ha is in [(ha, 0), (ha, ~0)].
+    // close(a, b) <=> |a-b| <= max(abs, rel*max(|a|,|b|,1)) = max(thr, fl(rel*max(|a|,|b|))) with thr = max(abs, rel),
+    // because fl(rel * .) is monotone; so "certainly far" <=> d > thr and d > fl(rel * upper bound of the magnitudes).
+    const uint32_t hb = hv + below, ha = hv + above + 1u;
+    const double db = __dadd_rn(v, -__hiloint2double((int)hb, -1));
+    const double da = __dadd_rn(__hiloint2double((int)ha, 0), -v);
+    const bool far_b = db > thr && db > __dmul_rn(rel_eps, v);
+    const bool far_a = da > thr && da > __dmul_rn(rel_eps, __hiloint2double((int)ha, -1));
+    const bool has_b = below >= 0x80000000u, has_a = above < 0x7FFFFFFFu && ha < 0x7FF00000u;
+    if ((has_b && !far_b) || (has_a && !far_a)) return false;
+    // np.mean of c copies of v in numpy's summation order: for c >= 8 the eight accumulators are identical (r = the
+    // sequential sum of c/8 copies) and their pairwise sum is 8r exactly; then the c%8 stragglers one by one.
+    double res = -0.0;  // -0.0 + v == v
+    if (c >= 8) {
+        double r = v;
+#pragma unroll
+        for (int k = 2; k <= N / 8; ++k)
+            if ((int)(c >> 3) >= k) r = __dadd_rn(r, v);
+        res = __dmul_rn(r, 8.0);
+    }
+    const uint32_t tail = c & 7u;
+#pragma unroll
+    for (int k = 1; k <= 7; ++k)
+        if ((int)tail >= k) res = __dadd_rn(res, v);
+    value = __ddiv_rn(__dadd_rn(0.0, res), (double)c);
+    meta = (c << 6) + (((uint32_t)N - tagged) << 13) + (((uint32_t)N - absent) << 20) + ((uint32_t)KC_FLAG_HAS_VALUE << 27);
+    return true;
+}
+
+// The TMA pipeline of numeric_tma_kernel with the fast path in front: cells stay in registers; groups the fast path
+// does not decide are queued per warp and, 32 at a time, re-read from global memory (L2-resident) and given to
+// numeric_core with every lane busy — the general path costs its instructions only for the groups that need it.
+template <int N, int WARPS, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const double *__restrict__ in, int64_t n_groups,
+                                                                      double rel_eps, double abs_eps,
+                                                                      double *__restrict__ out_value,
+                                                                      uint32_t *__restrict__ out_meta, bool mc) {
+    constexpr int ROW_BYTES = N * 8;
+    constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
+    constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
+    constexpr int T = WARPS * 32;
+    static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
+    __shared__ int64_t defer_q[WARPS][64];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t *my_smem = smem + (size_t)warp * STAGES * TILE_BYTES;
+    uint64_t *my_bar = full_bar + warp * STAGES;
+    int64_t *my_q = defer_q[warp];
+    int q_count = 0;  // warp-uniform
+    const PlaneRow row{smem_u32(smem + (size_t)WARPS * STAGES * TILE_BYTES) + threadIdx.x * 8u, T * 8u};
+    const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
+
+    const int64_t n_tiles = (n_groups + 31) >> 5;
+    const int64_t first = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t step = (int64_t)gridDim.x * WARPS;
+    uint64_t policy = 0;
+
+    if (lane == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&my_bar[s], 1);
+        fence_barrier_init();
+        policy = policy_evict_first();
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const int64_t t = first + (int64_t)s * step;
+            if (t < n_tiles) {
+                mbar_arrive_expect_tx(&my_bar[s], TILE_BYTES);
+                tma_load_2d(my_smem + (size_t)s * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP), &my_bar[s],
+                            policy);
+            }
+        }
+    }
+    __syncwarp();
+
+    // the first `count` queued groups through the general path, one per lane
+    auto drain = [&](int count) {
+        if (lane < count) {
+            const int64_t g = my_q[lane];
+            const double *src = in + g * N;
+            uint32_t hi[N];
+#pragma unroll
+            for (int q = 0; q < N / 2; ++q) {
+                const int4 v4 = ldg_nc_v4(src + 2 * q);
+                hi[2 * q + 0] = (uint32_t)v4.y;
+                hi[2 * q + 1] = (uint32_t)v4.w;
+                sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
+                sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
+            }
+            double v;
+            uint32_t m;
+            numeric_core<N, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
+        }
+        __syncwarp();
+    };
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t t = first; t < n_tiles; t += step) {
+        mbar_wait(&my_bar[stage], parity);
+        const uint32_t base = smem_u32(my_smem + (size_t)stage * TILE_BYTES);
+        const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
+        uint32_t hi[N], lo[N];
+        uint32_t touch = 0;
+#pragma unroll
+        for (int q = 0; q < N / 2; ++q) {
+            const int4 v4 = lds_v4(base + Swizzle<ROW_BYTES>::apply(row_off + q * 16));
+            lo[2 * q + 0] = (uint32_t)v4.x;
+            hi[2 * q + 0] = (uint32_t)v4.y;
+            lo[2 * q + 1] = (uint32_t)v4.z;
+            hi[2 * q + 1] = (uint32_t)v4.w;
+            touch |= (uint32_t)v4.w;  // one word of every LDS.128 is enough to depend on all of them
+        }
+        // the tile is in registers: hand the stage back (see numeric_tma_kernel for the ordering argument)
+        const uint32_t order = __shfl_sync(0xFFFFFFFFu, touch, 0) ^ touch;
+        if (lane == 0) {
+            const int64_t tn = t + (int64_t)STAGES * step;
+            if (tn < n_tiles) {
+                mbar_arrive_expect_tx(&my_bar[stage], TILE_BYTES);
+                tma_load_2d(my_smem + (size_t)stage * TILE_BYTES, &tmap, 0,
+                            (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP) + (int32_t)order, &my_bar[stage], policy);
+            }
+        }
+        const int64_t g = t * 32 + lane;
+        bool defer = false;
+        if (g < n_groups) {
+            double v;
+            uint32_t m;
+            if (numeric_fast<N>(hi, lo, rel_eps, thr, v, m)) {
+                store_out_f64(out_value + g, v, mc);
+                store_out_u32(out_meta + g, m, mc);
+            } else {
+                defer = true;
+            }
+        }
+        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (dm) {
+            if (defer) my_q[q_count + __popc(dm & ((1u << lane) - 1u))] = g;
+            q_count += __popc(dm);
+            __syncwarp();
+            if (q_count >= 32) {
+                drain(32);
+                const int64_t moved = (lane < q_count - 32) ? my_q[32 + lane] : 0;
+                __syncwarp();
+                if (lane < q_count - 32) my_q[lane] = moved;
+                q_count -= 32;
+                __syncwarp();
+            }
+        }
+        if (++stage == STAGES) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+    if (q_count > 0) drain(q_count);
+}
+
 template <int N, int WARPS, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,

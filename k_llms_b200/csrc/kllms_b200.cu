@@ -224,6 +224,31 @@ int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs
     return KC_OK;
 }
 
+// fast path in front (kc::numeric_fast), general path for the groups it leaves open; KC_NUM_FAST=0 disables it
+template <int N, int WARPS, int STAGES, int MIN_CTAS>
+int launch_numeric_tma_fast(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
+                            cudaStream_t st, bool mc) {
+    auto kernel = kc::numeric_tma_fast_kernel<N, WARPS, STAGES, MIN_CTAS>;
+    const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
+    for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
+        const int64_t gs = std::min(kMaxGroupsPerLaunch, G - g0);
+        CUtensorMap map;
+        int rc = make_row_tensor_map(map, vals + g0 * N, gs, N * 8, 32);
+        if (rc) return rc;
+        int grid = 0;
+        rc = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid);
+        if (rc) return rc;
+        kernel<<<grid, WARPS * 32, smem, st>>>(map, vals + g0 * N, gs, rel_eps, abs_eps, value + g0, meta + g0, mc);
+        KC_CUDA(cudaGetLastError());
+    }
+    return KC_OK;
+}
+
+static bool numeric_fast_enabled() {
+    static const bool on = [] { const char *e = getenv("KC_NUM_FAST"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int NP, int T>
 int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, double abs_eps, double *value,
                           uint32_t *meta, cudaStream_t st, bool mc) {
@@ -439,6 +464,12 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
             case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 16: {
                 static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
+                if (numeric_fast_enabled()) {
+                    if (cfg == 11) return launch_numeric_tma_fast<16, 4, 1, 5>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                    if (cfg == 12) return launch_numeric_tma_fast<16, 4, 2, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                    if (cfg == 13) return launch_numeric_tma_fast<16, 8, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                    return launch_numeric_tma_fast<16, 4, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                }
                 if (cfg == 1) return launch_numeric_tma<16, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                 if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                 if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
