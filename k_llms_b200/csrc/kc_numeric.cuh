@@ -514,18 +514,13 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
 //   4. anything else — no majority, a neighbour within reach, a cell sharing v's high word, a single non-None cell —
 //      is NOT decided here: the caller queues the group for numeric_core (exact, general).
 // Returns true when (value, meta) are final.
-// census += 0x100 for a non-finite cell, += 0x10000 for None, += 0x10001 for absent — as PREDICATED adds (the compiler
-// prefers select + add, two ALU-pipe instructions more per cell)
-__device__ __forceinline__ void census_cell(uint32_t h, uint32_t &census) {
-    asm("{\n\t.reg .pred p, q;\n\t.reg .u32 u, w;\n\t"
-        "setp.ge.u32 p, %1, 0x7FF00000;\n\t"
-        "@p add.u32 %0, %0, 256;\n\t"
-        "sub.u32 u, %1, %2;\n\t"
-        "setp.lt.u32 q, u, 2;\n\t"
-        "add.u32 w, u, 65536;\n\t"
-        "@q add.u32 %0, %0, w;\n\t}"
-        : "+r"(census)
-        : "r"(h), "n"(kNoneHi));
+// n += (x == key), as a predicated add (the compiler prefers select + add)
+__device__ __forceinline__ void count_equal(uint32_t x, uint32_t key, uint32_t &n) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, %1, %2;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t}"
+        : "+r"(n)
+        : "r"(x), "r"(key));
 }
 
 // a cell with v's high word: count it, and collect any difference of its low word
@@ -541,29 +536,47 @@ __device__ __forceinline__ void match_cell(uint32_t h, uint32_t l, uint32_t hv, 
 template <int N>
 __device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint32_t (&lo)[N], double rel_eps, double thr,
                                              double &value, uint32_t &meta) {
-    // Only groups without a negative cell are decided here (raw high words of non-negative doubles are already
-    // ordered like the values; -0.0 counts as negative).  Non-finite <=> hi >= 0x7FF00000.
-    uint32_t any = 0, census = 0;  // census = tagged << 16 | nonfinite << 8 | absent
+    // Only groups whose largest high word (unsigned) is at most the absent tag are decided here: no negative cell (-0.0
+    // included), no NaN payload above the tags; raw high words of non-negative doubles are ordered like the values.
+    // x = hi + 2^20 then has bit 31 set <=> the cell is not finite (exponent all ones).
+    constexpr uint32_t X_NONE = kNoneHi + 0x00100000u, X_ABSENT = kAbsentHi + 0x00100000u;
+    constexpr int PLANES = 32 - __builtin_clz((unsigned)N);  // weights 1 .. N
+    uint32_t x[N];
+    uint32_t top = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        any |= hi[i];
-        census_cell(hi[i], census);
+        x[i] = hi[i] + 0x00100000u;
+        top = max(top, hi[i]);
     }
-    const uint32_t hv = at_least_half(hi), lv = at_least_half(lo);
-    // d = hi - hv as a signed number: < 0 below v, > 0 above (all high words are < 2^31 here).  Unsigned max of d is
-    // the nearest cell below (if any is below), unsigned min of d - 1 the nearest above.
-    uint32_t c = 0, bad = 0, below = 0, above = 0xFFFFFFFFu;
-    const uint32_t neg_hv = 0u - hv, neg_hv1 = ~hv;
+    // per bit position, how many cells have the bit set: the two top planes give the "at least half" guess of v's
+    // high word, bit 31 of all planes the number of non-finite cells
+    uint32_t plane[PLANES];
+    bit_counts(x, plane);
+    const uint32_t xv = plane[PLANES - 1] | plane[PLANES - 2], lv = at_least_half(lo);
+    uint32_t nonfinite = 0;
+#pragma unroll
+    for (int k = 0; k < PLANES; ++k) nonfinite += (plane[k] >> 31) << k;
+    // d = x - xv as a signed number: < 0 below v, > 0 above.  Unsigned max of d is the nearest cell below (if any is
+    // below), unsigned min of d - 1 the nearest above.
+    uint32_t c = 0, bad = 0, below = 0, above = 0xFFFFFFFFu, none = 0, absent = 0;
+    const uint32_t neg_xv = 0u - xv, neg_xv1 = ~xv;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        below = max(below, hi[i] + neg_hv);
-        above = min(above, hi[i] + neg_hv1);
-        match_cell(hi[i], lo[i], hv, lv, c, bad);
+        below = max(below, x[i] + neg_xv);
+        above = min(above, x[i] + neg_xv1);
+        match_cell(x[i], lo[i], xv, lv, c, bad);
+        count_equal(x[i], X_NONE, none);
     }
-    const uint32_t nonfinite = (census >> 8) & 0xFFu, tagged = census >> 16, absent = census & 0xFFu;
-    // a negative cell / the guess is not a finite value / no strict majority of the finite cells / one non-None cell
-    if ((any & 0x80000000u) != 0 || hv >= 0x7FF00000u || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2))
+    if (top == kAbsentHi) {  // ragged candidates (rare): count the absent cells too
+#pragma unroll
+        for (int i = 0; i < N; ++i) count_equal(x[i], X_ABSENT, absent);
+    }
+    const uint32_t tagged = none + absent;
+    // a negative cell or an odd NaN / the guess is not a finite value / cells share v's high word only / no strict
+    // majority of the finite cells / a single non-None cell
+    if (top > kAbsentHi || (xv & 0x80000000u) != 0 || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2))
         return false;
+    const uint32_t hv = xv - 0x00100000u;
     const double v = __hiloint2double((int)hv, (int)lv);
     // Neighbours: every double with the high word hb is <= (hb, ~0) < v, every one with ha is in [(ha, 0), (ha, ~0)].
     // close(a, b) <=> |a-b| <= max(abs, rel*max(|a|,|b|,1)) = max(thr, fl(rel*max(|a|,|b|))) with thr = max(abs, rel),

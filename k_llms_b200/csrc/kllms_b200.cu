@@ -482,7 +482,14 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
                 if (cfg == 10) return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                 return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             }
-            case 32: return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+            case 32:
+                if (numeric_fast_enabled()) {
+                    static const int cfg32 = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
+                    if (cfg32 == 21) return launch_numeric_tma_fast<32, 4, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                    if (cfg32 == 22) return launch_numeric_tma_fast<32, 2, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                    return launch_numeric_tma_fast<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+                }
+                return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             default: break;
         }

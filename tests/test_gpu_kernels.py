@@ -109,6 +109,49 @@ def test_numeric_other_eps():
         assert ok.all()
 
 
+@pytest.mark.parametrize("n", [16, 32])
+def test_numeric_fast_path_edges(n):
+    """K2's majority shortcut (kc::numeric_fast) against the oracle where it has to give up or sit on a boundary:
+    neighbours right at the tolerance, cells sharing v's high word, signed zeros, -inf / negative NaN / odd NaN payloads,
+    absent cells, overflow of the sum, every majority size, several (rel, abs) tolerances."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(900 + n)
+    G = 20000
+    pool = np.array([0.0, -0.0, 1.0, 5e-324, 1e-310, 2.0 ** -1022, 1.7e308, 9e307, 123456.0, 0.1, 1e15 + 0.5, 3.0, 2.0 ** 52,
+                     1048576.0, 1048577.0, 0.999999, 33.333333333333336], dtype=np.float64)
+    v = pool[rng.integers(0, len(pool), G)]
+    odd = np.array([NONE, ABSENT, np.nan, -np.nan, np.inf, -np.inf], dtype=np.float64)
+    odd = np.concatenate([odd, np.array([0x7FFFFFFFFFFFFFFF, 0xFFF8000000000001, 0x7FF8C0DE00000001, 0x7FF8C0E000000000],
+                                        dtype=np.uint64).view(np.float64)])
+    factor = np.array([0.97, 0.9700000001, 0.9699999999, 1.03, 1.0300000001, 1.0299999999, 1 + 1e-9, 1 - 2.0 ** -20, 1 + 2.0 ** -21,
+                       1 + 2.0 ** -33, 0.5, 2.0, -1.0, 1.0309278350515465, 0.9708737864077669], dtype=np.float64)
+    vals = np.repeat(v[:, None], n, axis=1)
+    c = rng.integers(1, n + 1, G)                                  # copies of v kept
+    for g in range(G):
+        k = n - c[g]
+        if k == 0:
+            continue
+        pos = rng.choice(n, k, replace=False)
+        kind = rng.integers(0, 5, k)
+        repl = np.where(kind == 0, odd[rng.integers(0, len(odd), k)],
+                np.where(kind == 1, v[g] * factor[rng.integers(0, len(factor), k)],
+                np.where(kind == 2, np.nextafter(v[g], np.inf * rng.choice([-1.0, 1.0], k)),
+                np.where(kind == 3, NONE, rng.uniform(-10, 2e6, k)))))
+        vals[g, pos] = repl
+    vals = np.ascontiguousarray(vals)
+    d_vals = torch.from_numpy(vals).cuda()
+    for rel, ab in ((0.03, 1e-6), (0.0, 0.0), (0.9, 10.0), (1e-12, 1e-300)):
+        with np.errstate(all="ignore"):
+            exp_val, exp_meta = OC.numeric(vals, rel, ab)
+        val, meta = K.numeric(d_vals, rel, ab)
+        got_meta, g_ = meta.cpu().numpy().view(np.uint32), val.cpu().numpy()
+        bad = np.nonzero(got_meta != exp_meta)[0]
+        assert bad.size == 0, (rel, ab, bad[:3], vals[bad[:1]], OC.meta_fields(got_meta[bad[:1]]), OC.meta_fields(exp_meta[bad[:1]]))
+        ok = (g_.view(np.uint64) == exp_val.view(np.uint64)) | (np.isnan(g_) & np.isnan(exp_val))
+        assert ok.all(), (rel, ab, vals[~ok][:1], g_[~ok][:3], exp_val[~ok][:3])
+
+
 def test_confidence_matches_python_round():
     torch = _torch()
     from k_llms_b200 import _native as K
