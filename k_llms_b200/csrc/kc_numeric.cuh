@@ -607,6 +607,94 @@ __device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint
     return true;
 }
 
+// Register-prefetch front-end (n == NP, small rows) with the fast path: same deferral queue as the TMA variant below.
+template <int NP, int T>
+__global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__restrict__ vals, int64_t n_groups, double rel_eps,
+                                                                double abs_eps, double *__restrict__ out_value,
+                                                                uint32_t *__restrict__ out_meta, bool mc) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ int64_t defer_q[T / 32][64];
+    const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
+    const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
+    const int lane = threadIdx.x & 31;
+    int64_t *my_q = defer_q[threadIdx.x >> 5];
+    int q_count = 0;  // warp-uniform
+    const int64_t stride = (int64_t)gridDim.x * T;
+    const int64_t g0 = (int64_t)blockIdx.x * T + threadIdx.x;
+
+    auto general = [&](int64_t g) {
+        const int4 *p4 = reinterpret_cast<const int4 *>(vals + g * NP);
+        uint32_t hi[NP];
+#pragma unroll
+        for (int q = 0; q < NP / 2; ++q) {
+            const int4 t = ldg_nc_v4(p4 + q);
+            hi[2 * q + 0] = (uint32_t)t.y;
+            hi[2 * q + 1] = (uint32_t)t.w;
+            sts_f64(row.addr(2 * q + 0), __hiloint2double(t.y, t.x));
+            sts_f64(row.addr(2 * q + 1), __hiloint2double(t.w, t.z));
+        }
+        double v;
+        uint32_t m;
+        numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+        store_out_f64(out_value + g, v, mc);
+        store_out_u32(out_meta + g, m, mc);
+    };
+
+    int4 cur[NP / 2];
+    if (g0 < n_groups) {
+        const int4 *p4 = reinterpret_cast<const int4 *>(vals + g0 * NP);
+#pragma unroll
+        for (int q = 0; q < NP / 2; ++q) cur[q] = ldg_nc_v4(p4 + q);
+    }
+    // whole warps iterate together (the tail lanes idle) so that the queue bookkeeping stays warp-uniform
+    for (int64_t gw = g0 - lane; gw < n_groups; gw += stride) {
+        const int64_t g = gw + lane;
+        int4 nxt[NP / 2];
+        if (g + stride < n_groups) {  // request the next row before working on this one
+            const int4 *p4 = reinterpret_cast<const int4 *>(vals + (g + stride) * NP);
+#pragma unroll
+            for (int q = 0; q < NP / 2; ++q) nxt[q] = ldg_nc_v4(p4 + q);
+        }
+        bool defer = false;
+        if (g < n_groups) {
+            uint32_t hi[NP], lo[NP];
+#pragma unroll
+            for (int q = 0; q < NP / 2; ++q) {
+                lo[2 * q + 0] = (uint32_t)cur[q].x;
+                hi[2 * q + 0] = (uint32_t)cur[q].y;
+                lo[2 * q + 1] = (uint32_t)cur[q].z;
+                hi[2 * q + 1] = (uint32_t)cur[q].w;
+            }
+            double v;
+            uint32_t m;
+            if (numeric_fast<NP>(hi, lo, rel_eps, thr, v, m)) {
+                store_out_f64(out_value + g, v, mc);
+                store_out_u32(out_meta + g, m, mc);
+            } else {
+                defer = true;
+            }
+        }
+        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (dm) {
+            if (defer) my_q[q_count + __popc(dm & ((1u << lane) - 1u))] = g;
+            q_count += __popc(dm);
+            __syncwarp();
+            if (q_count >= 32) {
+                general(my_q[lane]);
+                __syncwarp();
+                const int64_t moved = (lane < q_count - 32) ? my_q[32 + lane] : 0;
+                __syncwarp();
+                if (lane < q_count - 32) my_q[lane] = moved;
+                q_count -= 32;
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP / 2; ++q) cur[q] = nxt[q];
+    }
+    if (lane < q_count) general(my_q[lane]);
+}
+
 // The TMA pipeline of numeric_tma_kernel with the fast path in front: cells stay in registers; groups the fast path
 // does not decide are queued per warp and, 32 at a time, re-read from global memory (L2-resident) and given to
 // numeric_core with every lane busy — the general path costs its instructions only for the groups that need it.

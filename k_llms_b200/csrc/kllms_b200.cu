@@ -493,6 +493,25 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
             case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             default: break;
         }
+    if (numeric_fast_enabled() && !force_direct() && (n == 8 || n == 4)) {
+        auto launch_fast = [&](auto kernel, int NP) -> int {
+            DeviceInfo info;
+            int rc = device_info(info);
+            if (rc) return rc;
+            const int T = 128;
+            const size_t smem = (size_t)T * NP * 8;
+            int per_sm = 0;
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+            if (per_sm < 1) return fail(KC_ECUDA, "numeric_direct_fast_kernel<%d> does not fit", NP);
+            const int64_t want = (n_groups + T - 1) / T;
+            const int grid = (int)std::min<int64_t>(want, (int64_t)info.sm_count * per_sm);
+            kernel<<<grid, T, smem, st>>>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, mc);
+            KC_CUDA(cudaGetLastError());
+            return KC_OK;
+        };
+        if (n == 8) return launch_fast(kc::numeric_direct_fast_kernel<8, 128>, 8);
+        return launch_fast(kc::numeric_direct_fast_kernel<4, 128>, 4);
+    }
     if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
     if (n <= 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
     if (n <= 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
