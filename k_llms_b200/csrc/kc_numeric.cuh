@@ -533,21 +533,23 @@ __device__ __forceinline__ void match_cell(uint32_t h, uint32_t l, uint32_t hv, 
         : "r"(h), "r"(l), "r"(hv), "r"(lv));
 }
 
+// Callers pass x = hi + 2^20 (kFastBias) for every cell and top = the largest raw high word (unsigned).
+constexpr uint32_t kFastBias = 0x00100000u;
+
+struct FastDecision {
+    double v;                    // the majority value
+    uint32_t c, tagged, absent;  // its copies; None + absent cells; absent cells
+};
+
+// Phase 1: decide.  True <=> the group's result is np.mean([v] * c); the cells are not needed afterwards.
 template <int N>
-__device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint32_t (&lo)[N], double rel_eps, double thr,
-                                             double &value, uint32_t &meta) {
+__device__ __forceinline__ bool numeric_fast_decide(const uint32_t (&x)[N], const uint32_t (&lo)[N], uint32_t top, double rel_eps,
+                                                    double thr, FastDecision &out) {
     // Only groups whose largest high word (unsigned) is at most the absent tag are decided here: no negative cell (-0.0
     // included), no NaN payload above the tags; raw high words of non-negative doubles are ordered like the values.
     // x = hi + 2^20 then has bit 31 set <=> the cell is not finite (exponent all ones).
-    constexpr uint32_t X_NONE = kNoneHi + 0x00100000u, X_ABSENT = kAbsentHi + 0x00100000u;
+    constexpr uint32_t X_NONE = kNoneHi + kFastBias, X_ABSENT = kAbsentHi + kFastBias;
     constexpr int PLANES = 32 - __builtin_clz((unsigned)N);  // weights 1 .. N
-    uint32_t x[N];
-    uint32_t top = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        x[i] = hi[i] + 0x00100000u;
-        top = max(top, hi[i]);
-    }
     // per bit position, how many cells have the bit set: the two top planes give the "at least half" guess of v's
     // high word, bit 31 of all planes the number of non-finite cells
     uint32_t plane[PLANES];
@@ -576,7 +578,7 @@ __device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint
     // majority of the finite cells / a single non-None cell
     if (top > kAbsentHi || (xv & 0x80000000u) != 0 || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2))
         return false;
-    const uint32_t hv = xv - 0x00100000u;
+    const uint32_t hv = xv - kFastBias;
     const double v = __hiloint2double((int)hv, (int)lv);
     // Neighbours: every double with the high word hb is <= (hb, ~0) < v, every one with ha is in [(ha, 0), (ha, ~0)].
     // close(a, b) <=> |a-b| <= max(abs, rel*max(|a|,|b|,1)) = max(thr, fl(rel*max(|a|,|b|))) with thr = max(abs, rel),
@@ -588,6 +590,18 @@ __device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint
     const bool far_a = da > thr && da > __dmul_rn(rel_eps, __hiloint2double((int)ha, -1));
     const bool has_b = below >= 0x80000000u, has_a = above < 0x7FFFFFFFu && ha < 0x7FF00000u;
     if ((has_b && !far_b) || (has_a && !far_a)) return false;
+    out.v = v;
+    out.c = c;
+    out.tagged = tagged;
+    out.absent = absent;
+    return true;
+}
+
+// Phase 2: the value and the result word of a decided group.
+template <int N>
+__device__ __forceinline__ void numeric_fast_finish(const FastDecision &d, double &value, uint32_t &meta) {
+    const double v = d.v;
+    const uint32_t c = d.c, tagged = d.tagged, absent = d.absent;
     // np.mean of c copies of v in numpy's summation order: for c >= 8 the eight accumulators are identical (r = the
     // sequential sum of c/8 copies) and their pairwise sum is 8r exactly; then the c%8 stragglers one by one.
     double res = -0.0;  // -0.0 + v == v
@@ -604,7 +618,6 @@ __device__ __forceinline__ bool numeric_fast(const uint32_t (&hi)[N], const uint
         if ((int)tail >= k) res = __dadd_rn(res, v);
     value = __ddiv_rn(__dadd_rn(0.0, res), (double)c);
     meta = (c << 6) + (((uint32_t)N - tagged) << 13) + (((uint32_t)N - absent) << 20) + ((uint32_t)KC_FLAG_HAS_VALUE << 27);
-    return true;
 }
 
 // Register-prefetch front-end (n == NP, small rows) with the fast path: same deferral queue as the TMA variant below.
@@ -622,22 +635,21 @@ __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__
     const int64_t stride = (int64_t)gridDim.x * T;
     const int64_t g0 = (int64_t)blockIdx.x * T + threadIdx.x;
 
-    auto general = [&](int64_t g) {
-        const int4 *p4 = reinterpret_cast<const int4 *>(vals + g * NP);
-        uint32_t hi[NP];
+    // deferred groups wait in the warp's 32 plane rows (slot s = the row of lane s), their indices in my_q
+    const uint32_t warp_plane = smem_u32(smem_raw) + (threadIdx.x & ~31u) * 8u;
+    auto drain = [&](int count) {
+        if (lane < count) {
+            const int64_t g = my_q[lane];
+            uint32_t hi[NP];
 #pragma unroll
-        for (int q = 0; q < NP / 2; ++q) {
-            const int4 t = ldg_nc_v4(p4 + q);
-            hi[2 * q + 0] = (uint32_t)t.y;
-            hi[2 * q + 1] = (uint32_t)t.w;
-            sts_f64(row.addr(2 * q + 0), __hiloint2double(t.y, t.x));
-            sts_f64(row.addr(2 * q + 1), __hiloint2double(t.w, t.z));
+            for (int i = 0; i < NP; ++i) hi[i] = lds_u32x2(row.addr(i)).y;
+            double v;
+            uint32_t m;
+            numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
         }
-        double v;
-        uint32_t m;
-        numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-        store_out_f64(out_value + g, v, mc);
-        store_out_u32(out_meta + g, m, mc);
+        __syncwarp();
     };
 
     int4 cur[NP / 2];
@@ -655,49 +667,64 @@ __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__
 #pragma unroll
             for (int q = 0; q < NP / 2; ++q) nxt[q] = ldg_nc_v4(p4 + q);
         }
-        bool defer = false;
-        if (g < n_groups) {
-            uint32_t hi[NP], lo[NP];
+        uint32_t x[NP], lo[NP], top = 0;  // x = high word + kFastBias
 #pragma unroll
-            for (int q = 0; q < NP / 2; ++q) {
-                lo[2 * q + 0] = (uint32_t)cur[q].x;
-                hi[2 * q + 0] = (uint32_t)cur[q].y;
-                lo[2 * q + 1] = (uint32_t)cur[q].z;
-                hi[2 * q + 1] = (uint32_t)cur[q].w;
-            }
-            double v;
-            uint32_t m;
-            if (numeric_fast<NP>(hi, lo, rel_eps, thr, v, m)) {
-                store_out_f64(out_value + g, v, mc);
-                store_out_u32(out_meta + g, m, mc);
-            } else {
-                defer = true;
+        for (int q = 0; q < NP / 2; ++q) {
+            lo[2 * q + 0] = (uint32_t)cur[q].x;
+            x[2 * q + 0] = (uint32_t)cur[q].y + kFastBias;
+            lo[2 * q + 1] = (uint32_t)cur[q].z;
+            x[2 * q + 1] = (uint32_t)cur[q].w + kFastBias;
+            top = max(top, max((uint32_t)cur[q].y, (uint32_t)cur[q].w));
+        }
+        FastDecision fd;
+        const bool decided = numeric_fast_decide<NP>(x, lo, top, rel_eps, thr, fd);
+        const bool defer = !decided && g < n_groups;
+        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) {  // park the cells in a free plane row; past the 32nd only the index is kept (re-read below)
+            const uint32_t slot = (uint32_t)q_count + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+            my_q[slot] = g;
+            if (slot < 32u) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i)
+                    sts_f64(warp_plane + slot * 8u + (uint32_t)i * (T * 8u), __hiloint2double((int)(x[i] - kFastBias), (int)lo[i]));
             }
         }
-        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
-        if (dm) {
-            if (defer) my_q[q_count + __popc(dm & ((1u << lane) - 1u))] = g;
-            q_count += __popc(dm);
+        q_count += __popc(dm);
+        if (decided && g < n_groups) {
+            double v;
+            uint32_t m;
+            numeric_fast_finish<NP>(fd, v, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
+        }
+        __syncwarp();
+        if (q_count >= 32) {
+            drain(32);
+            q_count -= 32;
+            const int64_t moved = (lane < q_count) ? my_q[32 + lane] : 0;
             __syncwarp();
-            if (q_count >= 32) {
-                general(my_q[lane]);
-                __syncwarp();
-                const int64_t moved = (lane < q_count - 32) ? my_q[32 + lane] : 0;
-                __syncwarp();
-                if (lane < q_count - 32) my_q[lane] = moved;
-                q_count -= 32;
-                __syncwarp();
+            if (lane < q_count) {
+                my_q[lane] = moved;
+                const int4 *p4 = reinterpret_cast<const int4 *>(vals + moved * NP);
+#pragma unroll
+                for (int q = 0; q < NP / 2; ++q) {
+                    const int4 v4 = ldg_nc_v4(p4 + q);
+                    sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
+                    sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
+                }
             }
+            __syncwarp();
         }
 #pragma unroll
         for (int q = 0; q < NP / 2; ++q) cur[q] = nxt[q];
     }
-    if (lane < q_count) general(my_q[lane]);
+    if (q_count > 0) drain(q_count);
 }
 
-// The TMA pipeline of numeric_tma_kernel with the fast path in front: cells stay in registers; groups the fast path
-// does not decide are queued per warp and, 32 at a time, re-read from global memory (L2-resident) and given to
-// numeric_core with every lane busy — the general path costs its instructions only for the groups that need it.
+// The TMA pipeline of numeric_tma_kernel with the fast path in front: cells stay in registers; a group the fast path
+// does not decide parks its cells in one of the warp's 32 plane rows, and when those are (nearly) full the warp runs
+// numeric_core on them with every lane busy — the general path costs its instructions only for the groups that need it,
+// and nothing is read twice.
 template <int N, int WARPS, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                       const double *__restrict__ in, int64_t n_groups,
@@ -746,20 +773,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
     }
     __syncwarp();
 
-    // the first `count` queued groups through the general path, one per lane
+    // Deferred groups wait in the warp's 32 plane rows (slot s = the row of lane s) with their group index in my_q;
+    // drain: the first `count` of them through the general path, one per lane.
+    const uint32_t warp_plane = smem_u32(smem + (size_t)WARPS * STAGES * TILE_BYTES) + (uint32_t)warp * 32u * 8u;
     auto drain = [&](int count) {
         if (lane < count) {
             const int64_t g = my_q[lane];
-            const double *src = in + g * N;
             uint32_t hi[N];
 #pragma unroll
-            for (int q = 0; q < N / 2; ++q) {
-                const int4 v4 = ldg_nc_v4(src + 2 * q);
-                hi[2 * q + 0] = (uint32_t)v4.y;
-                hi[2 * q + 1] = (uint32_t)v4.w;
-                sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
-                sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
-            }
+            for (int i = 0; i < N; ++i) hi[i] = lds_u32x2(row.addr(i)).y;
             double v;
             uint32_t m;
             numeric_core<N, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
@@ -775,15 +797,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
         mbar_wait(&my_bar[stage], parity);
         const uint32_t base = smem_u32(my_smem + (size_t)stage * TILE_BYTES);
         const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
-        uint32_t hi[N], lo[N];
-        uint32_t touch = 0;
+        uint32_t x[N], lo[N];  // x = high word + kFastBias
+        uint32_t touch = 0, top = 0;
 #pragma unroll
         for (int q = 0; q < N / 2; ++q) {
             const int4 v4 = lds_v4(base + Swizzle<ROW_BYTES>::apply(row_off + q * 16));
             lo[2 * q + 0] = (uint32_t)v4.x;
-            hi[2 * q + 0] = (uint32_t)v4.y;
+            x[2 * q + 0] = (uint32_t)v4.y + kFastBias;
             lo[2 * q + 1] = (uint32_t)v4.z;
-            hi[2 * q + 1] = (uint32_t)v4.w;
+            x[2 * q + 1] = (uint32_t)v4.w + kFastBias;
+            top = max(top, max((uint32_t)v4.y, (uint32_t)v4.w));
             touch |= (uint32_t)v4.w;  // one word of every LDS.128 is enough to depend on all of them
         }
         // the tile is in registers: hand the stage back (see numeric_tma_kernel for the ordering argument)
@@ -797,30 +820,44 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
             }
         }
         const int64_t g = t * 32 + lane;
-        bool defer = false;
-        if (g < n_groups) {
-            double v;
-            uint32_t m;
-            if (numeric_fast<N>(hi, lo, rel_eps, thr, v, m)) {
-                store_out_f64(out_value + g, v, mc);
-                store_out_u32(out_meta + g, m, mc);
-            } else {
-                defer = true;
+        FastDecision fd;
+        const bool decided = numeric_fast_decide<N>(x, lo, top, rel_eps, thr, fd);
+        const bool defer = !decided && g < n_groups;
+        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) {  // park the cells in a free plane row; past the 32nd only the index is kept (re-read below)
+            const uint32_t slot = (uint32_t)q_count + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+            my_q[slot] = g;
+            if (slot < 32u) {
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    sts_f64(warp_plane + slot * 8u + (uint32_t)i * (T * 8u), __hiloint2double((int)(x[i] - kFastBias), (int)lo[i]));
             }
         }
-        const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
-        if (dm) {
-            if (defer) my_q[q_count + __popc(dm & ((1u << lane) - 1u))] = g;
-            q_count += __popc(dm);
+        q_count += __popc(dm);
+        if (decided && g < n_groups) {
+            double v;
+            uint32_t m;
+            numeric_fast_finish<N>(fd, v, m);
+            store_out_f64(out_value + g, v, mc);
+            store_out_u32(out_meta + g, m, mc);
+        }
+        __syncwarp();
+        if (q_count >= 32) {  // nothing of this tile is live in registers any more
+            drain(32);
+            q_count -= 32;
+            const int64_t moved = (lane < q_count) ? my_q[32 + lane] : 0;
             __syncwarp();
-            if (q_count >= 32) {
-                drain(32);
-                const int64_t moved = (lane < q_count - 32) ? my_q[32 + lane] : 0;
-                __syncwarp();
-                if (lane < q_count - 32) my_q[lane] = moved;
-                q_count -= 32;
-                __syncwarp();
+            if (lane < q_count) {  // the overflow (a few groups at most): fetch their cells again
+                my_q[lane] = moved;
+                const int4 *p4 = reinterpret_cast<const int4 *>(in + moved * N);
+#pragma unroll
+                for (int q = 0; q < N / 2; ++q) {
+                    const int4 v4 = ldg_nc_v4(p4 + q);
+                    sts_f64(row.addr(2 * q + 0), __hiloint2double(v4.y, v4.x));
+                    sts_f64(row.addr(2 * q + 1), __hiloint2double(v4.w, v4.z));
+                }
             }
+            __syncwarp();
         }
         if (++stage == STAGES) {
             stage = 0;
