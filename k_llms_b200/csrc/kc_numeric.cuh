@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&my_bar[s], 1);
         fence_barrier_init();
-        policy = policy_evict_first();
+        policy = policy_evict_normal();
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int64_t t = first + (int64_t)s * step;
@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&my_bar[s], 1);
         fence_barrier_init();
-        policy = policy_evict_first();
+        policy = policy_evict_normal();
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int64_t t = first + (int64_t)s * step;
