@@ -220,7 +220,7 @@ def run_gpu_arm(args):
     fused = None
     if world > 1 and args.reassembly in ("auto", "fused"):
         try:
-            fused = FusedShardedConsensus(layout, dev)
+            fused = FusedShardedConsensus(layout, dev, route=args.route)
             if not fused.available():
                 fused = None
         except Exception as exc:  # symmetric memory unavailable on this stack
@@ -252,14 +252,14 @@ def run_gpu_arm(args):
             e[2].record()
             kernel_events.append(e)
 
-    def fused_launch(win_p, vmeta_p, value_p, nmeta_p):
+    def fused_launch(f):
         if timing[0]:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
-        K.check(lib.kc_vote_i32_ex(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win_p, vmeta_p, K.OUT_MULTIMEM, sp))
+        f.vote(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, sp)
         if timing[0]:
             e[1].record()
-        K.check(lib.kc_numeric_f64_ex(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value_p, nmeta_p, K.OUT_MULTIMEM, sp))
+        f.numeric(v2.data_ptr(), N * 8, n, 0.03, 1e-6, sp)
         if timing[0]:
             e[2].record()
             kernel_events.append(e)
@@ -374,12 +374,13 @@ def run_gpu_arm(args):
                                    (" with results multimem.st-replicated to every GPU through NVSwitch + one cross-GPU barrier"
                                     if fused is not None else " + pipelined NCCL all-gather of packed outputs")),
                            "parallelism": (f"records sharded {world}-way; reassembly "
-                                           + ("fused into the kernels (NVSwitch multicast)" if fused is not None else "NCCL all-gather"))
+                                           + ((f"fused into the kernels ({'P2P stores to the peers' if fused.route == 'peers' else 'NVSwitch multicast stores'})")
+                                              if fused is not None else "NCCL all-gather"))
                                           if world > 1 else "single GPU"},
                 "e2e": e2e, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
-                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else "fused-multimem" if fused is not None else "nccl"),
+                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else f"fused-{fused.route}" if fused is not None else "nccl"),
                                  "nvlink_floor_ms": (world - 1) * layout.nbytes / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
     if dist is not None:
@@ -420,6 +421,8 @@ def main():
     ap.add_argument("--e2e-cells", default="i8", choices=["i8", "i32"], help="host encoding of vote cells for the e2e leg")
     ap.add_argument("--chunks", type=int, default=8, help="N>1, NCCL reassembly: pipeline chunks of compute vs all-gather")
     ap.add_argument("--reassembly", default="auto", choices=["auto", "fused", "nccl"])
+    ap.add_argument("--route", default="peers", choices=["peers", "multimem"],
+                    help="fused reassembly: P2P stores to every peer's copy, or one multicast store through the switch")
     ap.add_argument("--cpu-records-per-core", type=int, default=1500)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -126,6 +126,19 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
                       uint32_t *d_meta, uint32_t out_mode, void *stream);
 
 /*
+ * The same fusion over peer-to-peer stores (KC_OUT_PEERS): the output pointers are LOCAL addresses inside a buffer that
+ * n_peers (<= 7) other GPUs map as well (e.g. torch symmetric memory's buffer_ptrs); every result is stored locally and
+ * at address + peer_delta_bytes[k] for each peer k (the distance from this GPU's mapping of the buffer to peer k's, a
+ * multiple of 8).  A multicast store also comes back to its sender, so every GPU receives world x its share; with P2P
+ * stores it receives (world - 1) shares and sends as many — the better trade on full-duplex NVLink (measured: DESIGN §7).
+ */
+#define KC_OUT_PEERS 2u
+int kc_vote_i32_peers(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                      int32_t *d_win_code, uint32_t *d_meta, int32_t n_peers, const int64_t *peer_delta_bytes, void *stream);
+int kc_numeric_f64_peers(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                         uint32_t *d_meta, int32_t n_peers, const int64_t *peer_delta_bytes, void *stream);
+
+/*
  * Confidences from result words, bit-exact with Python's round(x, 5) (cu:982,1178,1187,1219):
  *   vote    (numeric == 0): round(pvf * (support / present), 5)          cu:973,982
  *   numeric (numeric == 1): round(support / nn, 5); SINGLE: pvf * (1/present) unrounded (cu:1086,1444)

@@ -126,17 +126,43 @@ __device__ __forceinline__ int4 ldg_nc_v4(const void *p) {
 // Result stores.  mc == true: `p` is an NVSwitch MULTICAST address (CUDA multicast object mapped on every GPU of
 // the group); multimem.st makes the switch replicate the store into each GPU's copy of the buffer — the all-gather
 // of the outputs happens inside the producing kernel, tile by tile, instead of in a separate collective.
-__device__ __forceinline__ void store_out_u32(void *p, uint32_t v, bool mc) {
-    if (mc)
+// Where a kernel's results go.
+//   LOCAL     plain stores (L1 no-allocate) to the given addresses;
+//   MULTIMEM  the addresses are NVSwitch multicast addresses: multimem.st, the switch replicates every store into all
+//             GPUs' copies — also back into the sender's own, so every GPU RECEIVES world x its share;
+//   PEERS     the addresses are local and lie in a buffer that n_peers other GPUs map as well (symmetric memory): one
+//             local store plus one store per peer at address + delta[k] (P2P over NVLink).  Each GPU receives only
+//             (world - 1) shares and sends as many: less ingress than multicast, the better trade on full-duplex links.
+struct OutRoute {
+    uint32_t mode;       // KC_OUT_LOCAL / KC_OUT_MULTIMEM / KC_OUT_PEERS
+    int32_t n_peers;     // PEERS only
+    long long delta[7];  // byte offsets local address -> the same address in peer k's mapping
+    __host__ __device__ bool local() const { return mode == 0; }
+};
+
+__device__ __forceinline__ void store_out_u32(void *p, uint32_t v, const OutRoute &r) {
+    if (r.mode == 1u) {
         asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-    else
-        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        return;
+    }
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (r.mode == 2u) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            if (k < r.n_peers) asm volatile("st.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "r"(v) : "memory");
+    }
 }
-__device__ __forceinline__ void store_out_f64(void *p, double v, bool mc) {
-    if (mc)
+__device__ __forceinline__ void store_out_f64(void *p, double v, const OutRoute &r) {
+    if (r.mode == 1u) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-    else
-        asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+        return;
+    }
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    if (r.mode == 2u) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            if (k < r.n_peers) asm volatile("st.global.f64 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "d"(v) : "memory");
+    }
 }
 
 __device__ __forceinline__ int4 lds_v4(uint32_t addr) {

@@ -426,7 +426,7 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 template <int NP, int T, bool PREFETCH>
 __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restrict__ vals, int64_t n_groups, int n,
                                                            double rel_eps, double abs_eps, double *__restrict__ out_value,
-                                                           uint32_t *__restrict__ out_meta, bool mc) {
+                                                           uint32_t *__restrict__ out_meta, OutRoute mc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
     const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
@@ -624,7 +624,7 @@ __device__ __forceinline__ void numeric_fast_finish(const FastDecision &d, doubl
 template <int NP, int T>
 __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__restrict__ vals, int64_t n_groups, double rel_eps,
                                                                 double abs_eps, double *__restrict__ out_value,
-                                                                uint32_t *__restrict__ out_meta, bool mc) {
+                                                                uint32_t *__restrict__ out_meta, OutRoute mc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ int64_t defer_q[T / 32][64];
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
                                                                       const double *__restrict__ in, int64_t n_groups,
                                                                       double rel_eps, double abs_eps,
                                                                       double *__restrict__ out_value,
-                                                                      uint32_t *__restrict__ out_meta, bool mc) {
+                                                                      uint32_t *__restrict__ out_meta, OutRoute mc) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
@@ -871,7 +871,7 @@ template <int N, int WARPS, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,
                                                                  double *__restrict__ out_value,
-                                                                 uint32_t *__restrict__ out_meta, bool mc) {
+                                                                 uint32_t *__restrict__ out_meta, OutRoute mc) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;

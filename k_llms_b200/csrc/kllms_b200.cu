@@ -132,7 +132,7 @@ kc::FieldMap make_field_map(const int32_t *none_code, int n_fields) {
 
 template <int N, int WARPS, int STAGES, bool HAS_NC>
 int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
-                       cudaStream_t st, bool mc) {
+                       cudaStream_t st, kc::OutRoute mc) {
     auto kernel = kc::vote_tma_kernel<N, WARPS, STAGES, HAS_NC>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 4 + 1024;
     // a slab starts on a record boundary so that (g - g0) % n_fields == g % n_fields
@@ -153,7 +153,7 @@ int launch_vote_tma_nc(const int32_t *codes, int64_t G, const int32_t *none_code
 
 template <int N, int WARPS, int STAGES>
 int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
-                    cudaStream_t st, bool mc) {
+                    cudaStream_t st, kc::OutRoute mc) {
     if (none_code && n_fields < 60000)
         return launch_vote_tma_nc<N, WARPS, STAGES, true>(codes, G, none_code, n_fields, win, meta, st, mc);
     if (none_code) return fail(KC_EINVAL, "kc_vote_i32: more than 60000 fields with none_code is not supported");
@@ -162,7 +162,7 @@ int launch_vote_tma(const int32_t *codes, int64_t G, const int32_t *none_code, i
 
 template <int NP, bool VEC>
 int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *none_code, int n_fields, int32_t *win,
-                       uint32_t *meta, cudaStream_t st, bool mc) {
+                       uint32_t *meta, cudaStream_t st, kc::OutRoute mc) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -196,9 +196,9 @@ int launch_vote_i8(const int8_t *codes, int64_t G, int n, const int32_t *none_co
     const int grid = (int)std::min<int64_t>((G + threads - 1) / threads, (int64_t)info.sm_count * 8);
     const kc::FieldMap fm = make_field_map(none_code, n_fields);
     if (none_code)
-        kc::vote_i8_kernel<NP, VEC, true><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, false);
+        kc::vote_i8_kernel<NP, VEC, true><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, kc::OutRoute{});
     else
-        kc::vote_i8_kernel<NP, VEC, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, false);
+        kc::vote_i8_kernel<NP, VEC, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, kc::OutRoute{});
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }
@@ -207,7 +207,7 @@ int launch_vote_i8(const int8_t *codes, int64_t G, int n, const int32_t *none_co
 
 template <int N, int WARPS, int STAGES, int MIN_CTAS = 1>
 int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
-                       cudaStream_t st, bool mc) {
+                       cudaStream_t st, kc::OutRoute mc) {
     auto kernel = kc::numeric_tma_kernel<N, WARPS, STAGES, MIN_CTAS>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
@@ -227,7 +227,7 @@ int launch_numeric_tma(const double *vals, int64_t G, double rel_eps, double abs
 // fast path in front (kc::numeric_fast), general path for the groups it leaves open; KC_NUM_FAST=0 disables it
 template <int N, int WARPS, int STAGES, int MIN_CTAS>
 int launch_numeric_tma_fast(const double *vals, int64_t G, double rel_eps, double abs_eps, double *value, uint32_t *meta,
-                            cudaStream_t st, bool mc) {
+                            cudaStream_t st, kc::OutRoute mc) {
     auto kernel = kc::numeric_tma_fast_kernel<N, WARPS, STAGES, MIN_CTAS>;
     const size_t smem = (size_t)WARPS * STAGES * 32 * N * 8 + (size_t)WARPS * 32 * N * 8 + 1024;
     for (int64_t g0 = 0; g0 < G; g0 += kMaxGroupsPerLaunch) {
@@ -244,14 +244,14 @@ int launch_numeric_tma_fast(const double *vals, int64_t G, double rel_eps, doubl
     return KC_OK;
 }
 
-static bool numeric_fast_enabled() {
+static bool numeric_fast_env() {
     static const bool on = [] { const char *e = getenv("KC_NUM_FAST"); return !(e && e[0] == '0'); }();
     return on;
 }
 
 template <int NP, int T>
 int launch_numeric_direct(const double *vals, int64_t G, int n, double rel_eps, double abs_eps, double *value,
-                          uint32_t *meta, cudaStream_t st, bool mc) {
+                          uint32_t *meta, cudaStream_t st, kc::OutRoute mc) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -365,10 +365,40 @@ int kc_vote_i32(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32
     return kc_vote_i32_ex(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, KC_OUT_LOCAL, stream);
 }
 
+static int make_peer_route(const char *who, int32_t n_peers, const int64_t *peer_delta_bytes, kc::OutRoute &r) {
+    if (n_peers < 0 || n_peers > 7) return fail(KC_EINVAL, "%s: n_peers=%d outside [0,7]", who, n_peers);
+    if (n_peers > 0 && !peer_delta_bytes) return fail(KC_EINVAL, "%s: NULL peer_delta_bytes", who);
+    r = kc::OutRoute{};
+    r.mode = KC_OUT_PEERS;
+    r.n_peers = n_peers;
+    for (int k = 0; k < n_peers; ++k) {
+        if (peer_delta_bytes[k] % 8 != 0) return fail(KC_EINVAL, "%s: peer_delta_bytes[%d] is not a multiple of 8", who, k);
+        r.delta[k] = (long long)peer_delta_bytes[k];
+    }
+    return KC_OK;
+}
+
+static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                           int32_t *d_win_code, uint32_t *d_meta, kc::OutRoute mc, void *stream);
+
 int kc_vote_i32_ex(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
                    int32_t *d_win_code, uint32_t *d_meta, uint32_t out_mode, void *stream) {
-    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_vote_i32_ex: unknown out_mode %u", out_mode);
-    const bool mc = out_mode == KC_OUT_MULTIMEM;
+    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_vote_i32_ex: unknown out_mode %u (peers: kc_vote_i32_peers)", out_mode);
+    kc::OutRoute mc{};
+    mc.mode = out_mode;
+    return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
+}
+
+int kc_vote_i32_peers(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                      int32_t *d_win_code, uint32_t *d_meta, int32_t n_peers, const int64_t *peer_delta_bytes, void *stream) {
+    kc::OutRoute mc;
+    int rc = make_peer_route("kc_vote_i32_peers", n_peers, peer_delta_bytes, mc);
+    if (rc) return rc;
+    return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
+}
+
+static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                           int32_t *d_win_code, uint32_t *d_meta, kc::OutRoute mc, void *stream) {
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_vote_i32: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_groups < 0) return fail(KC_EINVAL, "kc_vote_i32: negative n_groups");
     if (n_groups == 0) return KC_OK;
@@ -445,10 +475,27 @@ int kc_numeric_f64(const double *d_vals, int64_t n_groups, int32_t n, double rel
     return kc_numeric_f64_ex(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, KC_OUT_LOCAL, stream);
 }
 
+static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                              uint32_t *d_meta, kc::OutRoute mc, void *stream);
+
 int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
                       uint32_t *d_meta, uint32_t out_mode, void *stream) {
-    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_numeric_f64_ex: unknown out_mode %u", out_mode);
-    const bool mc = out_mode == KC_OUT_MULTIMEM;
+    if (out_mode > KC_OUT_MULTIMEM) return fail(KC_EINVAL, "kc_numeric_f64_ex: unknown out_mode %u (peers: kc_numeric_f64_peers)", out_mode);
+    kc::OutRoute mc{};
+    mc.mode = out_mode;
+    return numeric_f64_routed(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, mc, stream);
+}
+
+int kc_numeric_f64_peers(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                         uint32_t *d_meta, int32_t n_peers, const int64_t *peer_delta_bytes, void *stream) {
+    kc::OutRoute mc;
+    int rc = make_peer_route("kc_numeric_f64_peers", n_peers, peer_delta_bytes, mc);
+    if (rc) return rc;
+    return numeric_f64_routed(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, mc, stream);
+}
+
+static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n, double rel_eps, double abs_eps, double *d_value,
+                              uint32_t *d_meta, kc::OutRoute mc, void *stream) {
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_numeric_f64: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);
     if (n_groups < 0) return fail(KC_EINVAL, "kc_numeric_f64: negative n_groups");
     if (!(rel_eps >= 0.0) || !(abs_eps >= 0.0)) return fail(KC_EINVAL, "kc_numeric_f64: rel_eps/abs_eps must be >= 0");
@@ -456,6 +503,11 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
     if (!d_vals || !d_value || !d_meta) return fail(KC_EINVAL, "kc_numeric_f64: NULL buffer");
     if (!aligned16(d_vals)) return fail(KC_EINVAL, "kc_numeric_f64: d_vals must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // The fast kernels store a group's result when it is decided — most lanes at once, the deferred ones later and
+    // scattered.  Local stores do not care; multicast stores do (measured at 2 GPUs: K2 0.33 ms with the general
+    // kernel's whole-warp stores, 0.57 ms with the fast kernel's), and a fused step is NVLink-bound anyway.
+    static const bool fast_routed = [] { const char *e = getenv("KC_NUM_FAST_ROUTED"); return e && e[0] == '1'; }();
+    const bool numeric_fast = numeric_fast_env() && (mc.local() || (fast_routed && mc.mode == KC_OUT_PEERS));
     // measured on B200: TMA pipeline wins at n = 16 and 32; direct at n <= 8 (tiles too small to prefetch far enough)
     // and at n = 64 (register pressure)
     if (!force_direct() && (force_tma() || n == 16 || n == 32))
@@ -464,7 +516,7 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
             case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 16: {
                 static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
-                if (numeric_fast_enabled()) {
+                if (numeric_fast) {
                     if (cfg == 11) return launch_numeric_tma_fast<16, 4, 1, 5>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                     if (cfg == 12) return launch_numeric_tma_fast<16, 4, 2, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                     if (cfg == 13) return launch_numeric_tma_fast<16, 8, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
@@ -483,7 +535,7 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
                 return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             }
             case 32:
-                if (numeric_fast_enabled()) {
+                if (numeric_fast) {
                     static const int cfg32 = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
                     if (cfg32 == 21) return launch_numeric_tma_fast<32, 4, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                     if (cfg32 == 22) return launch_numeric_tma_fast<32, 2, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
@@ -493,7 +545,7 @@ int kc_numeric_f64_ex(const double *d_vals, int64_t n_groups, int32_t n, double 
             case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             default: break;
         }
-    if (numeric_fast_enabled() && !force_direct() && (n == 8 || n == 4)) {
+    if (numeric_fast && !force_direct() && (n == 8 || n == 4)) {
         auto launch_fast = [&](auto kernel, int NP) -> int {
             DeviceInfo info;
             int rc = device_info(info);

@@ -88,30 +88,43 @@ class ShardedConsensus:
 
 
 class FusedShardedConsensus:
-    """Fused compute + reassembly over NVSwitch multicast (no NCCL collective on the data path).
+    """Fused compute + reassembly over NVLink (no NCCL collective on the data path).
 
-    The gathered buffer [world][nbytes] is torch symmetric memory with a multicast mapping; every rank's kernels store
-    their results to the MULTICAST address of the rank's slot with `multimem.st` (kc_*_ex, KC_OUT_MULTIMEM), so the
-    switch replicates each store into all GPUs' copies while the kernel is still computing the next groups.  One
-    cross-GPU barrier (symmetric-memory signal pads) closes the step.  Requires NVLS-capable hardware (B200 + NVSwitch);
-    `available()` says whether the multicast mapping exists — callers fall back to ShardedConsensus (NCCL) otherwise.
+    The gathered buffer [world][nbytes] is torch symmetric memory: every GPU maps every rank's copy, and an NVSwitch
+    multicast mapping covers all of them.  The kernels store each result into all copies while they compute the next
+    groups, either way:
+
+    * route "peers" (default): one local store plus one P2P store per peer (kc_*_peers, KC_OUT_PEERS) — every GPU
+      receives world-1 shares and sends as many;
+    * route "multimem": one `multimem.st` to the multicast address (kc_*_ex, KC_OUT_MULTIMEM); the switch replicates it
+      into all copies, the sender's included — every GPU receives `world` shares and sends one.
+
+    One cross-GPU barrier (symmetric-memory signal pads) closes the step.  `available()` says whether the mappings
+    exist — callers fall back to ShardedConsensus (NCCL) otherwise.
     """
 
-    def __init__(self, layout: OutputLayout, device, group=None):
+    def __init__(self, layout: OutputLayout, device, group=None, route: str = "peers"):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         assert dist.is_initialized(), "FusedShardedConsensus needs an initialised process group"
-        self.layout, self.device = layout, device
+        assert route in ("peers", "multimem")
+        self.layout, self.device, self.route = layout, device, route
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.flat = symm_mem.empty(self.world * layout.nbytes, dtype=torch.uint8, device=device)
         self.handle = symm_mem.rendezvous(self.flat, self.group)
         self.gathered = self.flat.view(self.world, layout.nbytes)
         self.mc_ptr = int(self.handle.multicast_ptr or 0)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        import ctypes
+        self.n_peers = self.world - 1
+        self.peer_deltas = (ctypes.c_int64 * max(self.n_peers, 1))(*[ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank])
 
     def available(self) -> bool:
-        return self.mc_ptr != 0
+        if self.route == "multimem":
+            return self.mc_ptr != 0
+        return 1 <= self.n_peers <= 7
 
     def slot_pointers(self, multicast: bool = True):
         """(win, vote_meta, value, num_meta) raw addresses of THIS rank's slot, in the multicast or the local mapping."""
@@ -122,9 +135,34 @@ class FusedShardedConsensus:
     def rank_views(self, r: int):
         return self.layout.views(self.gathered[r])
 
+    def vote(self, codes_ptr: int, n_groups: int, n: int, none_ptr: int, n_fields: int, stream_ptr: int) -> None:
+        """K1 over this rank's shard, results to every GPU's copy of this rank's slot (enqueued on the stream)."""
+        import ctypes
+        from . import _native as K
+        lib = K.load()
+        if self.route == "multimem":
+            win, vmeta, _, _ = self.slot_pointers(multicast=True)
+            K.check(lib.kc_vote_i32_ex(codes_ptr, n_groups, n, none_ptr, n_fields, win, vmeta, K.OUT_MULTIMEM, stream_ptr))
+        else:
+            win, vmeta, _, _ = self.slot_pointers(multicast=False)
+            K.check(lib.kc_vote_i32_peers(codes_ptr, n_groups, n, none_ptr, n_fields, win, vmeta, self.n_peers,
+                                          ctypes.addressof(self.peer_deltas), stream_ptr))
+
+    def numeric(self, vals_ptr: int, n_groups: int, n: int, rel_eps: float, abs_eps: float, stream_ptr: int) -> None:
+        import ctypes
+        from . import _native as K
+        lib = K.load()
+        if self.route == "multimem":
+            _, _, value, nmeta = self.slot_pointers(multicast=True)
+            K.check(lib.kc_numeric_f64_ex(vals_ptr, n_groups, n, rel_eps, abs_eps, value, nmeta, K.OUT_MULTIMEM, stream_ptr))
+        else:
+            _, _, value, nmeta = self.slot_pointers(multicast=False)
+            K.check(lib.kc_numeric_f64_peers(vals_ptr, n_groups, n, rel_eps, abs_eps, value, nmeta, self.n_peers,
+                                             ctypes.addressof(self.peer_deltas), stream_ptr))
+
     def step(self, launch: Callable):
-        """launch(win_ptr, vmeta_ptr, value_ptr, nmeta_ptr) enqueues the kernels with KC_OUT_MULTIMEM on the current
-        stream; the barrier afterwards makes every rank's stores visible everywhere."""
-        launch(*self.slot_pointers(multicast=True))
+        """launch(self) enqueues K1/K2 through self.vote / self.numeric on the current stream; the barrier afterwards makes
+        every rank's stores visible everywhere."""
+        launch(self)
         self.handle.barrier(channel=0)
         return self.gathered

@@ -39,42 +39,43 @@ def main():
     ref.step(compute)
     torch.cuda.synchronize()
 
-    fused = FusedShardedConsensus(layout, dev)
-    ok = fused.available()
-    if rank == 0:
-        print("multicast available:", ok, flush=True)
-    if ok:
-        fused.flat.zero_()
-        dist.barrier()
-
-        def launch(win, vmeta, value, nmeta):
-            K.check(lib.kc_vote_i32_ex(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, win, vmeta, K.OUT_MULTIMEM, sp))
-            K.check(lib.kc_numeric_f64_ex(v2.data_ptr(), N * 8, n, 0.03, 1e-6, value, nmeta, K.OUT_MULTIMEM, sp))
-
-        fused.step(launch)
-        torch.cuda.synchronize()
-        same = torch.equal(fused.gathered, ref.gathered[0])
-        t = torch.tensor([1 if same else 0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    for route in ("peers", "multimem"):
+        fused = FusedShardedConsensus(layout, dev, route=route)
+        ok = fused.available()
         if rank == 0:
-            print("fused == nccl on every rank:", bool(t.item()), flush=True)
-        assert bool(t.item())
-        # timing: fused vs nccl, device events, max over ranks
-        for name, fn in (("nccl", lambda: ref.step(compute)), ("fused", lambda: fused.step(launch))):
-            for _ in range(3):
-                fn()
+            print(f"route {route}: available:", ok, flush=True)
+        if ok:
+            fused.flat.zero_()
             dist.barrier()
+
+            def launch(f):
+                f.vote(c2.data_ptr(), N * 24, n, none_code.data_ptr(), 24, sp)
+                f.numeric(v2.data_ptr(), N * 8, n, 0.03, 1e-6, sp)
+
+            fused.step(launch)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            same = torch.equal(fused.gathered, ref.gathered[0])
+            t = torch.tensor([1 if same else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
             if rank == 0:
-                print(f"{name}: {ms.item():.3f} ms/step for {N} records/rank x {world} ranks", flush=True)
+                print("fused == nccl on every rank:", bool(t.item()), flush=True)
+            assert bool(t.item())
+            # timing: fused vs nccl, device events, max over ranks
+            for name, fn in (("nccl", lambda: ref.step(compute)), ("fused", lambda: fused.step(launch))):
+                for _ in range(3):
+                    fn()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    print(f"{name}: {ms.item():.3f} ms/step for {N} records/rank x {world} ranks", flush=True)
     dist.destroy_process_group()
 
 
