@@ -13,7 +13,7 @@ import os
 from typing import Optional, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkllms_b200.so")
+LIB_PATH = os.environ.get("KLLMS_B200_LIB") or os.path.join(_HERE, "libkllms_b200.so")
 
 KC_OK, KC_EINVAL, KC_ECUDA, KC_ENODEV, KC_ENOMEM = 0, -1, -2, -3, -4
 MAX_CANDIDATES = 64

@@ -140,28 +140,37 @@ struct OutRoute {
     __host__ __device__ bool local() const { return mode == 0; }
 };
 
+// the P2P copies, out of line: the local path pays one uniform compare per store for them
+__device__ __noinline__ void store_peers_u32(void *p, uint32_t v, const OutRoute &r) {
+    for (int k = 0; k < r.n_peers; ++k)
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "r"(v) : "memory");
+}
+__device__ __noinline__ void store_peers_f64(void *p, double v, const OutRoute &r) {
+    for (int k = 0; k < r.n_peers; ++k)
+        asm volatile("st.global.f64 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ void store_local_u32(void *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void store_local_f64(void *p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ void store_out_u32(void *p, uint32_t v, const OutRoute &r) {
     if (r.mode == 1u) {
         asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-        return;
-    }
-    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-    if (r.mode == 2u) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k)
-            if (k < r.n_peers) asm volatile("st.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "r"(v) : "memory");
+    } else {
+        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        if (r.mode == 2u) store_peers_u32(p, v, r);
     }
 }
 __device__ __forceinline__ void store_out_f64(void *p, double v, const OutRoute &r) {
     if (r.mode == 1u) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-        return;
-    }
-    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-    if (r.mode == 2u) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k)
-            if (k < r.n_peers) asm volatile("st.global.f64 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "d"(v) : "memory");
+    } else {
+        asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+        if (r.mode == 2u) store_peers_f64(p, v, r);
     }
 }
 

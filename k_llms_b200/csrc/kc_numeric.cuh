@@ -426,7 +426,7 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
 template <int NP, int T, bool PREFETCH>
 __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restrict__ vals, int64_t n_groups, int n,
                                                            double rel_eps, double abs_eps, double *__restrict__ out_value,
-                                                           uint32_t *__restrict__ out_meta, OutRoute mc) {
+                                                           uint32_t *__restrict__ out_meta, const __grid_constant__ OutRoute mc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
     const double thr = abs_eps > rel_eps ? abs_eps : rel_eps;
@@ -624,7 +624,7 @@ __device__ __forceinline__ void numeric_fast_finish(const FastDecision &d, doubl
 template <int NP, int T>
 __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__restrict__ vals, int64_t n_groups, double rel_eps,
                                                                 double abs_eps, double *__restrict__ out_value,
-                                                                uint32_t *__restrict__ out_meta, OutRoute mc) {
+                                                                uint32_t *__restrict__ out_meta, const __grid_constant__ OutRoute /* local only: see the launcher */) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ int64_t defer_q[T / 32][64];
     const PlaneRow row{smem_u32(smem_raw) + threadIdx.x * 8u, T * 8u};
@@ -646,8 +646,8 @@ __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__
             double v;
             uint32_t m;
             numeric_core<NP, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-            store_out_f64(out_value + g, v, mc);
-            store_out_u32(out_meta + g, m, mc);
+            store_local_f64(out_value + g, v);
+            store_local_u32(out_meta + g, m);
         }
         __syncwarp();
     };
@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(T) numeric_direct_fast_kernel(const double *__
             double v;
             uint32_t m;
             numeric_fast_finish<NP>(fd, v, m);
-            store_out_f64(out_value + g, v, mc);
-            store_out_u32(out_meta + g, m, mc);
+            store_local_f64(out_value + g, v);
+            store_local_u32(out_meta + g, m);
         }
         __syncwarp();
         if (q_count >= 32) {
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
                                                                       const double *__restrict__ in, int64_t n_groups,
                                                                       double rel_eps, double abs_eps,
                                                                       double *__restrict__ out_value,
-                                                                      uint32_t *__restrict__ out_meta, OutRoute mc) {
+                                                                      uint32_t *__restrict__ out_meta, const __grid_constant__ OutRoute /* local only: see the launcher */) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
@@ -785,8 +785,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
             double v;
             uint32_t m;
             numeric_core<N, PlaneRow>(hi, row, rel_eps, abs_eps, thr, v, m);
-            store_out_f64(out_value + g, v, mc);
-            store_out_u32(out_meta + g, m, mc);
+            store_local_f64(out_value + g, v);
+            store_local_u32(out_meta + g, m);
         }
         __syncwarp();
     };
@@ -838,8 +838,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_fast_kernel(
             double v;
             uint32_t m;
             numeric_fast_finish<N>(fd, v, m);
-            store_out_f64(out_value + g, v, mc);
-            store_out_u32(out_meta + g, m, mc);
+            store_local_f64(out_value + g, v);
+            store_local_u32(out_meta + g, m);
         }
         __syncwarp();
         if (q_count >= 32) {  // nothing of this tile is live in registers any more
@@ -871,7 +871,7 @@ template <int N, int WARPS, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) numeric_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  int64_t n_groups, double rel_eps, double abs_eps,
                                                                  double *__restrict__ out_value,
-                                                                 uint32_t *__restrict__ out_meta, OutRoute mc) {
+                                                                 uint32_t *__restrict__ out_meta, const __grid_constant__ OutRoute mc) {
     constexpr int ROW_BYTES = N * 8;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;

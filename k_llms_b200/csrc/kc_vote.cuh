@@ -206,7 +206,7 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ codes, int6
 template <int NP, bool VEC, bool HAS_NC, bool PREFETCH>
 __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restrict__ codes, int64_t n_groups, int n,
                                                           FieldMap fm, int32_t *__restrict__ win,
-                                                          uint32_t *__restrict__ meta, OutRoute mc) {
+                                                          uint32_t *__restrict__ meta, const __grid_constant__ OutRoute mc) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t f = 0, fstep = 0;
@@ -278,7 +278,7 @@ __device__ __forceinline__ void load_row_i8(const int8_t *__restrict__ codes, in
 
 template <int NP, bool VEC, bool HAS_NC>
 __global__ void __launch_bounds__(256) vote_i8_kernel(const int8_t *__restrict__ codes, int64_t n_groups, int n, FieldMap fm,
-                                                      int32_t *__restrict__ win, uint32_t *__restrict__ meta, OutRoute mc) {
+                                                      int32_t *__restrict__ win, uint32_t *__restrict__ meta, const __grid_constant__ OutRoute mc) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t f = 0, fstep = 0;
@@ -320,7 +320,7 @@ struct Swizzle {  // TMA swizzle mode for a row of ROW_BYTES (rows wider than 12
 template <int N, int WARPS, int STAGES, bool HAS_NC>
 __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t n_groups,
                                                               FieldMap fm, int32_t *__restrict__ win,
-                                                              uint32_t *__restrict__ meta, OutRoute mc) {
+                                                              uint32_t *__restrict__ meta, const __grid_constant__ OutRoute mc) {
     constexpr int ROW_BYTES = N * 4;
     constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
     constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;

@@ -506,8 +506,7 @@ static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n,
     // The fast kernels store a group's result when it is decided — most lanes at once, the deferred ones later and
     // scattered.  Local stores do not care; multicast stores do (measured at 2 GPUs: K2 0.33 ms with the general
     // kernel's whole-warp stores, 0.57 ms with the fast kernel's), and a fused step is NVLink-bound anyway.
-    static const bool fast_routed = [] { const char *e = getenv("KC_NUM_FAST_ROUTED"); return e && e[0] == '1'; }();
-    const bool numeric_fast = numeric_fast_env() && (mc.local() || (fast_routed && mc.mode == KC_OUT_PEERS));
+    const bool numeric_fast = numeric_fast_env() && mc.local();  // the fast kernels only have local stores
     // measured on B200: TMA pipeline wins at n = 16 and 32; direct at n <= 8 (tiles too small to prefetch far enough)
     // and at n = 64 (register pressure)
     if (!force_direct() && (force_tma() || n == 16 || n == 32))
