@@ -92,6 +92,67 @@ __global__ void __launch_bounds__(256) logprob_sum_kernel(const float *__restric
     }
 }
 
+// K3, staged: sequences of a few dozen tokens leave a warp-per-sequence kernel with one or two elements per lane and
+// ~25 instructions of bookkeeping per sequence (measured 0.36 of HBM peak on config 4).  Here a CTA copies the CONTIGUOUS
+// token range of its T sequences into shared memory with 16-byte cp.async (coalesced, no register staging), then every
+// thread sums ONE sequence in exactly the documented order: partial l = elements l, l+32, ... added left to right from
+// +0.0f, then the tree the xor butterfly 16,8,4,2,1 forms (lane 0's view of it).  A tile whose tokens do not fit CAP
+// floats (long sequences) falls back to the warp-per-sequence loop.
+template <int T, int CAP>
+__global__ void __launch_bounds__(T) logprob_sum_tile_kernel(const float *__restrict__ lp, const int64_t *__restrict__ offsets,
+                                                             int64_t n_seq, float *__restrict__ out) {
+    extern __shared__ __align__(16) float tok[];  // CAP + 4 floats
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_tiles = (n_seq + T - 1) / T;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * T;
+        const int cnt = (int)min((int64_t)T, n_seq - s0);
+        // all four offset loads in flight together: the tile's range and this thread's sequence
+        const int64_t t0 = __ldg(offsets + s0), t1 = __ldg(offsets + s0 + cnt);
+        const int64_t my_b = __ldg(offsets + s0 + (tid < cnt ? tid : 0)), my_e = __ldg(offsets + s0 + (tid < cnt ? tid + 1 : 0));
+        const int64_t t0a = t0 & ~int64_t(3);  // the copy starts at the 16-byte boundary at or below t0
+        const int64_t span = t1 - t0a;
+        if (span <= CAP) {
+            const int n_vec = (int)(span >> 2);  // whole 16-byte pieces inside [t0a, t1)
+            const uint32_t dst = smem_u32(tok);
+            for (int v = tid; v < n_vec; v += T)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)v * 16u), "l"(lp + t0a + (int64_t)v * 4) : "memory");
+            for (int i = (n_vec << 2) + tid; i < (int)span; i += T) tok[i] = __ldg(lp + t0a + i);  // < 4 stragglers
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (tid < cnt) {
+                const int64_t b = my_b, e = my_e;
+                const float *x = tok + (b - t0a);
+                const int len = (int)(e - b);
+                float p[32];
+#pragma unroll
+                for (int l = 0; l < 32; ++l) p[l] = 0.0f;
+                for (int k = 0; k < len; k += 32) {
+#pragma unroll
+                    for (int l = 0; l < 32; ++l)
+                        if (k + l < len) p[l] = __fadd_rn(p[l], x[k + l]);
+                }
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+#pragma unroll
+                    for (int l = 0; l < st; ++l) p[l] = __fadd_rn(p[l], p[l + st]);
+                }
+                out[s0 + tid] = p[0];
+            }
+            __syncthreads();  // the tile buffer is reused
+        } else {
+            for (int q = warp; q < cnt; q += T / 32) {
+                const int64_t b = __ldg(offsets + s0 + q), e = __ldg(offsets + s0 + q + 1);
+                float acc = 0.0f;
+                for (int64_t i = b + lane; i < e; i += 32) acc = __fadd_rn(acc, __ldg(lp + i));
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, st));
+                if (lane == 0) out[s0 + q] = acc;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- K3b: likelihood-weighted vote (self-defined spec)
 
 // exp(x) for x <= 0, built only from single IEEE fp32 operations in a fixed order so that the C oracle
@@ -182,6 +243,103 @@ __global__ void __launch_bounds__(128) weighted_vote_kernel(const int32_t *__res
         meta[g] = pack_meta(best_idx, best_cnt, voters, present,
                             voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
         weight[g] = voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
+    }
+}
+
+// K3b, weights once per record: the candidate weights depend on the record only, not on the field.  A CTA of T threads
+// covers T consecutive groups (fields of a handful of records); its warps first compute w_c = kexp(s_c - max s) for
+// those records into shared memory (lane = candidate, warp max by shuffles), then every thread votes its group with the
+// weights read from there (same class sums, same order as weighted_vote_kernel).
+template <int NP, int T>
+__global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__restrict__ codes, const float *__restrict__ seq_lp,
+                                                              int64_t n_groups, int n, FieldMap fm, bool has_nc,
+                                                              int32_t *__restrict__ win, uint32_t *__restrict__ meta,
+                                                              float *__restrict__ weight) {
+    using M = typename MaskOf<NP>::type;
+    extern __shared__ float wts[];  // [records of the tile][NP], then the codes as a [cell][thread] plane
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int max_recs = T / (int)fm.n_fields + 2;
+    int32_t *plane = reinterpret_cast<int32_t *>(wts + (size_t)max_recs * NP);  // data-dependent cell index, no bank conflicts
+    const int64_t n_tiles = (n_groups + T - 1) / T;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * T, g1 = min(g0 + T, n_groups);
+        const int64_t r0 = g0 / fm.n_fields, r1 = (g1 - 1) / fm.n_fields;
+        for (int64_t r = r0 + warp; r <= r1; r += T / 32) {
+            float s_lo = (lane < n) ? __ldg(seq_lp + r * n + lane) : -3.0e38f;
+            float s_hi = (NP > 32 && lane + 32 < n) ? __ldg(seq_lp + r * n + lane + 32) : -3.0e38f;
+            float smax = fmaxf(s_lo, s_hi);
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xFFFFFFFFu, smax, st));
+            float *w = wts + (r - r0) * NP;
+            if (lane < NP) w[lane] = kexp(__fadd_rn(s_lo, -smax));
+            if (NP > 32) w[lane + 32] = kexp(__fadd_rn(s_hi, -smax));
+        }
+        __syncthreads();
+        const int64_t g = g0 + tid;
+        if (g < g1) {
+            // record and field of this thread without a 64-bit division: offset inside the tile's first record
+            const uint32_t fpos = (uint32_t)(g0 - r0 * fm.n_fields) + (uint32_t)tid;
+            const uint32_t rec_local = fm.div_small(fpos);
+            const uint32_t field = fpos - rec_local * fm.n_fields;
+            const int32_t nc = has_nc ? __ldg(fm.none_code + field) : KC_CODE_NONE;
+            const float *w = wts + rec_local * NP;
+            int32_t x[NP], rawrow[NP];
+            if (n == NP) load_row<NP, true>(codes, g, n, rawrow);
+            else load_row<NP, false>(codes, g, n, rawrow);
+            M live = 0;
+            int present = 0;
+            float total = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int32_t raw = rawrow[i];
+                int32_t c = (raw == KC_CODE_NONE) ? nc : raw;  // None votes as none_code where it is >= 0
+                c = c < KC_CODE_NONE ? KC_CODE_NONE : c;        // absent cells never vote
+                x[i] = c;
+                plane[i * T + tid] = c;
+                present += raw < KC_CODE_NONE ? 0 : 1;
+                if (c >= 0) {
+                    live |= M(1) << i;
+                    total = __fadd_rn(total, w[i]);
+                }
+            }
+            const int voters = popc_m(live);
+            float best_w = -1.0f;
+            int best_idx = 0, best_cnt = 0;
+            int32_t best_code = KC_CODE_NONE;
+            bool tie = false;
+            float consumed = 0.0f;
+            while (live) {
+                // Every class still waiting sums a subset of the unconsumed weights, so its fp32 sum is at most
+                // (total - consumed) up to rounding (< 32 * 2^-23 relative on each side); 5e-5 * total is a safe slack.
+                // Below best_w it can neither win nor tie: stop.  (An agreeing majority ends the loop after one class.)
+                if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;
+                const int i = ffs_mask(live) - 1;
+                const int32_t c = plane[i * T + tid];
+                M eq = 0;
+                float cw = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const bool e = x[j] == c;  // cells before i with this code were consumed with their class
+                    eq |= e ? (M(1) << j) : M(0);
+                    cw = e ? __fadd_rn(cw, w[j]) : cw;
+                }
+                if (cw > best_w) {
+                    best_w = cw;
+                    best_idx = i;
+                    best_cnt = popc_m(eq);
+                    best_code = c;
+                    tie = false;
+                } else if (cw == best_w) {
+                    tie = true;
+                }
+                consumed = __fadd_rn(consumed, cw);
+                live &= ~eq;
+            }
+            win[g] = best_code;
+            meta[g] = pack_meta(best_idx, best_cnt, voters, present, voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
+            weight[g] = voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
+        }
+        __syncthreads();
     }
 }
 

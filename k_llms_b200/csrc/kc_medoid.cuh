@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
             u += __popc(mask);
         }
         __syncwarp();
-        for (int i = lane; i < k; i += 32) s_cls[i] = s_cls[s_rep[i]];  // representatives already hold their own class
+        for (int i = lane; i < k; i += 32)
+            if (s_rep[i] != i) s_cls[i] = s_cls[s_rep[i]];  // representatives already hold their own class (and only they are read)
         // 2. match tables of the distinct strings that can be a pattern
         for (int a = lane; a < u; a += 32) {
             const int i = s_uniq[a], o = s_off[i], l = s_len[i];

@@ -168,7 +168,9 @@ struct FieldMap {
     const int32_t *none_code;  // NULL => no field has voting Nones
     uint32_t n_fields;
     uint32_t magic;
-    __device__ __forceinline__ uint32_t mod_small(uint32_t x) const { return x - __umulhi(x, magic) * n_fields; }
+    // x / n_fields and x % n_fields for x < n_fields + a few hundred (magic = 2^32 / n_fields + 1 does not fit for n_fields = 1)
+    __device__ __forceinline__ uint32_t div_small(uint32_t x) const { return n_fields == 1u ? x : __umulhi(x, magic); }
+    __device__ __forceinline__ uint32_t mod_small(uint32_t x) const { return x - div_small(x) * n_fields; }
 };
 
 // ---------------------------------------------------------------- direct front-end

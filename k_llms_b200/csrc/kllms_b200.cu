@@ -203,6 +203,25 @@ int launch_vote_i8(const int8_t *codes, int64_t G, int n, const int32_t *none_co
     return KC_OK;
 }
 
+// ---------------------------------------------------------------- K3 launcher
+
+template <int T, int CAP>
+static int launch_logprob_tile(const float *d_logprobs, const int64_t *d_offsets, int64_t n_seq, float *d_sum, const DeviceInfo &info,
+                               void *stream) {
+    // T sequences per tile, their contiguous tokens staged in shared memory (up to CAP floats; longer tiles fall back to
+    // the warp-per-sequence loop inside the kernel)
+    auto kernel = kc::logprob_sum_tile_kernel<T, CAP>;
+    const size_t smem = (size_t)(CAP + 4) * sizeof(float);
+    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+    const int64_t tiles = (n_seq + T - 1) / T;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)info.sm_count * std::max(per_sm, 1));
+    kernel<<<grid, T, smem, static_cast<cudaStream_t>(stream)>>>(d_logprobs, d_offsets, n_seq, d_sum);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+}
+
 // ---------------------------------------------------------------- K2 launchers
 
 template <int N, int WARPS, int STAGES, int MIN_CTAS = 1>
@@ -593,6 +612,14 @@ int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
+    static const bool staged = [] { const char *e = getenv("KC_K3_STAGED"); return !e || e[0] != '0'; }();
+    if (staged && n_seq >= 4096 && aligned16(d_logprobs)) {
+        static const int k3cfg = [] { const char *e = getenv("KC_K3_CFG"); return e ? atoi(e) : 0; }();
+        if (k3cfg == 1) return launch_logprob_tile<128, 12 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
+        if (k3cfg == 2) return launch_logprob_tile<64, 4 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
+        if (k3cfg == 3) return launch_logprob_tile<32, 3 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
+        return launch_logprob_tile<64, 6 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
+    }
     const int threads = 256;  // 8 warps, one sequence per warp per iteration
     const int64_t warps = n_seq;
     const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)info.sm_count * 8);
@@ -616,6 +643,24 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
     const int grid = (int)std::min<int64_t>((G + threads - 1) / threads, (int64_t)info.sm_count * 8);
     const kc::FieldMap fm = make_field_map(d_none_code, n_fields);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool per_record = [] { const char *e = getenv("KC_K3B_REC"); return !e || e[0] != '0'; }();
+    if (per_record && n >= 8) {  // weights once per record, codes in a shared-memory plane
+        const int max_recs = threads / n_fields + 2;
+        auto launch = [&](auto kernel, int NP) -> int {
+            const size_t smem = (size_t)max_recs * NP * 4 + (size_t)NP * threads * 4;
+            KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+            const int g2 = (int)std::min<int64_t>((G + threads - 1) / threads, (int64_t)info.sm_count * std::max(per_sm, 1));
+            kernel<<<g2, threads, smem, st>>>(d_codes, d_seq_logprob, G, n, fm, d_none_code != nullptr, d_win_code, d_meta, d_weight);
+            KC_CUDA(cudaGetLastError());
+            return KC_OK;
+        };
+        if (n <= 8) return launch(kc::weighted_vote_rec_kernel<8, 128>, 8);
+        if (n <= 16) return launch(kc::weighted_vote_rec_kernel<16, 128>, 16);
+        if (n <= 32) return launch(kc::weighted_vote_rec_kernel<32, 128>, 32);
+        return launch(kc::weighted_vote_rec_kernel<64, 128>, 64);
+    }
 #define KC_WV(NP) kc::weighted_vote_kernel<NP><<<grid, threads, 0, st>>>(d_codes, d_seq_logprob, G, n, fm, d_none_code != nullptr, d_win_code, d_meta, d_weight)
     if (n <= 2) KC_WV(2);
     else if (n <= 4) KC_WV(4);

@@ -74,6 +74,19 @@ def test_vote_matches_oracle(n):
             assert np.array_equal(meta.cpu().numpy().view(np.uint32), exp_meta)
 
 
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+def test_vote_single_field_with_none_code(n):
+    """One vote field whose Nones vote (none_code given, n_fields = 1): the field index arithmetic of every front-end."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(n)
+    codes = random_codes(rng, 5000, n, 4, p_none=0.3)
+    for nc in (np.array([2], dtype=np.int32), np.array([-1], dtype=np.int32)):
+        exp_win, exp_meta = OC.vote(codes, nc)
+        win, meta = K.vote(torch.from_numpy(codes).cuda(), torch.from_numpy(nc).cuda())
+        assert np.array_equal(win.cpu().numpy(), exp_win) and np.array_equal(meta.cpu().numpy().view(np.uint32), exp_meta)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 16, 24, 32, 48, 64])
 @pytest.mark.parametrize("style", ["ints", "near", "pow10", "floats", "lowbits"])
 def test_numeric_matches_oracle(n, style):
@@ -310,6 +323,43 @@ def test_config4_logprob_pipeline_n32():
     assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
     ref64 = np.add.reduceat(lp.astype(np.float64), offsets[:-1])
     assert np.max(np.abs(exp_sums - ref64)) < 1e-4
+
+
+def test_logprob_sum_staged_tiles_and_fallback():
+    """K3's shared-memory-staged kernel (>= 4096 sequences): empty and 1-token sequences, lengths around the 32-lane
+    stride, tiles whose tokens exceed the staging buffer (warp-per-sequence fallback inside the kernel), -0.0 inputs."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(12)
+    S = 20000
+    lens = rng.choice([0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 200], S)
+    lens[5000:5003] = [30000, 7, 15000]        # tiles 39: far beyond the buffer
+    lens[12800:12928] = 97                     # a full tile just above 12288 tokens
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    lp = (-rng.exponential(1.0, offsets[-1])).astype(np.float32)
+    lp[rng.random(lp.size) < 0.01] = -0.0
+    got = K.logprob_sum(torch.from_numpy(lp).cuda(), torch.from_numpy(offsets).cuda()).cpu().numpy()
+    exp = OC.logprob_sum(lp, offsets)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+@pytest.mark.parametrize("fields", [1, 5, 24, 200])
+def test_weighted_vote_per_record_kernel(n, fields):
+    """K3b's weights-once-per-record kernel over several fields-per-record shapes (tiles spanning 1 .. 128 records)."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(n * 1000 + fields)
+    R = max(2, 30000 // fields)
+    codes = random_codes(rng, R * fields, n, 5, p_absent=0.05).reshape(R, fields, n)
+    seq = (-rng.exponential(20.0, (R, n))).astype(np.float32)
+    none_code = rng.choice([-1, 0, 3], fields).astype(np.int32)
+    for nc in (None, none_code):
+        win, meta, wt = K.weighted_vote(torch.from_numpy(codes).cuda(), torch.from_numpy(seq).cuda(),
+                                        torch.from_numpy(nc).cuda() if nc is not None else None)
+        ew, em, ewt = OC.weighted_vote(codes, seq, nc)
+        assert np.array_equal(win.cpu().numpy(), ew) and np.array_equal(meta.cpu().numpy().view(np.uint32), em)
+        assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
 
 
 @pytest.mark.parametrize("n", [3, 4, 8, 16, 32, 64])
