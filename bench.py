@@ -5,8 +5,10 @@
 
 A "step" is one pass of the hot path over one batch: K1 (vote, 24 fields) + K2 (numeric, 8 fields) over
 `records` records per GPU with n candidates (BASELINE configs[1]: 1M x 32 fields, n=16); at N > 1 every rank owns
-its own 1M-record shard (weak scaling, configs[4]) and a step ends with the NCCL all-gather that reassembles the
-packed output columns on every rank.  One JSON line on stdout (rank 0).
+its own 1M-record shard (weak scaling, configs[4]) and a step ends with every rank holding every rank's packed output
+columns: by default the reassembly is fused into the kernels (P2P stores into the peers' copies of a symmetric-memory
+buffer; --route multimem: NVSwitch multicast stores), --reassembly nccl runs a pipelined NCCL all-gather instead.
+One JSON line on stdout (rank 0).
 
 value      whole-job records/s, inputs resident in HBM, CUDA events, max over ranks, barrier + synchronize on both sides.
 e2e        same metric through the C-ABI call with HOST buffers (kc_consensus_host: pinned host -> H2D -> K1/K2 -> D2H),
