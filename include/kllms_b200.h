@@ -182,6 +182,10 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
 int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
                   int32_t max_group, int32_t *d_best_idx, double *d_best_avg, void *stream);
 
+/* K4 with HOST buffers (H2D, one launch, D2H; synchronous): what the host planners call for a batch of string groups. */
+int kc_medoid_str_host(const uint8_t *h_chars, int64_t n_chars, const int32_t *h_str_off, const int32_t *h_grp_off, int64_t n_groups,
+                       int32_t max_group, int32_t *h_best_idx, double *h_best_avg, int device);
+
 /*
  * End-to-end entry with HOST buffers (the call a k_llms binding makes for a batch of records of one
  * flat schema): chunked, double-buffered H2D -> K1/K2 -> D2H on internal streams of `device`.

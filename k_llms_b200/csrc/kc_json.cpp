@@ -425,18 +425,22 @@ void json_value(const Tok &t, std::string &out) {
 
 // ---------------------------------------------------------------- per-record plan
 
-enum GroupKind : uint8_t { G_ALLNULL = 0, G_VOTE_STR, G_VOTE_BOOL, G_NUMERIC };
+enum GroupKind : uint8_t { G_ALLNULL = 0, G_VOTE_STR, G_VOTE_BOOL, G_NUMERIC, G_MEDOID };
 
 struct Group {
     GroupKind kind;
     std::string_view key;
-    int64_t row = -1;  // row in the vote / numeric cell matrix
+    int64_t row = -1;       // row in the vote / numeric cell matrix, or the medoid group index
+    uint32_t m_first = 0;   // G_MEDOID: first string of the group in Record::mlen, and how many (the non-None cells)
+    uint32_t m_count = 0;
 };
 
 struct Record {
     uint8_t status = 0;        // 0 native, 1 needs the Python path
     std::vector<Group> groups;
     std::vector<Tok> cells;    // groups.size() * n tokens, group-major (T_MISSING / T_NULL count as None)
+    std::string mchars;        // normalize_string() of the cells of the medoid groups, back to back
+    std::vector<int32_t> mlen; // their lengths
 };
 
 const double kF64None = [] { const uint64_t b = KC_F64_NONE_BITS; double d; memcpy(&d, &b, 8); return d; }();
@@ -483,6 +487,8 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     rec.groups.clear();
     rec.cells.clear();
+    rec.mchars.clear();
+    rec.mlen.clear();
     rec.cells.reserve(keys.size() * (size_t)n);
     std::vector<size_t> cursor((size_t)n, 0);
     for (auto &key : keys) {
@@ -509,21 +515,55 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
             rec.status = 1;
             return;
         } else if (first->type == T_STR || first->type == T_TRUE || first->type == T_FALSE) {
+            bool multi_word = false, all_str = true;
+            int live = 0;
             for (int c = 0; c < n; ++c) {
                 const Tok &t = cells[c];
                 if (t.type <= T_NULL) continue;
+                ++live;
                 if (t.type == T_NESTED) {  // str(dict) is almost never enum-like: leave it to Python
                     rec.status = 1;
                     return;
                 }
+                all_str &= t.type == T_STR;
                 if (t.type == T_STR) {  // numbers and bools print as one word
                     tmp.clear();
                     py_str(t, tmp);
-                    if (word_count(tmp) >= 3) {  // not enum-like -> similarity medoid (host)
-                        rec.status = 1;
-                        return;
+                    multi_word |= word_count(tmp) >= 3;
+                }
+            }
+            if (multi_word) {
+                // Not enum-like (cu:1405): the similarity medoid of consensus_as_primitive (cu:1221-1237).  K4 takes it when
+                // every pair is a Levenshtein pair inside its contract (same rule as columnar.Plan._medoid_on_device under
+                // the default string_similarity_method "embeddings"); anything else goes to the Python path.
+                if (!all_str) {
+                    rec.status = 1;
+                    return;
+                }
+                g.kind = G_MEDOID;
+                g.m_first = (uint32_t)rec.mlen.size();
+                g.m_count = (uint32_t)live;
+                if (live >= 2) {
+                    int long_raw = 0, long_norm = 0;
+                    thread_local std::string norm;
+                    for (int c = 0; c < n; ++c) {
+                        const Tok &t = cells[c];
+                        if (t.type != T_STR) continue;
+                        tmp.clear();
+                        py_str(t, tmp);
+                        sanitize(tmp, norm);  // == normalize_string (cu:660-673) on ASCII text
+                        long_raw += tmp.size() > 50;
+                        long_norm += norm.size() > 64;
+                        if (norm.size() > 2000 || long_raw > 1 || long_norm > 1) {
+                            rec.status = 1;
+                            return;
+                        }
+                        rec.mchars += norm;
+                        rec.mlen.push_back((int32_t)norm.size());
                     }
                 }
+                rec.groups.push_back(g);
+                continue;
             }
             if (first->type == T_STR) {
                 g.kind = G_VOTE_STR;
@@ -599,8 +639,8 @@ double py_round5(double x) {
     return (double)(uint64_t)q / 100000.0;
 }
 
-void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, std::string &content,
-                 std::string &lik) {
+void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, const int32_t *midx,
+                 const double *mavg, std::string &content, std::string &lik) {
     content = "{";
     lik = "{";
     bool first = true;
@@ -646,6 +686,18 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
             } else {
                 conf = present == 0 ? 1.0 : 0.0;
             }
+        } else if (g.kind == G_MEDOID) {
+            // cu:1444 then cu:1085-1086 (one non-None cell, unrounded) or cu:1233-1237 (the medoid, rounded)
+            const double sub = 1.0 * ((double)g.m_count / (double)n);
+            int want = g.m_count >= 2 ? midx[g.row] : 0;
+            for (int c = 0; c < n; ++c) {
+                if (cells[c].type <= T_NULL) continue;
+                if (want-- == 0) {
+                    value = cells[c];
+                    break;
+                }
+            }
+            conf = g.m_count >= 2 ? py_round5(sub * mavg[g.row]) : sub * (1.0 / 1.0);
         }  // G_ALLNULL: None, 0.0 (cu:1401-1402)
         json_value(value, content);
         json_float(conf, lik);
@@ -697,14 +749,27 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
     parallel_for(n_records, threads, [&](int64_t r) { plan_record(texts + r * n, lens ? lens + r * n : nullptr, n, recs[(size_t)r]); });
 
     const auto t1 = now();
-    int64_t gv = 0, gx = 0;
+    int64_t gv = 0, gx = 0, gm = 0;
+    // medoid groups of the whole batch in CSR form for ONE K4 launch
+    std::vector<uint8_t> m_chars;
+    std::vector<int32_t> m_str_off{0}, m_grp_off{0};
+    int32_t m_max_group = 2;
     for (auto &rec : recs) {
         if (rec.status) continue;
         for (auto &g : rec.groups) {
             if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) g.row = gv++;
             else if (g.kind == G_NUMERIC) g.row = gx++;
+            else if (g.kind == G_MEDOID && g.m_count >= 2) {
+                g.row = gm++;
+                for (uint32_t k = 0; k < g.m_count; ++k) m_str_off.push_back(m_str_off.back() + rec.mlen[g.m_first + k]);
+                m_grp_off.push_back(m_grp_off.back() + (int32_t)g.m_count);
+                m_max_group = std::max(m_max_group, (int32_t)g.m_count);
+            }
         }
+        if (!rec.mchars.empty()) m_chars.insert(m_chars.end(), rec.mchars.begin(), rec.mchars.end());
     }
+    std::vector<int32_t> m_idx((size_t)gm);
+    std::vector<double> m_avg((size_t)gm);
     // page-locked staging buffers are expensive to create: keep them (grow-only) across calls
     static std::mutex pool_mu;
     static struct { void *p = nullptr; size_t cap = 0; } pool[6];
@@ -744,6 +809,9 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
         // one "field" per group: the two halves are independent calls of the host-buffer entry
         if (gv) rc = kc_consensus_host_i8(h_codes, 1, nullptr, nullptr, 0, gv, n, rel_eps, abs_eps, h_win, h_vmeta, nullptr, nullptr, device, nullptr);
         if (!rc && gx) rc = kc_consensus_host_i8(nullptr, 0, nullptr, h_vals, 1, gx, n, rel_eps, abs_eps, nullptr, nullptr, h_value, h_nmeta, device, nullptr);
+        if (!rc && gm)
+            rc = kc_medoid_str_host(m_chars.data(), (int64_t)m_chars.size(), m_str_off.data(), m_grp_off.data(), gm, m_max_group, m_idx.data(),
+                                    m_avg.data(), device);
     }
     t4 = now();
     if (!rc) {
@@ -754,7 +822,7 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
             out_likelihoods[r] = nullptr;
             if (rec.status) return;
             std::string content, lik;
-            emit_record(rec, n, h_vmeta, h_value, h_nmeta, content, lik);
+            emit_record(rec, n, h_vmeta, h_value, h_nmeta, m_idx.data(), m_avg.data(), content, lik);
             out_content[r] = dup_string(content);
             out_likelihoods[r] = dup_string(lik);
         });

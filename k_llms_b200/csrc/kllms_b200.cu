@@ -697,6 +697,42 @@ int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_
     return KC_OK;
 }
 
+int kc_medoid_str_host(const uint8_t *h_chars, int64_t n_chars, const int32_t *h_str_off, const int32_t *h_grp_off, int64_t n_groups,
+                       int32_t max_group, int32_t *h_best_idx, double *h_best_avg, int device) {
+    if (n_groups < 0 || n_chars < 0) return fail(KC_EINVAL, "kc_medoid_str_host: negative size");
+    if (n_groups == 0) return KC_OK;
+    if (!h_str_off || !h_grp_off || !h_best_idx || !h_best_avg || (n_chars && !h_chars)) return fail(KC_EINVAL, "kc_medoid_str_host: NULL buffer");
+    KC_CUDA(cudaSetDevice(device));
+    const int64_t n_str = h_grp_off[n_groups];
+    if (n_str < 0 || h_str_off[n_str] != n_chars) return fail(KC_EINVAL, "kc_medoid_str_host: offsets do not add up to n_chars");
+    const size_t b_chars = ((size_t)n_chars + 255) & ~size_t(255), b_str = (((size_t)n_str + 1) * 4 + 255) & ~size_t(255),
+                 b_grp = (((size_t)n_groups + 1) * 4 + 255) & ~size_t(255), b_idx = ((size_t)n_groups * 4 + 255) & ~size_t(255),
+                 b_avg = (size_t)n_groups * 8;
+    uint8_t *d = nullptr;
+    KC_CUDA(cudaMalloc(&d, b_chars + b_str + b_grp + b_idx + b_avg + 256));
+    uint8_t *d_chars = d, *d_str = d + b_chars + 256, *d_grp = d_str + b_str, *d_idx = d_grp + b_grp, *d_avg = d_idx + b_idx;
+    int rc = KC_OK;
+    cudaStream_t st = nullptr;
+    auto guard = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == KC_OK) rc = fail(KC_ECUDA, "kc_medoid_str_host: %s: %s", what, cudaGetErrorString(e));
+    };
+    guard(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
+    if (n_chars) guard(cudaMemcpyAsync(d_chars, h_chars, (size_t)n_chars, cudaMemcpyHostToDevice, st), "H2D chars");
+    guard(cudaMemcpyAsync(d_str, h_str_off, ((size_t)n_str + 1) * 4, cudaMemcpyHostToDevice, st), "H2D str_off");
+    guard(cudaMemcpyAsync(d_grp, h_grp_off, ((size_t)n_groups + 1) * 4, cudaMemcpyHostToDevice, st), "H2D grp_off");
+    if (rc == KC_OK)
+        rc = kc_medoid_str(d_chars, reinterpret_cast<int32_t *>(d_str), reinterpret_cast<int32_t *>(d_grp), n_groups, max_group,
+                           reinterpret_cast<int32_t *>(d_idx), reinterpret_cast<double *>(d_avg), st);
+    guard(cudaMemcpyAsync(h_best_idx, d_idx, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st), "D2H idx");
+    guard(cudaMemcpyAsync(h_best_avg, d_avg, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st), "D2H avg");
+    if (st) {
+        guard(cudaStreamSynchronize(st), "sync");
+        cudaStreamDestroy(st);
+    }
+    cudaFree(d);
+    return rc;
+}
+
 void *kc_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -10,6 +10,27 @@ from tests.helpers import raising_embeddings
 
 pytestmark = pytest.mark.gpu
 
+PHRASE_WORDS = "invoice total due amount net gross payment bank transfer within thirty days from receipt of goods acme corp ltd".split()
+
+
+def _phrase(rng, lo=3, hi=8):
+    return " ".join(rng.choice(PHRASE_WORDS) for _ in range(rng.randrange(lo, hi + 1)))
+
+
+def _phrase_variant(rng, base):
+    words = base.split()
+    r = rng.random()
+    if r < 0.3:
+        words[rng.randrange(len(words))] = rng.choice(PHRASE_WORDS)
+    elif r < 0.5:
+        words = words[:-1] if len(words) > 1 else words     # may leave fewer than three words
+    elif r < 0.7:
+        words = [w.upper() if rng.random() < 0.5 else w + "," for w in words]
+    elif r < 0.8:
+        return _phrase(rng, 12, 16)                         # one long candidate (> 50 characters) stays inside K4's contract
+    return " ".join(words)
+
+
 WORDS = ["alpha", "Bravo", "charlie", "DELTA", "echo", "fox-trot", "golf", "Hotel", "", "a b", "x\ty", 'q"uote', "back\\slash", "nl\n"]
 
 
@@ -22,14 +43,14 @@ def _expected(texts):
 
 def _random_record(rng, n):
     n_fields = rng.randrange(1, 7)
-    kinds = [rng.choice(["str", "bool", "int", "float", "near", "big", "mixnum"]) for _ in range(n_fields)]
+    kinds = [rng.choice(["str", "bool", "int", "float", "near", "big", "mixnum", "phrase", "phrase"]) for _ in range(n_fields)]
     truth = {}
     for f, k in enumerate(kinds):
         truth[f] = {"str": lambda: rng.choice(WORDS), "bool": lambda: rng.random() < 0.5,
                     "int": lambda: rng.randrange(-50, 10 ** rng.randrange(1, 8)), "float": lambda: rng.uniform(-1e3, 1e5),
                     "near": lambda: rng.choice([1.0, 100.0, 1e-5, 1e16, 123456789.125, 0.0, -0.0]),
                     "big": lambda: rng.choice([10 ** 30, 2 ** 63, -(10 ** 25), 10 ** 400]),
-                    "mixnum": lambda: rng.choice([1, 1.0, 2, 2.5])}[k]()
+                    "mixnum": lambda: rng.choice([1, 1.0, 2, 2.5]), "phrase": lambda: _phrase(rng)}[k]()
     texts = []
     for _ in range(n):
         d = {}
@@ -42,7 +63,8 @@ def _random_record(rng, n):
                 v = {"str": lambda: rng.choice(WORDS).upper(), "bool": lambda: rng.random() < 0.5,
                      "int": lambda: rng.randrange(0, 1000), "float": lambda: rng.uniform(0, 10),
                      "near": lambda: truth[f] * rng.choice([1.02, 0.97, 1.05, 10.0]) if isinstance(truth[f], float) else 3.0,
-                     "big": lambda: rng.choice([10 ** 30 + 1, 7]), "mixnum": lambda: rng.choice([True, "1", None, 3])}[k]()
+                     "big": lambda: rng.choice([10 ** 30 + 1, 7]), "mixnum": lambda: rng.choice([True, "1", None, 3]),
+                     "phrase": lambda: _phrase_variant(rng, truth[f])}[k]()
             if r > 0.93:
                 v = None
             d[f"k{f}" if rng.random() > 0.02 else "reasoning___why"] = v
@@ -69,6 +91,10 @@ def test_native_json_matches_reference_client_order():
         ['{"f": 1e400}', '{"f": 3}', '{"f": 3}'], ['{"f": 1E5}', '{"f": 100000.0}', '{"f": 1e+5}'],
         ['{"s": "a\\u0041b"}', '{"s": "aAb"}'], ['{"v": 0.1}', '{"v": 0.1}', '{"v": 0.30000000000000004}'],
         ['{"t": true, "u": "true"}', '{"t": null, "u": true}', '{"t": false, "u": "TRUE!"}'],
+        ['{"p": "the big cat"}', '{"p": "the big cat"}', '{"p": "the big dog"}'],                  # medoid on K4
+        ['{"p": "the big cat"}', '{"p": null}', '{}'],                                              # one non-None phrase
+        ['{"p": "the big cat sat"}', '{"p": "a b"}', '{"p": ""}', '{"p": "THE BIG CAT SAT!"}'],     # short and empty members
+        ['{"p": "one two three", "q": "x y z w"}', '{"p": "one two tree", "q": "x y z"}', '{"q": "x y z w"}'],
     ]
     for s in specials:
         records.append((len(s), s))
@@ -91,7 +117,9 @@ def test_native_json_matches_reference_client_order():
 
 def test_native_json_declines_what_it_cannot_express():
     from k_llms_b200 import _native as K
-    recs = [['{"a": {"b": 1}}', '{"a": {"b": 1}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": "x"}'],
+    long1, long2 = " ".join(["payment"] * 9), " ".join(["transfer"] * 8)
+    recs = [['{"a": {"b": 1}}', '{"a": {"b": 1}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": 7}'],
+            [json.dumps({"a": long1}), json.dumps({"a": long2})],  # two strings > 50 chars: an embeddings pair
             ['{"a": "caf\\u00e9"}', '{"a": "cafe"}'], ['[1, 2]', '{"a": 1}'], ['', '{"a": 1}'], ['{"a": true}', '{"a": 1}']]
     assert K.consolidate_json(recs) == [None] * len(recs)
     ok = K.consolidate_json([['{"a": "x"}', '{"a": "X!"}']])
