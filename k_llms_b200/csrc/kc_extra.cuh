@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
     extern __shared__ float wts[];  // [records of the tile][NP], then the codes as a [cell][thread] plane
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int max_recs = T / (int)fm.n_fields + 2;
-    int32_t *plane = reinterpret_cast<int32_t *>(wts + (size_t)max_recs * NP);  // data-dependent cell index, no bank conflicts
+    int32_t *heavy = reinterpret_cast<int32_t *>(wts + (size_t)max_recs * NP);  // [records of the tile]
+    int32_t *plane = heavy + max_recs;  // the codes, [cell][thread]: data-dependent cell index, no bank conflicts
     const int64_t n_tiles = (n_groups + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t g0 = tile * T, g1 = min(g0 + T, n_groups);
@@ -273,6 +274,9 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             float *w = wts + (r - r0) * NP;
             if (lane < NP) w[lane] = kexp(__fadd_rn(s_lo, -smax));
             if (NP > 32) w[lane + 32] = kexp(__fadd_rn(s_hi, -smax));
+            // the heaviest candidate (first of equals): its class is visited first, which usually ends the class walk at once
+            const uint32_t is_lo = __ballot_sync(0xFFFFFFFFu, s_lo == smax), is_hi = __ballot_sync(0xFFFFFFFFu, s_hi == smax);
+            if (lane == 0) heavy[r - r0] = is_lo ? __ffs((int)is_lo) - 1 : 32 + __ffs((int)is_hi) - 1;
         }
         __syncthreads();
         const int64_t g = g0 + tid;
@@ -308,13 +312,19 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             int32_t best_code = KC_CODE_NONE;
             bool tie = false;
             float consumed = 0.0f;
+            // Order of the walk: the class of the record's heaviest candidate first (if it votes here), then first-seen
+            // order.  The outcome does not depend on the order: the heaviest class wins, equal weights go to the class seen
+            // first (smaller first index), `tie` says whether another class equals the winner.
+            int first_pick = heavy[rec_local];
+            if (!((live >> first_pick) & 1)) first_pick = -1;
             while (live) {
                 // Every class still waiting sums a subset of the unconsumed weights, so its fp32 sum is at most
                 // (total - consumed) up to rounding (< 32 * 2^-23 relative on each side); 5e-5 * total is a safe slack.
                 // Below best_w it can neither win nor tie: stop.  (An agreeing majority ends the loop after one class.)
                 if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;
-                const int i = ffs_mask(live) - 1;
-                const int32_t c = plane[i * T + tid];
+                const int pick = first_pick >= 0 ? first_pick : ffs_mask(live) - 1;
+                first_pick = -1;
+                const int32_t c = plane[pick * T + tid];
                 M eq = 0;
                 float cw = 0.0f;
 #pragma unroll
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
                     eq |= e ? (M(1) << j) : M(0);
                     cw = e ? __fadd_rn(cw, w[j]) : cw;
                 }
+                const int i = ffs_mask(eq) - 1;  // the class's first cell
                 if (cw > best_w) {
                     best_w = cw;
                     best_idx = i;
@@ -331,6 +342,11 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
                     tie = false;
                 } else if (cw == best_w) {
                     tie = true;
+                    if (i < best_idx) {  // an equally heavy class that was seen earlier
+                        best_idx = i;
+                        best_cnt = popc_m(eq);
+                        best_code = c;
+                    }
                 }
                 consumed = __fadd_rn(consumed, cw);
                 live &= ~eq;

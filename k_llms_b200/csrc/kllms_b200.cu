@@ -647,7 +647,7 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
     if (per_record && n >= 8) {  // weights once per record, codes in a shared-memory plane
         const int max_recs = threads / n_fields + 2;
         auto launch = [&](auto kernel, int NP) -> int {
-            const size_t smem = (size_t)max_recs * NP * 4 + (size_t)NP * threads * 4;
+            const size_t smem = (size_t)max_recs * NP * 4 + (size_t)max_recs * 4 + (size_t)NP * threads * 4;
             KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
