@@ -352,14 +352,17 @@ def test_weighted_vote_per_record_kernel(n, fields):
     rng = np.random.default_rng(n * 1000 + fields)
     R = max(2, 30000 // fields)
     codes = random_codes(rng, R * fields, n, 5, p_absent=0.05).reshape(R, fields, n)
-    seq = (-rng.exponential(20.0, (R, n))).astype(np.float32)
     none_code = rng.choice([-1, 0, 3], fields).astype(np.int32)
-    for nc in (None, none_code):
-        win, meta, wt = K.weighted_vote(torch.from_numpy(codes).cuda(), torch.from_numpy(seq).cuda(),
-                                        torch.from_numpy(nc).cuda() if nc is not None else None)
-        ew, em, ewt = OC.weighted_vote(codes, seq, nc)
-        assert np.array_equal(win.cpu().numpy(), ew) and np.array_equal(meta.cpu().numpy().view(np.uint32), em)
-        assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
+    # skewed weights; then weights from a two-value set (equal class weights are common: ties, first-seen rule, and the
+    # heaviest candidate is rarely in the first-seen class)
+    for seq in ((-rng.exponential(20.0, (R, n))).astype(np.float32), rng.choice([-1.0, -1.0, -2.0], (R, n)).astype(np.float32),
+                np.zeros((R, n), dtype=np.float32)):
+        for nc in (None, none_code):
+            win, meta, wt = K.weighted_vote(torch.from_numpy(codes).cuda(), torch.from_numpy(seq).cuda(),
+                                            torch.from_numpy(nc).cuda() if nc is not None else None)
+            ew, em, ewt = OC.weighted_vote(codes, seq, nc)
+            assert np.array_equal(win.cpu().numpy(), ew) and np.array_equal(meta.cpu().numpy().view(np.uint32), em)
+            assert np.array_equal(wt.cpu().numpy().view(np.uint32), ewt.view(np.uint32))
 
 
 @pytest.mark.parametrize("n", [3, 4, 8, 16, 32, 64])
