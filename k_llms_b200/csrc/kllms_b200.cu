@@ -444,15 +444,7 @@ static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, 
         case 2: return launch_vote_direct<2, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         case 4: return launch_vote_direct<4, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         case 8: return launch_vote_tma<8, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-        case 16: {
-            static const int cfg = [] { const char *e = getenv("KC_VOTE_CFG"); return e ? atoi(e) : 0; }();
-            if (cfg == 1) return launch_vote_tma<16, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-            if (cfg == 2) return launch_vote_tma<16, 4, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-            if (cfg == 3) return launch_vote_tma<16, 16, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-            if (cfg == 4) return launch_vote_tma<16, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-            if (cfg == 5) return launch_vote_tma<16, 8, 8>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-            return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
-        }
+        case 16: return launch_vote_tma<16, 8, 4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);  // KC_FORCE_TMA only
         case 32: return launch_vote_tma<32, 8, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         case 64: return launch_vote_tma<64, 4, 2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st, mc);
         default: break;
@@ -532,33 +524,11 @@ static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n,
         switch (n) {
             case 4: return launch_numeric_tma<4, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 8: return launch_numeric_tma<8, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-            case 16: {
-                static const int cfg = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
-                if (numeric_fast) {
-                    if (cfg == 11) return launch_numeric_tma_fast<16, 4, 1, 5>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                    if (cfg == 12) return launch_numeric_tma_fast<16, 4, 2, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                    if (cfg == 13) return launch_numeric_tma_fast<16, 8, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                    return launch_numeric_tma_fast<16, 4, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                }
-                if (cfg == 1) return launch_numeric_tma<16, 8, 2, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 2) return launch_numeric_tma<16, 8, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 3) return launch_numeric_tma<16, 4, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 4) return launch_numeric_tma<16, 2, 2>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 5) return launch_numeric_tma<16, 4, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 6) return launch_numeric_tma<16, 8, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 7) return launch_numeric_tma<16, 2, 1>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 8) return launch_numeric_tma<16, 8, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 9) return launch_numeric_tma<16, 4, 1, 8>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                if (cfg == 10) return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
+            case 16:
+                if (numeric_fast) return launch_numeric_tma_fast<16, 4, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                 return launch_numeric_tma<16, 4, 1, 7>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-            }
             case 32:
-                if (numeric_fast) {
-                    static const int cfg32 = [] { const char *e = getenv("KC_NUM_CFG"); return e ? atoi(e) : 0; }();
-                    if (cfg32 == 21) return launch_numeric_tma_fast<32, 4, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                    if (cfg32 == 22) return launch_numeric_tma_fast<32, 2, 1, 6>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                    return launch_numeric_tma_fast<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
-                }
+                if (numeric_fast) return launch_numeric_tma_fast<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
                 return launch_numeric_tma<32, 4, 1, 4>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             case 64: return launch_numeric_tma<64, 2, 1, 3>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta, st, mc);
             default: break;
@@ -614,10 +584,8 @@ int kc_logprob_sum_f32(const float *d_logprobs, const int64_t *d_offsets, int64_
     if (rc) return rc;
     static const bool staged = [] { const char *e = getenv("KC_K3_STAGED"); return !e || e[0] != '0'; }();
     if (staged && n_seq >= 4096 && aligned16(d_logprobs)) {
-        static const int k3cfg = [] { const char *e = getenv("KC_K3_CFG"); return e ? atoi(e) : 0; }();
-        if (k3cfg == 1) return launch_logprob_tile<128, 12 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
-        if (k3cfg == 2) return launch_logprob_tile<64, 4 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
-        if (k3cfg == 3) return launch_logprob_tile<32, 3 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
+        // 64 sequences per tile, 24 KB of staged tokens: measured best of {128/48 KB, 64/24 KB, 64/16 KB}; 32/12 KB is 3 % faster
+        // on config 4 but falls back from 96 tokens per sequence on
         return launch_logprob_tile<64, 6 * 1024>(d_logprobs, d_offsets, n_seq, d_sum, info, stream);
     }
     const int threads = 256;  // 8 warps, one sequence per warp per iteration
