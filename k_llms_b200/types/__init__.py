@@ -1,4 +1,4 @@
-from .completions import KLLMsChatCompletion
-from .parsed import KLLMsParsedChatCompletion
+"""Result types of the KLLMs client surface."""
+from ._models import KLLMsChatCompletion, KLLMsParsedChatCompletion
 
-__all__ = ["KLLMsParsedChatCompletion", "KLLMsChatCompletion"]
+__all__ = ["KLLMsChatCompletion", "KLLMsParsedChatCompletion"]
