@@ -144,28 +144,42 @@ struct Scanner {
         }
         return false;
     }
-    bool skip_nested() {  // at '{' or '[': skip a balanced value
-        int depth = 0;
-        while (p < end) {
-            const char c = *p;
-            if (c == '"') {
+    // at '{' or '[': validate the nested value exactly as json.loads would (a malformed inner value makes the WHOLE candidate
+    // text invalid JSON, which the caller then treats as free text, consolidation.py:25-38) and skip it
+    bool skip_nested(int depth = 0) {
+        if (depth > 200) return false;
+        const char open = *p++;
+        const char close = open == '{' ? '}' : ']';
+        ws();
+        if (p < end && *p == close) {
+            ++p;
+            return true;
+        }
+        for (;;) {
+            ws();
+            if (open == '{') {
+                if (p >= end || *p != '"') return false;
                 const char *sp;
                 uint32_t sl;
                 bool esc;
                 if (!string(sp, sl, esc)) return false;
+                ws();
+                if (p >= end || *p != ':') return false;
+                ++p;
+            }
+            Tok inner;
+            if (!value(inner, depth + 1)) return false;
+            ws();
+            if (p < end && *p == ',') {
+                ++p;
                 continue;
             }
-            if (c == '{' || c == '[') ++depth;
-            if (c == '}' || c == ']') {
-                --depth;
-                if (depth == 0) {
-                    ++p;
-                    return true;
-                }
+            if (p < end && *p == close) {
+                ++p;
+                return true;
             }
-            ++p;
+            return false;
         }
-        return false;
     }
     bool number(Tok &t) {
         const char *s = p;
@@ -207,7 +221,7 @@ struct Scanner {
         }
         return true;
     }
-    bool value(Tok &t) {
+    bool value(Tok &t, int depth = 0) {
         ws();
         if (p >= end) return false;
         const char c = *p;
@@ -217,7 +231,10 @@ struct Scanner {
         }
         if (c == '{' || c == '[') {
             t.type = T_NESTED;
-            return skip_nested();
+            t.p = p;
+            const bool ok = skip_nested(depth);
+            t.len = (uint32_t)(p - t.p);
+            return ok;
         }
         if (c == 't' && lit("true", 4)) { t.type = T_TRUE; return true; }
         if (c == 'f' && lit("false", 5)) { t.type = T_FALSE; return true; }
@@ -435,8 +452,16 @@ struct Group {
     uint32_t m_count = 0;
 };
 
+// Shape of the consensus object: a dict node lists its children (sorted keys), a leaf points at its group.
+struct Node {
+    std::string_view key;
+    int32_t group = -1;        // >= 0: leaf
+    std::vector<int32_t> kids; // dict: indices into Record::nodes
+};
+
 struct Record {
     uint8_t status = 0;        // 0 native, 1 needs the Python path
+    std::vector<Node> nodes;   // nodes[0] is the root dict
     std::vector<Group> groups;
     std::vector<Tok> cells;    // groups.size() * n tokens, group-major (T_MISSING / T_NULL count as None)
     std::string mchars;        // normalize_string() of the cells of the medoid groups, back to back
@@ -445,10 +470,174 @@ struct Record {
 
 const double kF64None = [] { const uint64_t b = KC_F64_NONE_BITS; double d; memcpy(&d, &b, 8); return d; }();
 
+// Scalar field: which kernel decides it (cu:1405-1411 vote, cu:1443-1453 numeric / medoid).  False: Python path.
+bool plan_leaf(Record &rec, Group &g, const Tok *cells, int n, std::string &tmp) {
+    const Tok *first = nullptr;
+    for (int c = 0; c < n && !first; ++c)
+        if (cells[c].type > T_NULL) first = &cells[c];
+    if (!first) {
+        g.kind = G_ALLNULL;
+    } else if (first->type == T_NESTED) {
+        rec.status = 1;
+        return false;
+    } else if (first->type == T_STR || first->type == T_TRUE || first->type == T_FALSE) {
+        bool multi_word = false, all_str = true;
+        int live = 0;
+        for (int c = 0; c < n; ++c) {
+            const Tok &t = cells[c];
+            if (t.type <= T_NULL) continue;
+            ++live;
+            if (t.type == T_NESTED) {  // str(dict) is almost never enum-like: leave it to Python
+                rec.status = 1;
+                return false;
+            }
+            all_str &= t.type == T_STR;
+            if (t.type == T_STR) {  // numbers and bools print as one word
+                tmp.clear();
+                py_str(t, tmp);
+                multi_word |= word_count(tmp) >= 3;
+            }
+        }
+        if (multi_word) {
+            // Not enum-like (cu:1405): the similarity medoid of consensus_as_primitive (cu:1221-1237).  K4 takes it when
+            // every pair is a Levenshtein pair inside its contract (same rule as columnar.Plan._medoid_on_device under
+            // the default string_similarity_method "embeddings"); anything else goes to the Python path.
+            if (!all_str) {
+                rec.status = 1;
+                return false;
+            }
+            g.kind = G_MEDOID;
+            g.m_first = (uint32_t)rec.mlen.size();
+            g.m_count = (uint32_t)live;
+            if (live >= 2) {
+                int long_raw = 0, long_norm = 0;
+                thread_local std::string norm;
+                for (int c = 0; c < n; ++c) {
+                    const Tok &t = cells[c];
+                    if (t.type != T_STR) continue;
+                    tmp.clear();
+                    py_str(t, tmp);
+                    sanitize(tmp, norm);  // == normalize_string (cu:660-673) on ASCII text
+                    long_raw += tmp.size() > 50;
+                    long_norm += norm.size() > 64;
+                    if (norm.size() > 2000 || long_raw > 1 || long_norm > 1) {
+                        rec.status = 1;
+                        return false;
+                    }
+                    rec.mchars += norm;
+                    rec.mlen.push_back((int32_t)norm.size());
+                }
+            }
+            return true;
+        }
+        if (first->type == T_STR) {
+            g.kind = G_VOTE_STR;
+        } else {
+            for (int c = 0; c < n; ++c)  // `v or False` on non-bool values compares Python objects: Python path
+                if (cells[c].type > T_FALSE) {
+                    rec.status = 1;
+                    return false;
+                }
+            g.kind = G_VOTE_BOOL;
+        }
+    } else {
+        g.kind = G_NUMERIC;
+    }
+    return true;
+}
+
+constexpr int kMaxDepth = 16;
+
+// One dict level of the alignment pre-pass + dispatcher (cu:516-548 then cu:1414-1426): `items[c]` is candidate c's
+// (key-sorted) dict at this node, or nullptr where it has none — the pre-pass turns None into a dict of Nones, so after
+// it EVERY candidate is a dict here and parent_valid_frac stays 1.  Keys are visited in sorted order; a key whose values
+// are all objects recurses, any list (or a mix of objects and scalars) sends the record to the Python path.
+struct LevelScratch {  // per recursion depth, reused across records (no allocation in the steady state)
+    std::vector<std::string_view> keys;
+    std::vector<size_t> cursor;
+    std::vector<Tok> cells;
+    std::vector<std::vector<Item>> child_items;
+    std::vector<const std::vector<Item> *> child;
+};
+
+void plan_dict(Record &rec, int32_t node, const std::vector<Item> *const *items, int n, int depth) {
+    thread_local std::vector<LevelScratch> levels(kMaxDepth + 1);  // sized once: references stay valid through the recursion
+    thread_local std::string tmp;
+    LevelScratch &L = levels[(size_t)depth];
+    std::vector<std::string_view> &keys = L.keys;
+    keys.clear();
+    for (int c = 0; c < n; ++c)
+        if (items[c])
+            for (auto &it : *items[c]) keys.push_back(it.key);
+    std::sort(keys.begin(), keys.end());  // code-point order == byte order for ASCII (consensus_utils.py:521-522)
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    std::vector<size_t> &cursor = L.cursor;
+    cursor.assign((size_t)n, 0);
+    std::vector<Tok> &cells = L.cells;
+    cells.resize((size_t)n);
+    for (size_t ki = 0; ki < keys.size(); ++ki) {
+        const std::string_view key = keys[ki];
+        for (int c = 0; c < n; ++c) {  // merge: both sides are sorted by key; of duplicates the last one wins
+            cells[(size_t)c] = Tok();
+            if (!items[c]) continue;
+            const auto &its = *items[c];
+            size_t &k = cursor[(size_t)c];
+            while (k < its.size() && its[k].key == key) cells[(size_t)c] = its[k++].tok;
+        }
+        if (key.find("reasoning___") != std::string_view::npos || key.find("source___") != std::string_view::npos) continue;  // cu:1292
+        const Tok *first = nullptr;
+        for (int c = 0; c < n && !first; ++c)
+            if (cells[(size_t)c].type > T_NULL) first = &cells[(size_t)c];
+        if (first && first->type == T_NESTED) {
+            if (*first->p != '{' || depth + 1 >= kMaxDepth) {  // lists need the alignment of cu:185-430: Python path
+                rec.status = 1;
+                return;
+            }
+            auto &child_items = L.child_items;
+            if ((int)child_items.size() < n) child_items.resize((size_t)n);
+            auto &child = L.child;
+            child.assign((size_t)n, nullptr);
+            for (int c = 0; c < n; ++c) {
+                const Tok &t = cells[(size_t)c];
+                if (t.type <= T_NULL) continue;
+                if (t.type != T_NESTED || *t.p != '{') {  // not all of one type: the pre-pass leaves the values alone (cu:507-512)
+                    rec.status = 1;
+                    return;
+                }
+                bool not_object = false, non_ascii = false, odd = false;
+                if (!parse_object(t.p, t.len, child_items[(size_t)c], not_object, non_ascii, odd) || not_object || non_ascii || odd) {
+                    rec.status = 1;
+                    return;
+                }
+                std::stable_sort(child_items[(size_t)c].begin(), child_items[(size_t)c].end(),
+                                 [](const Item &a, const Item &b) { return a.key < b.key; });
+                child[(size_t)c] = &child_items[(size_t)c];
+            }
+            const int32_t kid = (int32_t)rec.nodes.size();
+            rec.nodes.emplace_back();
+            rec.nodes[(size_t)kid].key = key;
+            rec.nodes[(size_t)node].kids.push_back(kid);
+            plan_dict(rec, kid, child.data(), n, depth + 1);
+            if (rec.status) return;
+            continue;
+        }
+        const size_t base = rec.cells.size();
+        rec.cells.insert(rec.cells.end(), cells.begin(), cells.end());
+        const Tok *gcells = &rec.cells[base];
+        Group g;
+        g.key = key;
+        if (!plan_leaf(rec, g, gcells, n, tmp)) return;
+        const int32_t kid = (int32_t)rec.nodes.size();
+        rec.nodes.emplace_back();
+        rec.nodes[(size_t)kid].key = key;
+        rec.nodes[(size_t)kid].group = (int32_t)rec.groups.size();
+        rec.nodes[(size_t)node].kids.push_back(kid);
+        rec.groups.push_back(g);
+    }
+}
+
 void plan_record(const char *const *texts, const int64_t *lens, int n, Record &rec) {
     thread_local std::vector<std::vector<Item>> cands;
-    thread_local std::vector<std::string_view> keys;
-    thread_local std::string tmp;
     if ((int)cands.size() < n) cands.resize((size_t)n);
     static const char kTextKey[] = "text";
     for (int c = 0; c < n; ++c) {
@@ -480,106 +669,16 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
         // sort by key; of duplicates the LAST one in the text wins (dict construction)
         std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.key < b.key; });
     }
-    keys.clear();
-    for (int c = 0; c < n; ++c)
-        for (auto &it : cands[(size_t)c]) keys.push_back(it.key);
-    std::sort(keys.begin(), keys.end());  // code-point order == byte order for ASCII (consensus_utils.py:521-522)
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     rec.groups.clear();
     rec.cells.clear();
     rec.mchars.clear();
     rec.mlen.clear();
-    rec.cells.reserve(keys.size() * (size_t)n);
-    std::vector<size_t> cursor((size_t)n, 0);
-    for (auto &key : keys) {
-        const size_t base = rec.cells.size();
-        rec.cells.resize(base + (size_t)n);
-        for (int c = 0; c < n; ++c) {  // merge: both sides are sorted by key
-            auto &items = cands[(size_t)c];
-            size_t &k = cursor[(size_t)c];
-            while (k < items.size() && items[k].key == key) rec.cells[base + (size_t)c] = items[k++].tok;
-        }
-        if (key.find("reasoning___") != std::string_view::npos || key.find("source___") != std::string_view::npos) {  // cu:1292
-            rec.cells.resize(base);
-            continue;
-        }
-        Group g;
-        g.key = key;
-        const Tok *cells = &rec.cells[base];
-        const Tok *first = nullptr;
-        for (int c = 0; c < n && !first; ++c)
-            if (cells[c].type > T_NULL) first = &cells[c];
-        if (!first) {
-            g.kind = G_ALLNULL;
-        } else if (first->type == T_NESTED) {
-            rec.status = 1;
-            return;
-        } else if (first->type == T_STR || first->type == T_TRUE || first->type == T_FALSE) {
-            bool multi_word = false, all_str = true;
-            int live = 0;
-            for (int c = 0; c < n; ++c) {
-                const Tok &t = cells[c];
-                if (t.type <= T_NULL) continue;
-                ++live;
-                if (t.type == T_NESTED) {  // str(dict) is almost never enum-like: leave it to Python
-                    rec.status = 1;
-                    return;
-                }
-                all_str &= t.type == T_STR;
-                if (t.type == T_STR) {  // numbers and bools print as one word
-                    tmp.clear();
-                    py_str(t, tmp);
-                    multi_word |= word_count(tmp) >= 3;
-                }
-            }
-            if (multi_word) {
-                // Not enum-like (cu:1405): the similarity medoid of consensus_as_primitive (cu:1221-1237).  K4 takes it when
-                // every pair is a Levenshtein pair inside its contract (same rule as columnar.Plan._medoid_on_device under
-                // the default string_similarity_method "embeddings"); anything else goes to the Python path.
-                if (!all_str) {
-                    rec.status = 1;
-                    return;
-                }
-                g.kind = G_MEDOID;
-                g.m_first = (uint32_t)rec.mlen.size();
-                g.m_count = (uint32_t)live;
-                if (live >= 2) {
-                    int long_raw = 0, long_norm = 0;
-                    thread_local std::string norm;
-                    for (int c = 0; c < n; ++c) {
-                        const Tok &t = cells[c];
-                        if (t.type != T_STR) continue;
-                        tmp.clear();
-                        py_str(t, tmp);
-                        sanitize(tmp, norm);  // == normalize_string (cu:660-673) on ASCII text
-                        long_raw += tmp.size() > 50;
-                        long_norm += norm.size() > 64;
-                        if (norm.size() > 2000 || long_raw > 1 || long_norm > 1) {
-                            rec.status = 1;
-                            return;
-                        }
-                        rec.mchars += norm;
-                        rec.mlen.push_back((int32_t)norm.size());
-                    }
-                }
-                rec.groups.push_back(g);
-                continue;
-            }
-            if (first->type == T_STR) {
-                g.kind = G_VOTE_STR;
-            } else {
-                for (int c = 0; c < n; ++c)  // `v or False` on non-bool values compares Python objects: Python path
-                    if (cells[c].type > T_FALSE) {
-                        rec.status = 1;
-                        return;
-                    }
-                g.kind = G_VOTE_BOOL;
-            }
-        } else {
-            g.kind = G_NUMERIC;
-        }
-        rec.groups.push_back(g);
-    }
+    rec.nodes.clear();
+    rec.nodes.emplace_back();
+    thread_local std::vector<const std::vector<Item> *> top;
+    top.assign((size_t)n, nullptr);
+    for (int c = 0; c < n; ++c) top[(size_t)c] = &cands[(size_t)c];
+    plan_dict(rec, 0, top.data(), n, 0);
 }
 
 void encode_vote(GroupKind kind, const Tok *toks, int n, int8_t *cells) {
@@ -639,24 +738,25 @@ double py_round5(double x) {
     return (double)(uint64_t)q / 100000.0;
 }
 
-void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, const int32_t *midx,
-                 const double *mavg, std::string &content, std::string &lik) {
-    content = "{";
-    lik = "{";
-    bool first = true;
-    const Tok *single_text = nullptr;
-    for (size_t gi = 0; gi < rec.groups.size(); ++gi) {
-        const Group &g = rec.groups[gi];
-        const Tok *cells = &rec.cells[gi * (size_t)n];
-        if (!first) {
-            content += ", ";
-            lik += ", ";
-        }
-        first = false;
-        json_string(g.key, content);
-        json_string(g.key, lik);
-        content += ": ";
-        lik += ": ";
+struct EmitCtx {
+    const Record &rec;
+    int n;
+    const uint32_t *vmeta;
+    const double *nvalue;
+    const uint32_t *nmeta;
+    const int32_t *midx;
+    const double *mavg;
+};
+
+// value and confidence of one leaf group (the epilogue of cu:971-982, cu:1085-1086, cu:1116, cu:1177-1219, cu:1233-1237)
+void emit_leaf(const EmitCtx &cx, size_t gi, std::string &content, std::string &lik) {
+    const Record &rec = cx.rec;
+    const int n = cx.n;
+    const uint32_t *vmeta = cx.vmeta, *nmeta = cx.nmeta;
+    const double *nvalue = cx.nvalue, *mavg = cx.mavg;
+    const int32_t *midx = cx.midx;
+    const Group &g = rec.groups[gi];
+    const Tok *cells = &rec.cells[gi * (size_t)n];
         double conf = 0.0;
         Tok value;  // T_MISSING == None
         if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) {
@@ -701,11 +801,61 @@ void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *
         }  // G_ALLNULL: None, 0.0 (cu:1401-1402)
         json_value(value, content);
         json_float(conf, lik);
-        if (rec.groups.size() == 1 && g.key == "text" && value.type == T_STR) single_text = &cells[KC_META_IDX(vmeta[g.row])];
+}
+
+void emit_node(const EmitCtx &cx, int32_t ni, std::string &content, std::string &lik) {
+    const Node &node = cx.rec.nodes[(size_t)ni];
+    if (node.group >= 0) {
+        emit_leaf(cx, (size_t)node.group, content, lik);
+        return;
+    }
+    content += "{";
+    lik += "{";
+    bool first = true;
+    for (int32_t kid : node.kids) {
+        if (!first) {
+            content += ", ";
+            lik += ", ";
+        }
+        first = false;
+        const std::string_view key = cx.rec.nodes[(size_t)kid].key;
+        json_string(key, content);
+        json_string(key, lik);
+        content += ": ";
+        lik += ": ";
+        emit_node(cx, kid, content, lik);
     }
     content += "}";
     lik += "}";
-    if (single_text) tok_string(*single_text, content);  // {"text": s} -> s (consolidation.py:55-57)
+}
+
+void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, const int32_t *midx,
+                 const double *mavg, std::string &content, std::string &lik) {
+    const EmitCtx cx{rec, n, vmeta, nvalue, nmeta, midx, mavg};
+    content.clear();
+    lik.clear();
+    emit_node(cx, 0, content, lik);
+    // {"text": s} -> s (consolidation.py:55-57): a single top-level string field called "text"
+    const Node &root = rec.nodes[0];
+    if (root.kids.size() == 1) {
+        const Node &only = rec.nodes[(size_t)root.kids[0]];
+        if (only.group >= 0 && only.key == "text") {
+            const Group &g = rec.groups[(size_t)only.group];
+            const Tok *cells = &rec.cells[(size_t)only.group * (size_t)n];
+            const Tok *picked = nullptr;
+            if (g.kind == G_VOTE_STR) {
+                picked = &cells[KC_META_IDX(vmeta[g.row])];
+            } else if (g.kind == G_MEDOID) {
+                int want = g.m_count >= 2 ? midx[g.row] : 0;
+                for (int c = 0; c < n && !picked; ++c)
+                    if (cells[c].type > T_NULL && want-- == 0) picked = &cells[c];
+            }
+            if (picked && picked->type == T_STR) {
+                content.clear();
+                tok_string(*picked, content);
+            }
+        }
+    }
 }
 
 char *dup_string(const std::string &s) {

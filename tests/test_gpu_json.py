@@ -75,6 +75,80 @@ def _random_record(rng, n):
     return texts
 
 
+def _random_nested_record(rng, n, depth=0):
+    """Candidates sharing a schema of nested objects (no lists): missing / null sub-objects, empty objects, leaf fields of
+    every kind, and now and then a candidate whose sub-object is a scalar or a list (the native path must decline those)."""
+    def schema(d):
+        out = {}
+        for f in range(rng.randrange(1, 5)):
+            r = rng.random()
+            if d < 3 and r < 0.35:
+                out[f"o{f}"] = schema(d + 1)
+            else:
+                out[f"k{f}"] = rng.choice(["str", "bool", "int", "float", "phrase"])
+        return out
+
+    def truth_of(sc):
+        return {k: (truth_of(v) if isinstance(v, dict) else
+                    {"str": lambda: rng.choice(WORDS), "bool": lambda: rng.random() < 0.5, "int": lambda: rng.randrange(0, 500),
+                     "float": lambda: round(rng.uniform(0, 100), 2), "phrase": lambda: _phrase(rng)}[v]()) for k, v in sc.items()}
+
+    def noisy(sc, tr):
+        out = {}
+        for k, v in sc.items():
+            r = rng.random()
+            if r < 0.07:
+                continue
+            if r < 0.12:
+                out[k] = None
+                continue
+            if isinstance(v, dict):
+                out[k] = {} if rng.random() < 0.05 else noisy(v, tr[k])
+            elif rng.random() < 0.25:
+                out[k] = {"str": lambda: rng.choice(WORDS).upper(), "bool": lambda: rng.random() < 0.5, "int": lambda: rng.randrange(0, 500),
+                          "float": lambda: round(rng.uniform(0, 100), 2), "phrase": lambda: _phrase_variant(rng, tr[k])}[v]()
+            else:
+                out[k] = tr[k]
+        return out
+
+    sc = schema(0)
+    tr = truth_of(sc)
+    return [json.dumps(noisy(sc, tr)) for _ in range(n)]
+
+
+def test_native_json_nested_objects():
+    """Nested objects (no lists) stay on the native path: sorted keys and None fill at every level, nested output."""
+    from k_llms_b200 import _native as K
+    rng = random.Random(77)
+    by_n = {}
+    for _ in range(1500):
+        n = rng.choice([2, 3, 5, 8])
+        by_n.setdefault(n, []).append(_random_nested_record(rng, n))
+    specials = [
+        ['{"a": {"b": 1, "c": {"d": "x"}}}', '{"a": {"b": 1, "c": {"d": "X!"}}}', '{"a": null}'],
+        ['{"a": {}}', '{"a": {}}'], ['{"a": {"b": {}}}', '{"a": {}}', '{}'],
+        ['{"a": {"b": 1}, "a": {"b": 2}}', '{"a": {"b": 2}}'],                       # duplicate key: the last object wins
+        ['{"a": {"reasoning___x": {"deep": [1, 2]}, "v": 3}}', '{"a": {"v": 3}}'],     # skipped key holding a list
+        ['{"a": {"b": tru}}', '{"a": {"b": true}}', '{"a": {"b": true}}'],            # malformed inner value: whole text is free text
+        ['{"text": {"text": "x"}}', '{"text": {"text": "x"}}'],
+    ]
+    for sp in specials:
+        by_n.setdefault(len(sp), []).append(sp)
+    native = nested_native = 0
+    for n, recs in by_n.items():
+        out = K.consolidate_json(recs)
+        for texts, got in zip(recs, out):
+            if got is None:
+                continue
+            native += 1
+            nested_native += '": {' in got[0]
+            exp = _expected(texts)
+            assert got[0] == exp[0] and got[1] == exp[1], (texts, got, exp)
+    assert native > 1200 and nested_native > 600
+    declined = [['{"a": {"b": 1}}', '{"a": 5}'], ['{"a": {"b": [1]}}', '{"a": {"b": [1]}}'], ['{"a": [{"b": 1}]}', '{"a": [{"b": 1}]}']]
+    assert K.consolidate_json(declined) == [None] * len(declined)
+
+
 def test_native_json_matches_reference_client_order():
     from k_llms_b200 import _native as K
     rng = random.Random(2024)
@@ -118,7 +192,7 @@ def test_native_json_matches_reference_client_order():
 def test_native_json_declines_what_it_cannot_express():
     from k_llms_b200 import _native as K
     long1, long2 = " ".join(["payment"] * 9), " ".join(["transfer"] * 8)
-    recs = [['{"a": {"b": 1}}', '{"a": {"b": 1}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": 7}'],
+    recs = [['{"a": {"b": [1]}}', '{"a": {"b": [1]}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": 7}'],
             [json.dumps({"a": long1}), json.dumps({"a": long2})],  # two strings > 50 chars: an embeddings pair
             ['{"a": "caf\\u00e9"}', '{"a": "cafe"}'], ['[1, 2]', '{"a": 1}'], ['', '{"a": 1}'], ['{"a": true}', '{"a": 1}']]
     assert K.consolidate_json(recs) == [None] * len(recs)
