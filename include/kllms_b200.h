@@ -204,7 +204,7 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
                          float *device_ms);
 
 /*
- * H1 — native columnariser / decoder for FLAT records: for each record, n candidate JSON texts in ->
+ * H1 — native columnariser / decoder for records of scalars and nested objects: for each record, n candidate JSON texts in ->
  * consensus JSON text + likelihoods JSON text out, multi-threaded on the host with K1/K2 in between.  Replaces, for such
  * records, the Python around the hot path: _safe_parse_content (consolidation.py:25-38), the dict part of
  * recursive_list_alignments (consensus_utils.py:516-548: keys sorted, missing -> None), the dispatcher
@@ -212,7 +212,7 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
  *   texts   [n_records * n] candidate contents (record-major); lens [n_records * n] byte lengths or NULL (NUL-terminated)
  *   out_content / out_likelihoods [n_records] malloc'ed NUL-terminated strings (free with kc_free_strings), byte-identical
  *           to the reference's json.dumps output; out_status [n_records]: 0 = consolidated here, 1 = not expressible as
- *           scalar groups (nested values, multi-word strings, non-ASCII, empty content, ...) -> caller uses the Python path
+ *           groups for K1/K2/K4 (lists, a key mixing objects and scalars, non-ASCII, empty content, ...) -> caller uses the Python path
  *   threads <= 0: min(32, hardware threads).  Blocks until done; callers are serialised (one staging pool per process).
  */
 int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, double rel_eps,

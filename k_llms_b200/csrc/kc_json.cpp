@@ -5,11 +5,12 @@
 // Python around the hot path:
 //     _safe_parse_content            consolidation.py:25-38   (json.loads, or {"text": content})
 //     recursive_list_alignments      consensus_utils.py:516-548 (dict part: every candidate gets every key, keys SORTED)
-//     consensus_values dispatcher    consensus_utils.py:1376-1454 (flat records: scalar fields only)
+//     consensus_values dispatcher    consensus_utils.py:1376-1454 (scalar fields and nested objects)
 //     sanitize_value / `v or False`  consensus_utils.py:925-933, 956   -> local dictionary codes (int8 cells)
 //     _format_consensus_content      consolidation.py:41-60   (json.dumps of the consensus; {"text": s} -> s)
-// Records it cannot express as scalar groups (nested dicts / lists, multi-word strings that need the similarity medoid,
-// non-ASCII text, mixed-type bool groups) are NOT guessed at: they get status 1 and the Python path handles them.
+//     similarity medoid              consensus_utils.py:1221-1237 for multi-word string fields (batched into one K4 launch)
+// Records it cannot express (lists, a key mixing objects and scalars, string groups outside K4's contract, non-ASCII
+// text, mixed-type bool groups) are NOT guessed at: they get status 1 and the Python path handles them.
 //
 // Text formats follow CPython exactly: float -> float.__repr__ (shortest round-trip digits, exponent form outside
 // 1e-4 <= |x| < 1e16, always a fractional part), json.dumps separators ", " / ": " and ensure_ascii escaping.
