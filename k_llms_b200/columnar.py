@@ -11,8 +11,9 @@ instead of computing a scalar field it RECORDS it as a group:
 
 The shape of the result (dict keys in first-seen order cu:1281-1282, list lengths cu:1332-1341, the
 parent_valid_frac products cu:1418,1433,1444) depends only on the input structure, so it is fixed while
-planning; the GPU fills in the leaves.  Multi-word strings and mixed payloads (the similarity medoid,
-cu:1221-1237) are computed by `k_llms_b200.utils.similarity` on the host (next row).
+planning; the GPU fills in the leaves.  Multi-word string fields (the similarity medoid, cu:1221-1237) are recorded as
+medoid groups for K4 when every pair is a Levenshtein pair inside the kernel's contract (`Plan._medoid_on_device`);
+mixed payloads and the other similarity methods are computed by `k_llms_b200.utils.similarity` on the host.
 """
 from __future__ import annotations
 
@@ -104,7 +105,7 @@ class _ListNode:
 
 
 class Plan:
-    """Leaf groups of one or many records, ready for one K1 and one K2 launch."""
+    """Leaf groups of one or many records, ready for one K1, one K2 and one K4 launch."""
 
     def __init__(self, n: int, allow_none_as_candidate: bool, rel_eps: float, abs_eps: float, host_primitive: Callable):
         if n > MAX_CANDIDATES:
