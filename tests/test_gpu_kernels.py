@@ -108,6 +108,29 @@ def test_numeric_matches_oracle(n, style):
     assert not badv, (badv[:5], vals[badv[:1]], got_val[badv[:1]], exp_val[badv[:1]])
 
 
+@pytest.mark.parametrize("n", [4, 8, 16, 32])
+def test_kernels_tiny_and_ragged_group_counts(n):
+    """Group counts below / around one warp and one tile: partially filled warps in the queueing fast kernels and TMA
+    tiles that hang over the end of the input."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    rng = np.random.default_rng(n)
+    for G in (1, 2, 31, 32, 33, 127, 129, 1000):
+        vals = random_vals(rng, G, n, "ints")
+        vals[:, : n // 2 + 1] = vals[:, :1]  # a majority of identical cells in most groups: the fast path decides them
+        vals[rng.random((G, n)) < 0.05] = NONE
+        vals = np.ascontiguousarray(vals)
+        exp_val, exp_meta = OC.numeric(vals)
+        val, meta = K.numeric(torch.from_numpy(vals).cuda())
+        assert np.array_equal(meta.cpu().numpy().view(np.uint32), exp_meta), (n, G)
+        g_, e_ = val.cpu().numpy(), exp_val
+        assert ((g_.view(np.uint64) == e_.view(np.uint64)) | (np.isnan(g_) & np.isnan(e_))).all(), (n, G)
+        codes = random_codes(rng, G, n, 4)
+        ew, em = OC.vote(codes, None)
+        w, m = K.vote(torch.from_numpy(codes).cuda(), None)
+        assert np.array_equal(w.cpu().numpy(), ew) and np.array_equal(m.cpu().numpy().view(np.uint32), em), (n, G)
+
+
 def test_numeric_other_eps():
     torch = _torch()
     from k_llms_b200 import _native as K
