@@ -560,23 +560,27 @@ __device__ __forceinline__ bool numeric_fast_decide(const uint32_t (&x)[N], cons
     for (int k = 0; k < PLANES; ++k) nonfinite += (plane[k] >> 31) << k;
     // d = x - xv as a signed number: < 0 below v, > 0 above.  Unsigned max of d is the nearest cell below (if any is
     // below), unsigned min of d - 1 the nearest above.
-    uint32_t c = 0, bad = 0, below = 0, above = 0xFFFFFFFFu, none = 0, absent = 0;
+    // low_nf: the smallest non-finite x, as an offset from 2^31 (finite cells wrap to >= 2^31 and never win the min)
+    uint32_t c = 0, bad = 0, below = 0, above = 0xFFFFFFFFu, low_nf = 0xFFFFFFFFu, absent = 0;
     const uint32_t neg_xv = 0u - xv, neg_xv1 = ~xv;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         below = max(below, x[i] + neg_xv);
         above = min(above, x[i] + neg_xv1);
+        low_nf = min(low_nf, x[i] + 0x80000000u);
         match_cell(x[i], lo[i], xv, lv, c, bad);
-        count_equal(x[i], X_NONE, none);
     }
-    if (top == kAbsentHi) {  // ragged candidates (rare): count the absent cells too
+    if (top == kAbsentHi) {  // ragged candidates (rare): count the absent cells
 #pragma unroll
         for (int i = 0; i < N; ++i) count_equal(x[i], X_ABSENT, absent);
     }
-    const uint32_t tagged = none + absent;
+    // With no non-finite cell below the None tag (inf, a plain NaN: decided by the general path) and none above the absent
+    // tag (`top`), every non-finite cell is None or absent.
+    const uint32_t tagged = nonfinite;
     // a negative cell or an odd NaN / the guess is not a finite value / cells share v's high word only / no strict
-    // majority of the finite cells / a single non-None cell
-    if (top > kAbsentHi || (xv & 0x80000000u) != 0 || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2))
+    // majority of the finite cells / a single non-None cell / an untagged non-finite cell
+    if (top > kAbsentHi || (xv & 0x80000000u) != 0 || bad != 0 || 2 * c + nonfinite <= (uint32_t)N || tagged > (uint32_t)(N - 2) ||
+        (nonfinite != 0 && low_nf < X_NONE - 0x80000000u))
         return false;
     const uint32_t hv = xv - kFastBias;
     const double v = __hiloint2double((int)hv, (int)lv);
