@@ -511,9 +511,12 @@ __global__ void __launch_bounds__(T) numeric_direct_kernel(const double *__restr
 //      double sharing that high word.  They are certified far from v with
 //      fl() monotonicity alone: |v - x| >= fl(v - x_nearest_possible) and tol(x, v) <= max(abs, fl(rel * max(|x|_max,
 //      |v|, 1))) for rel >= 0 (the launcher rejects rel < 0);
-//   4. anything else — no majority, a neighbour within reach, a cell sharing v's high word, a single non-None cell —
-//      is NOT decided here: the caller queues the group for numeric_core (exact, general).
-// Returns true when (value, meta) are final.
+//   4. the cell census comes from the same adder tree (bit 31 of x = hi + 2^20 counts the non-finite cells) plus one
+//      min scan that proves every non-finite cell is a None / absent tag;
+//   5. anything else — no majority, a neighbour within reach, a cell sharing v's high word, a negative cell, an inf or
+//      an untagged NaN, a single non-None cell — is NOT decided here: the caller parks the group for numeric_core
+//      (exact, general).
+// numeric_fast_decide() returns true when the group is decided; numeric_fast_finish() then produces (value, meta).
 // n += (x == key), as a predicated add (the compiler prefers select + add)
 __device__ __forceinline__ void count_equal(uint32_t x, uint32_t key, uint32_t &n) {
     asm("{\n\t.reg .pred p;\n\t"
