@@ -18,6 +18,7 @@ mixed payloads and the other similarity methods are computed by `k_llms_b200.uti
 from __future__ import annotations
 
 import math
+import re
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -51,12 +52,15 @@ def _normalize(text: str) -> str:
     return "".join(ch for ch in text if ch.isascii() and ch.isalnum()).lower() if text else ""
 
 
+_NOT_ALNUM = re.compile(r"[^a-zA-Z0-9]")
+
+
 def sanitize_value(v: Any) -> str:
     """str() -> lower -> drop spaces -> unidecode -> keep [a-zA-Z0-9]  (cu:925-933)."""
     s = str(v).lower().replace(" ", "")
     if not s.isascii():
         s = _fold_non_ascii(s)
-    return "".join(ch for ch in s if ch.isascii() and ch.isalnum())
+    return _NOT_ALNUM.sub("", s)
 
 
 # ----------------------------------------------------------------------------- plan nodes
