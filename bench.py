@@ -216,7 +216,9 @@ def run_gpu_arm(args):
     N, n = args.records, args.n
     codes, none_code, vals = synth.s32_torch(N, n, 20260921 + 2 + rank, dev)  # §8d: seed 20260921 + cfg, per-rank shard
     c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
-    layout = OutputLayout(N, 24, 8)
+    # N > 1, fused P2P route: the gathered vote results travel packed (one word instead of two; full results stay local)
+    packed = world > 1 and args.results == "packed" and args.reassembly in ("auto", "fused") and args.route == "peers"
+    layout = OutputLayout(N, 24, 8, packed_votes=packed)
     # N > 1: reassembly is fused into the kernels (multimem.st through NVSwitch) when the multicast mapping exists,
     # else the pipelined NCCL all-gather (--reassembly nccl forces it).
     fused = None
@@ -230,6 +232,9 @@ def run_gpu_arm(args):
             fused = None
         if fused is None and args.reassembly == "fused":
             raise RuntimeError("--reassembly fused requested but no multicast mapping is available")
+    if fused is None and layout.packed_votes:  # the NCCL path gathers the full two-word vote results
+        packed = False
+        layout = OutputLayout(N, 24, 8)
     chunks = args.chunks if (world > 1 and fused is None) else 1  # NCCL path: pipeline depth of compute vs all-gather
     while N % chunks:
         chunks -= 1
@@ -309,6 +314,14 @@ def run_gpu_arm(args):
         gather_ms = max_over_ranks(g0.elapsed_time(g1) / 5)
     if fused is not None:
         win, vmeta, value, nmeta = fused.rank_views(rank)
+        if layout.packed_votes:
+            if fused.packed_overflowed():
+                raise RuntimeError("a winning code >= 2^18 cannot travel packed: rerun with --results full")
+            # the gathered words must be the packing of the full local results
+            lw, lm = fused.local_win, fused.local_vmeta
+            expect = (lw & 0x3FFFF) | (((lm >> 6) & 0x7F) << 18) | (((lm >> 20) & 0x7F) << 25)
+            assert torch.equal(win, expect), "packed gathered vote words differ from the local full results"
+            win = lw
     else:
         win, vmeta, value, nmeta = [torch.cat([sharded.my_views(c)[k] for c in range(chunks)]) for k in range(4)]
 
@@ -373,8 +386,11 @@ def run_gpu_arm(args):
                                        f"n={n}, p_agree=0.8, p_none=0.05; {world} GPU(s), {world * N} records total",
                            "l2": f"inputs are {(bytes_vote + bytes_num) / 1e9:.2f} GB per step per GPU, > 126 MB L2: no flush needed",
                            "step": "K1 vote + K2 numeric" + ("" if world == 1 else
-                                   (" with results multimem.st-replicated to every GPU through NVSwitch + one cross-GPU barrier"
-                                    if fused is not None else " + pipelined NCCL all-gather of packed outputs")),
+                                   ((" with every result also stored into the peers' copies (P2P over NVLink"
+                                     + (", vote results as one packed word: 192 B/record" if layout.packed_votes else ", 288 B/record")
+                                     + ") + one cross-GPU barrier" if fused.route == "peers" else
+                                     " with results multimem.st-replicated to every GPU through NVSwitch + one cross-GPU barrier")
+                                    if fused is not None else " + pipelined NCCL all-gather of the output columns")),
                            "parallelism": (f"records sharded {world}-way; reassembly "
                                            + ((f"fused into the kernels ({'P2P stores to the peers' if fused.route == 'peers' else 'NVSwitch multicast stores'})")
                                               if fused is not None else "NCCL all-gather"))
@@ -382,7 +398,8 @@ def run_gpu_arm(args):
                 "e2e": e2e, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
-                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else f"fused-{fused.route}" if fused is not None else "nccl"),
+                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
+                                                if fused is not None else "nccl"),
                                  "nvlink_floor_ms": (world - 1) * layout.nbytes / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
     if dist is not None:
@@ -423,6 +440,9 @@ def main():
     ap.add_argument("--e2e-cells", default="i8", choices=["i8", "i32"], help="host encoding of vote cells for the e2e leg")
     ap.add_argument("--chunks", type=int, default=8, help="N>1, NCCL reassembly: pipeline chunks of compute vs all-gather")
     ap.add_argument("--reassembly", default="auto", choices=["auto", "fused", "nccl"])
+    ap.add_argument("--results", default="packed", choices=["packed", "full"],
+                    help="N>1 with the fused P2P route: gathered vote results as one packed word (code:18|support:7|present:7, "
+                         "192 B/record over NVLink) or as the full two words (288 B/record)")
     ap.add_argument("--route", default="peers", choices=["peers", "multimem"],
                     help="fused reassembly: P2P stores to every peer's copy, or one multicast store through the switch")
     ap.add_argument("--cpu-records-per-core", type=int, default=1500)

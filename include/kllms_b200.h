@@ -139,6 +139,21 @@ int kc_numeric_f64_peers(const double *d_vals, int64_t n_groups, int32_t n, doub
                          uint32_t *d_meta, int32_t n_peers, const int64_t *peer_delta_bytes, void *stream);
 
 /*
+ * K1 with a PACKED gathered result.  The full result (d_win_code, d_meta: plain local arrays, not shared) stays on the
+ * owning GPU — its decoder needs the first-seen index in the result word — and one word per group,
+ *     KC_PACKED_VOTE: code:18 | support:7 | present:7      (support == 0: no value; confidence = support / present)
+ * goes to d_packed (a LOCAL address inside the shared buffer) and to d_packed + peer_delta_bytes[k] on every peer: 4 instead
+ * of 8 bytes per vote field cross NVLink, and the fused reassembly is NVLink-ingress-bound.  A winning code >= 2^18 cannot
+ * be packed: the kernel sets *d_overflow (device uint32, zeroed by the caller) and the caller repeats with kc_vote_i32_peers.
+ */
+#define KC_PACKED_CODE(w) ((uint32_t)(w) & 0x3FFFFu)
+#define KC_PACKED_SUPPORT(w) (((uint32_t)(w) >> 18) & 0x7Fu)
+#define KC_PACKED_PRESENT(w) (((uint32_t)(w) >> 25) & 0x7Fu)
+int kc_vote_i32_peers_packed(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                             int32_t *d_win_code, uint32_t *d_meta, uint32_t *d_packed, int32_t n_peers,
+                             const int64_t *peer_delta_bytes, uint32_t *d_overflow, void *stream);
+
+/*
  * Confidences from result words, bit-exact with Python's round(x, 5) (cu:982,1178,1187,1219):
  *   vote    (numeric == 0): round(pvf * (support / present), 5)          cu:973,982
  *   numeric (numeric == 1): round(support / nn, 5); SINGLE: pvf * (1/present) unrounded (cu:1086,1444)

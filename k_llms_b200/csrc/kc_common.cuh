@@ -133,10 +133,16 @@ __device__ __forceinline__ int4 ldg_nc_v4(const void *p) {
 //   PEERS     the addresses are local and lie in a buffer that n_peers other GPUs map as well (symmetric memory): one
 //             local store plus one store per peer at address + delta[k] (P2P over NVLink).  Each GPU receives only
 //             (world - 1) shares and sends as many: less ingress than multicast, the better trade on full-duplex links.
+//   PEERS_PACKED  (votes) the full result (winning code, result word) stays in LOCAL arrays — the owning rank's decoder
+//             needs the first-seen index in it — and ONE packed word code:18 | support:7 | present:7, everything a remote
+//             consumer needs for the value and its confidence, goes to `packed` (local + peers): 4 instead of 8 bytes per
+//             vote field over NVLink.  A winning code >= 2^18 sets *overflow (the caller then falls back to PEERS).
 struct OutRoute {
-    uint32_t mode;       // KC_OUT_LOCAL / KC_OUT_MULTIMEM / KC_OUT_PEERS
-    int32_t n_peers;     // PEERS only
+    uint32_t mode;       // KC_OUT_LOCAL / KC_OUT_MULTIMEM / KC_OUT_PEERS / 3 = PEERS_PACKED
+    int32_t n_peers;     // PEERS*, only
     long long delta[7];  // byte offsets local address -> the same address in peer k's mapping
+    uint32_t *packed;    // PEERS_PACKED: local address (inside the shared buffer) of the packed vote words
+    uint32_t *overflow;  // PEERS_PACKED: device flag
     __host__ __device__ bool local() const { return mode == 0; }
 };
 
@@ -162,15 +168,31 @@ __device__ __forceinline__ void store_out_u32(void *p, uint32_t v, const OutRout
         asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     } else {
         asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-        if (r.mode == 2u) store_peers_u32(p, v, r);
+        if (r.mode >= 2u) store_peers_u32(p, v, r);
     }
 }
+// K1's two result words of group g, routed
+__device__ __forceinline__ void store_vote_result(int32_t *win, uint32_t *meta, int64_t g, int32_t w, uint32_t m, const OutRoute &r) {
+    if (r.mode != 3u) {
+        store_out_u32(win + g, (uint32_t)w, r);
+        store_out_u32(meta + g, m, r);
+        return;
+    }
+    store_local_u32(win + g, (uint32_t)w);
+    store_local_u32(meta + g, m);
+    const uint32_t support = (m >> 6) & 0x7Fu, present = (m >> 20) & 0x7Fu;
+    if (support != 0 && (uint32_t)w >= (1u << 18)) atomicOr(r.overflow, 1u);
+    const uint32_t word = ((uint32_t)w & 0x3FFFFu) | (support << 18) | (present << 25);
+    store_local_u32(r.packed + g, word);
+    store_peers_u32(r.packed + g, word, r);
+}
+
 __device__ __forceinline__ void store_out_f64(void *p, double v, const OutRoute &r) {
     if (r.mode == 1u) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
     } else {
         asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-        if (r.mode == 2u) store_peers_f64(p, v, r);
+        if (r.mode >= 2u) store_peers_f64(p, v, r);
     }
 }
 

@@ -234,8 +234,7 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
         int32_t w;
         uint32_t m;
         vote_core<NP, HAS_NC>(raw, row_min<NP>(raw), nc, w, m);
-        store_out_u32(win + g, (uint32_t)w, mc);
-        store_out_u32(meta + g, m, mc);
+        store_vote_result(win, meta, g, w, m, mc);
         if constexpr (PREFETCH) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) raw[i] = nxt[i];
@@ -300,8 +299,7 @@ __global__ void __launch_bounds__(256) vote_i8_kernel(const int8_t *__restrict__
         int32_t w;
         uint32_t m;
         vote_core<NP, HAS_NC>(raw, row_min<NP>(raw), nc, w, m);
-        store_out_u32(win + g, (uint32_t)w, mc);
-        store_out_u32(meta + g, m, mc);
+        store_vote_result(win, meta, g, w, m, mc);
     }
 }
 
@@ -410,8 +408,7 @@ __global__ void __launch_bounds__(WARPS * 32) vote_tma_kernel(const __grid_const
             int32_t w;
             uint32_t m;
             vote_core<N, HAS_NC>(raw, lo, nc, w, m);
-            store_out_u32(win + g, (uint32_t)w, mc);
-            store_out_u32(meta + g, m, mc);
+            store_vote_result(win, meta, g, w, m, mc);
         }
     }
 }

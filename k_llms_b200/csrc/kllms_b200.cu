@@ -416,6 +416,19 @@ int kc_vote_i32_peers(const int32_t *d_codes, int64_t n_groups, int32_t n, const
     return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
 }
 
+int kc_vote_i32_peers_packed(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                             int32_t *d_win_code, uint32_t *d_meta, uint32_t *d_packed, int32_t n_peers,
+                             const int64_t *peer_delta_bytes, uint32_t *d_overflow, void *stream) {
+    if (!d_packed || !d_overflow) return fail(KC_EINVAL, "kc_vote_i32_peers_packed: NULL d_packed / d_overflow");
+    kc::OutRoute mc;
+    int rc = make_peer_route("kc_vote_i32_peers_packed", n_peers, peer_delta_bytes, mc);
+    if (rc) return rc;
+    mc.mode = 3u;
+    mc.packed = d_packed;
+    mc.overflow = d_overflow;
+    return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
+}
+
 static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
                            int32_t *d_win_code, uint32_t *d_meta, kc::OutRoute mc, void *stream) {
     if (n < 1 || n > KC_MAX_CANDIDATES) return fail(KC_EINVAL, "kc_vote_i32: n=%d outside [1,%d]", n, KC_MAX_CANDIDATES);

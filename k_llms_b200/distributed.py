@@ -23,6 +23,7 @@ class OutputLayout:
     n_records: int  # records per rank (equal on every rank: pad the batch if needed)
     n_vote_fields: int
     n_num_fields: int
+    packed_votes: bool = False  # gathered vote results as ONE word code:18|support:7|present:7 (include/kllms_b200.h)
 
     @property
     def gv(self) -> int:
@@ -33,16 +34,23 @@ class OutputLayout:
         return self.n_records * self.n_num_fields
 
     @property
+    def vote_bytes(self) -> int:
+        return self.gv * (4 if self.packed_votes else 8)
+
+    @property
     def nbytes(self) -> int:
-        raw = self.gv * 8 + self.gx * 12
+        raw = self.vote_bytes + self.gx * 12
         return (raw + 15) // 16 * 16
 
     def views(self, buf):
-        """Typed views into one rank's slot (a 1-D uint8 tensor of nbytes)."""
+        """Typed views into one rank's slot (a 1-D uint8 tensor of nbytes): (win, vote_meta, value, num_meta), or with
+        packed votes (packed, None, value, num_meta)."""
         import torch
         o = 0
         win = buf[o:o + self.gv * 4].view(torch.int32); o += self.gv * 4
-        vmeta = buf[o:o + self.gv * 4].view(torch.int32); o += self.gv * 4
+        vmeta = None
+        if not self.packed_votes:
+            vmeta = buf[o:o + self.gv * 4].view(torch.int32); o += self.gv * 4
         value = buf[o:o + self.gx * 8].view(torch.float64); o += self.gx * 8
         nmeta = buf[o:o + self.gx * 4].view(torch.int32)
         return win, vmeta, value, nmeta
@@ -120,6 +128,12 @@ class FusedShardedConsensus:
         import ctypes
         self.n_peers = self.world - 1
         self.peer_deltas = (ctypes.c_int64 * max(self.n_peers, 1))(*[ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank])
+        if layout.packed_votes:
+            assert route == "peers", "packed vote results travel as P2P stores"
+            # the full K1 results of this rank's shard stay local (the owner's decoder needs the first-seen index)
+            self.local_win = torch.empty(layout.gv, dtype=torch.int32, device=device)
+            self.local_vmeta = torch.empty(layout.gv, dtype=torch.int32, device=device)
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
 
     def available(self) -> bool:
         if self.route == "multimem":
@@ -127,10 +141,11 @@ class FusedShardedConsensus:
         return 1 <= self.n_peers <= 7
 
     def slot_pointers(self, multicast: bool = True):
-        """(win, vote_meta, value, num_meta) raw addresses of THIS rank's slot, in the multicast or the local mapping."""
+        """(win or packed, vote_meta, value, num_meta) raw addresses of THIS rank's slot, in the multicast or the local
+        mapping."""
         base = (self.mc_ptr if multicast else self.flat.data_ptr()) + self.rank * self.layout.nbytes
-        gv, gx = self.layout.gv, self.layout.gx
-        return base, base + gv * 4, base + gv * 8, base + gv * 8 + gx * 8
+        gv, gx, vb = self.layout.gv, self.layout.gx, self.layout.vote_bytes
+        return base, base + gv * 4, base + vb, base + vb + gx * 8
 
     def rank_views(self, r: int):
         return self.layout.views(self.gathered[r])
@@ -143,6 +158,11 @@ class FusedShardedConsensus:
         if self.route == "multimem":
             win, vmeta, _, _ = self.slot_pointers(multicast=True)
             K.check(lib.kc_vote_i32_ex(codes_ptr, n_groups, n, none_ptr, n_fields, win, vmeta, K.OUT_MULTIMEM, stream_ptr))
+        elif self.layout.packed_votes:
+            packed, _, _, _ = self.slot_pointers(multicast=False)
+            K.check(lib.kc_vote_i32_peers_packed(codes_ptr, n_groups, n, none_ptr, n_fields, self.local_win.data_ptr(),
+                                                 self.local_vmeta.data_ptr(), packed, self.n_peers,
+                                                 ctypes.addressof(self.peer_deltas), self.overflow.data_ptr(), stream_ptr))
         else:
             win, vmeta, _, _ = self.slot_pointers(multicast=False)
             K.check(lib.kc_vote_i32_peers(codes_ptr, n_groups, n, none_ptr, n_fields, win, vmeta, self.n_peers,
@@ -159,6 +179,11 @@ class FusedShardedConsensus:
             _, _, value, nmeta = self.slot_pointers(multicast=False)
             K.check(lib.kc_numeric_f64_peers(vals_ptr, n_groups, n, rel_eps, abs_eps, value, nmeta, self.n_peers,
                                              ctypes.addressof(self.peer_deltas), stream_ptr))
+
+    def packed_overflowed(self) -> bool:
+        """True if a winning code did not fit 18 bits in some step since construction (the gathered words are then unusable:
+        rebuild with packed_votes=False).  Synchronises."""
+        return bool(self.layout.packed_votes and int(self.overflow.item()) != 0)
 
     def step(self, launch: Callable):
         """launch(self) enqueues K1/K2 through self.vote / self.numeric on the current stream; the barrier afterwards makes

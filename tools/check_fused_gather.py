@@ -39,8 +39,9 @@ def main():
     ref.step(compute)
     torch.cuda.synchronize()
 
-    for route in ("peers", "multimem"):
-        fused = FusedShardedConsensus(layout, dev, route=route)
+    for route in ("peers", "multimem", "peers-packed"):
+        packed = route == "peers-packed"
+        fused = FusedShardedConsensus(OutputLayout(N, 24, 8, packed_votes=packed), dev, route="peers" if packed else route)
         ok = fused.available()
         if rank == 0:
             print(f"route {route}: available:", ok, flush=True)
@@ -54,7 +55,17 @@ def main():
 
             fused.step(launch)
             torch.cuda.synchronize()
-            same = torch.equal(fused.gathered, ref.gathered[0])
+            if packed:  # every rank's slot must hold the packing of that rank's NCCL-gathered full results
+                same = not fused.packed_overflowed()
+                for r in range(world):
+                    rw, rm, rv, rn = ref.rank_views(r)
+                    pw, _, pv, pn = fused.rank_views(r)
+                    expect = (rw & 0x3FFFF) | (((rm >> 6) & 0x7F) << 18) | (((rm >> 20) & 0x7F) << 25)
+                    same = same and torch.equal(pw, expect) and torch.equal(pv.view(torch.int64), rv.view(torch.int64)) and torch.equal(pn, rn)
+                rw, rm, _, _ = ref.rank_views(rank)
+                same = same and torch.equal(fused.local_win, rw) and torch.equal(fused.local_vmeta, rm)
+            else:
+                same = torch.equal(fused.gathered, ref.gathered[0])
             t = torch.tensor([1 if same else 0], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             if rank == 0:
