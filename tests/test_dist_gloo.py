@@ -67,3 +67,17 @@ def test_two_rank_sharding_and_all_gather(tmp_path):
         assert np.array_equal(got["vmeta"].view(np.uint32), m)
         assert np.array_equal(got["value"].view(np.uint64), v.view(np.uint64))
         assert np.array_equal(got["nmeta"].view(np.uint32), nm)
+
+
+def test_output_layout_packed_votes_views():
+    """Packed gathered vote results: one word per vote group; value / result-word columns follow at the packed offset."""
+    import torch
+    from k_llms_b200.distributed import OutputLayout
+    full, packed = OutputLayout(10, 24, 8), OutputLayout(10, 24, 8, packed_votes=True)
+    assert full.nbytes == (240 * 8 + 80 * 12 + 15) // 16 * 16 and packed.nbytes == (240 * 4 + 80 * 12 + 15) // 16 * 16
+    buf = torch.arange(packed.nbytes, dtype=torch.int64).to(torch.uint8)
+    words, vmeta, value, nmeta = packed.views(buf)
+    assert vmeta is None and words.numel() == 240 and value.numel() == 80 and nmeta.numel() == 80
+    assert value.data_ptr() - buf.data_ptr() == 240 * 4 and nmeta.data_ptr() - buf.data_ptr() == 240 * 4 + 80 * 8
+    w, m, v, nm = full.views(torch.zeros(full.nbytes, dtype=torch.uint8))
+    assert m.numel() == 240 and v.data_ptr() - w.data_ptr() == 240 * 8
