@@ -219,6 +219,22 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
                          float *device_ms);
 
 /*
+ * H2 — the alignment pre-pass of the client path, natively: recursive_list_alignments
+ * (consensus_utils.py:458-613; lists_alignment :383-430 with the dynamic threshold :185-252, the reference list :255-333, the
+ * min-cost assignment :336-380 = scipy's linear_sum_assignment restated, pruning :109-149; majority ordering
+ * majority_sorting.py:8-112) for ONE record: n candidate values as JSON texts ("null" = None) in, out_texts[c] = json.dumps of
+ * candidate c's aligned value (free with kc_free_strings).  Host code, no GPU.  The default string similarity method
+ * ("embeddings") is assumed.  Returns 0; 1 = the record needs the Python path (two strings both longer than 50 characters
+ * would be compared through the embeddings service, consensus_utils.py:813; non-ASCII text); KC_EINVAL for invalid JSON.
+ * Dict-field similarities are summed in sorted key order (the reference's order depends on PYTHONHASHSEED): similarities agree
+ * to an ulp, alignments are pinned on the reference's goldens (tests/test_align_native.py).
+ */
+int kc_align_json(const char *const *texts, const int64_t *lens, int32_t n, double min_support_ratio, char **out_texts);
+/* test hooks of H2: generic_similarity (consensus_utils.py:892-917) of two JSON values; scipy.optimize.linear_sum_assignment */
+int kc_debug_similarity_json(const char *a, const char *b, double *out);
+int kc_debug_lsap(int32_t nr, int32_t nc, const double *cost, int32_t *row_ind, int32_t *col_ind);
+
+/*
  * H1 — native columnariser / decoder for records of scalars and nested objects: for each record, n candidate JSON texts in ->
  * consensus JSON text + likelihoods JSON text out, multi-threaded on the host with K1/K2 in between.  Replaces, for such
  * records, the Python around the hot path: _safe_parse_content (consolidation.py:25-38), the dict part of

@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM, OUT_PEERS = 0, 1, 2
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -71,6 +71,11 @@ def load() -> ctypes.CDLL:
     lib.kc_numeric_f64_peers.argtypes = [vp, i64, i32, f64, f64, vp, vp, i32, vp, vp]
     lib.kc_vote_i32_peers_packed.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp]
     lib.kc_vote_i32_peers.restype = lib.kc_numeric_f64_peers.restype = lib.kc_vote_i32_peers_packed.restype = c.c_int
+    lib.kc_align_json.argtypes = [c.POINTER(c.c_char_p), vp, i32, f64, c.POINTER(c.c_char_p)]
+    lib.kc_align_json.restype = c.c_int
+    lib.kc_debug_similarity_json.argtypes = [c.c_char_p, c.c_char_p, c.POINTER(c.c_double)]
+    lib.kc_debug_lsap.argtypes = [i32, i32, vp, vp, vp]
+    lib.kc_debug_similarity_json.restype = lib.kc_debug_lsap.restype = c.c_int
     lib.kc_medoid_str_host.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, c.c_int]
     lib.kc_medoid_str_host.restype = c.c_int
     lib.kc_medoid_str.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
@@ -84,7 +89,7 @@ def load() -> ctypes.CDLL:
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib
@@ -251,6 +256,28 @@ def medoid_str(chars, str_off, grp_off, max_group=MAX_CANDIDATES, stream=None):
                                avg.data_ptr(),
                                _stream_ptr(torch, stream)))
     return idx, avg
+
+
+def align_json(values, min_support_ratio: float):
+    """H2: the alignment pre-pass (recursive_list_alignments, default similarity method) of ONE record in native code.
+    values: n JSON-serialisable candidate values.  Returns the aligned values, or None when the record needs the Python
+    pre-pass (long string pairs that go to the embeddings service, non-ASCII text, values json cannot carry)."""
+    import json
+    n = len(values)
+    if n == 0:
+        return None
+    try:
+        texts = (ctypes.c_char_p * n)(*[json.dumps(v).encode("ascii") for v in values])
+    except (TypeError, ValueError):
+        return None
+    out = (ctypes.c_char_p * n)()
+    rc = load().kc_align_json(texts, None, n, float(min_support_ratio), out)
+    if rc != 0:
+        return None
+    try:
+        return [json.loads(out[i]) for i in range(n)]
+    finally:
+        load().kc_free_strings(out, n)
 
 
 def levenshtein(a: str, b: str) -> int:
