@@ -48,17 +48,31 @@ def _contents_of(choices) -> List[dict]:
     return [_safe_parse_content(c.message.content) for c in choices if c.message.content]
 
 
+def _native_alignment(contents, settings):
+    """The alignment pre-pass in native code (H2, `kc_align_json`: same result as `recursive_list_alignments`, pinned on the
+    reference's goldens) — or None when the record needs the Python pre-pass: another similarity method than the default,
+    string pairs that go to the embeddings service (both longer than 50 characters), non-ASCII text."""
+    if settings.string_similarity_method != "embeddings":
+        return None
+    from .. import _native
+    return _native.align_json(contents, settings.min_support_ratio)
+
+
 def _consensus_sync(contents, settings, embed, client):
     if len(contents) >= 2:  # reference consolidation.py:96-104
-        aligned, _ = recursive_list_alignments(contents, settings.string_similarity_method, embed, client, settings.min_support_ratio)
+        aligned = _native_alignment(contents, settings)
+        if aligned is None:
+            aligned, _ = recursive_list_alignments(contents, settings.string_similarity_method, embed, client, settings.min_support_ratio)
         contents = [(d if isinstance(d, dict) else {}) for d in aligned]
     return consensus_values(contents, settings, embed, client=client)
 
 
 async def _consensus_async(contents, settings, embed, client):
     if len(contents) >= 2:
-        aligned, _ = await async_recursive_list_alignments(contents, settings.string_similarity_method, embed, client,
-                                                           settings.min_support_ratio)
+        aligned = _native_alignment(contents, settings)
+        if aligned is None:
+            aligned, _ = await async_recursive_list_alignments(contents, settings.string_similarity_method, embed, client,
+                                                               settings.min_support_ratio)
         contents = [(d if isinstance(d, dict) else {}) for d in aligned]
     return await async_consensus_values(contents, settings, embed, client=client)
 

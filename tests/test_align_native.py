@@ -132,3 +132,19 @@ def test_native_similarity_matches_python():
         out = ctypes.c_double()
         rc = lib.kc_debug_similarity_json(json.dumps(a).encode(), json.dumps(b).encode(), ctypes.byref(out))
         assert rc == 0 and abs(out.value - exp) <= 1e-12, (a, b, exp, out.value)
+
+
+def test_consolidation_uses_the_native_prepass_with_identical_results():
+    """The hook consolidation.py calls before the vote: same aligned contents as the Python pre-pass on every client-order
+    golden input, and None (Python fallback) for the non-default similarity methods."""
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings
+    from k_llms_b200.utils.consolidation import _native_alignment
+    used = 0
+    for case in load_golden("client_order"):
+        contents = json.loads(json.dumps(case["values"]))
+        native = _native_alignment(contents, ConsensusSettings())
+        assert native is not None
+        used += 1
+        assert json.dumps(native) == json.dumps(_python_align(contents))
+    assert used > 100
+    assert _native_alignment([{"a": [1]}, {"a": [1]}], ConsensusSettings(string_similarity_method="jaccard")) is None
