@@ -219,6 +219,24 @@ int kc_consensus_host_i8(const int8_t *h_codes, int32_t n_vote_fields, const int
                          float *device_ms);
 
 /*
+ * H1 in two phases, for callers that run K1 / K2 / K4 themselves (own streams, another device; the CPU tests put the oracle
+ * in their place to check the host logic without a GPU).  kc_json_plan parses, plans and encodes a batch into host arrays owned
+ * by the handle; kc_json_inputs exposes them (vote cells int8[n_vote_groups][n] as kc_vote_i8 takes them with n_fields = 1 and
+ * no none_code; numeric cells float64[n_num_groups][n]; medoid groups in kc_medoid_str's CSR form); the caller computes
+ * vote_meta uint32[n_vote_groups], num_value float64 / num_meta uint32 [n_num_groups], medoid_idx int32 / medoid_avg float64
+ * [n_medoid_groups]; kc_json_emit turns them into the texts kc_consolidate_json returns.  The candidate texts must stay alive
+ * until kc_json_emit has returned (cells are views into them).
+ */
+typedef struct kc_json_batch kc_json_batch;
+int kc_json_plan(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, int32_t threads, kc_json_batch **out);
+int kc_json_inputs(const kc_json_batch *h, const int8_t **vote_cells, int64_t *n_vote_groups, const double **num_cells,
+                   int64_t *n_num_groups, const uint8_t **medoid_chars, const int32_t **medoid_str_off, const int32_t **medoid_grp_off,
+                   int64_t *n_medoid_groups, int32_t *max_medoid_group);
+int kc_json_emit(kc_json_batch *h, const uint32_t *vote_meta, const double *num_value, const uint32_t *num_meta, const int32_t *medoid_idx,
+                 const double *medoid_avg, char **out_content, char **out_likelihoods, uint8_t *out_status);
+void kc_json_free(kc_json_batch *h);
+
+/*
  * H2 — the alignment pre-pass of the client path, natively: recursive_list_alignments
  * (consensus_utils.py:458-613; lists_alignment :383-430 with the dynamic threshold :185-252, the reference list :255-333, the
  * min-cost assignment :336-380 = scipy's linear_sum_assignment restated, pruning :109-149; majority ordering

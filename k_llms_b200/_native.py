@@ -24,7 +24,7 @@ FLAG_HAS_VALUE, FLAG_SINGLE, FLAG_TIE, FLAG_NO_FINITE = 1, 2, 4, 8
 OUT_LOCAL, OUT_MULTIMEM, OUT_PEERS = 0, 1, 2
 
 EXPORTS = (
-    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
+    "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
 )
 
@@ -71,6 +71,12 @@ def load() -> ctypes.CDLL:
     lib.kc_numeric_f64_peers.argtypes = [vp, i64, i32, f64, f64, vp, vp, i32, vp, vp]
     lib.kc_vote_i32_peers_packed.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp]
     lib.kc_vote_i32_peers.restype = lib.kc_numeric_f64_peers.restype = lib.kc_vote_i32_peers_packed.restype = c.c_int
+    lib.kc_json_plan.argtypes = [vp, vp, i64, i32, i32, c.POINTER(vp)]
+    lib.kc_json_inputs.argtypes = [vp] + [vp] * 9
+    lib.kc_json_emit.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.kc_json_plan.restype = lib.kc_json_inputs.restype = lib.kc_json_emit.restype = c.c_int
+    lib.kc_json_free.argtypes = [vp]
+    lib.kc_json_free.restype = None
     lib.kc_align_json.argtypes = [c.POINTER(c.c_char_p), vp, i32, f64, c.POINTER(c.c_char_p)]
     lib.kc_align_json.restype = c.c_int
     lib.kc_debug_similarity_json.argtypes = [c.c_char_p, c.c_char_p, c.POINTER(c.c_double)]
@@ -89,7 +95,7 @@ def load() -> ctypes.CDLL:
     lib.kc_host_free.argtypes = [vp]
     lib.kc_host_free.restype = None
     for name in ("kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_confidence_f64", "kc_logprob_sum_f32",
-                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
+                 "kc_weighted_vote_i32", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
                  "kc_consensus_host"):
         getattr(lib, name).restype = c.c_int
     _lib = lib

@@ -1644,6 +1644,69 @@ void align_values(AlignCtx &cx, std::vector<int32_t> &values, double min_support
     }
 }
 
+
+// ---------------------------------------------------------------- a batch of records: plan, encode, emit
+
+struct Batch {
+    int n = 0;
+    std::vector<Record> recs;
+    int64_t gv = 0, gx = 0, gm = 0;       // vote / numeric / medoid groups of the records with status 0
+    std::vector<uint8_t> m_chars;         // medoid groups of the whole batch in CSR form for ONE K4 launch
+    std::vector<int32_t> m_str_off{0}, m_grp_off{0};
+    int32_t m_max_group = 2;
+};
+
+int default_threads() { return (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency())); }  // parsing saturates memory / malloc beyond ~32
+
+void plan_batch(Batch &b, const char *const *texts, const int64_t *lens, int64_t n_records, int n, int threads) {
+    b.n = n;
+    b.recs.assign((size_t)n_records, Record());
+    parallel_for(n_records, threads, [&](int64_t r) { plan_record(texts + r * n, lens ? lens + r * n : nullptr, n, b.recs[(size_t)r]); });
+    for (auto &rec : b.recs) {
+        if (rec.status) continue;
+        for (auto &g : rec.groups) {
+            if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) g.row = b.gv++;
+            else if (g.kind == G_NUMERIC) g.row = b.gx++;
+            else if (g.kind == G_MEDOID && g.m_count >= 2) {
+                g.row = b.gm++;
+                for (uint32_t k = 0; k < g.m_count; ++k) b.m_str_off.push_back(b.m_str_off.back() + rec.mlen[g.m_first + k]);
+                b.m_grp_off.push_back(b.m_grp_off.back() + (int32_t)g.m_count);
+                b.m_max_group = std::max(b.m_max_group, (int32_t)g.m_count);
+            }
+        }
+        if (!rec.mchars.empty()) b.m_chars.insert(b.m_chars.end(), rec.mchars.begin(), rec.mchars.end());
+    }
+}
+
+void encode_batch(const Batch &b, int8_t *codes, double *vals, int threads) {
+    const int n = b.n;
+    parallel_for((int64_t)b.recs.size(), threads, [&](int64_t r) {
+        const Record &rec = b.recs[(size_t)r];
+        if (rec.status) return;
+        for (size_t gi = 0; gi < rec.groups.size(); ++gi) {
+            const Group &g = rec.groups[gi];
+            const Tok *toks = &rec.cells[gi * (size_t)n];
+            if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) encode_vote(g.kind, toks, n, codes + g.row * n);
+            else if (g.kind == G_NUMERIC) encode_numeric(toks, n, vals + g.row * n);
+        }
+    });
+}
+
+void emit_batch(const Batch &b, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, const int32_t *midx, const double *mavg,
+                int threads, char **out_content, char **out_likelihoods, uint8_t *out_status) {
+    parallel_for((int64_t)b.recs.size(), threads, [&](int64_t r) {
+        const Record &rec = b.recs[(size_t)r];
+        out_status[r] = rec.status;
+        out_content[r] = nullptr;
+        out_likelihoods[r] = nullptr;
+        if (rec.status) return;
+        std::string content, lik;
+        emit_record(rec, b.n, vmeta, nvalue, nmeta, midx, mavg, content, lik);
+        out_content[r] = dup_string(content);
+        out_likelihoods[r] = dup_string(lik);
+    });
+}
+
 }  // namespace
 
 extern "C" {
@@ -1653,34 +1716,15 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
                         uint8_t *out_status) {
     if (n < 2 || n > KC_MAX_CANDIDATES || n_records < 0 || !texts || !out_content || !out_likelihoods || !out_status)
         return KC_EINVAL;
-    if (threads <= 0) threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));  // parsing saturates memory / malloc beyond ~32
+    if (threads <= 0) threads = default_threads();
     const bool timing = getenv("KC_JSON_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = now();
-    std::vector<Record> recs((size_t)n_records);
-    parallel_for(n_records, threads, [&](int64_t r) { plan_record(texts + r * n, lens ? lens + r * n : nullptr, n, recs[(size_t)r]); });
-
+    Batch batch;
+    plan_batch(batch, texts, lens, n_records, n, threads);
     const auto t1 = now();
-    int64_t gv = 0, gx = 0, gm = 0;
-    // medoid groups of the whole batch in CSR form for ONE K4 launch
-    std::vector<uint8_t> m_chars;
-    std::vector<int32_t> m_str_off{0}, m_grp_off{0};
-    int32_t m_max_group = 2;
-    for (auto &rec : recs) {
-        if (rec.status) continue;
-        for (auto &g : rec.groups) {
-            if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) g.row = gv++;
-            else if (g.kind == G_NUMERIC) g.row = gx++;
-            else if (g.kind == G_MEDOID && g.m_count >= 2) {
-                g.row = gm++;
-                for (uint32_t k = 0; k < g.m_count; ++k) m_str_off.push_back(m_str_off.back() + rec.mlen[g.m_first + k]);
-                m_grp_off.push_back(m_grp_off.back() + (int32_t)g.m_count);
-                m_max_group = std::max(m_max_group, (int32_t)g.m_count);
-            }
-        }
-        if (!rec.mchars.empty()) m_chars.insert(m_chars.end(), rec.mchars.begin(), rec.mchars.end());
-    }
+    const int64_t gv = batch.gv, gx = batch.gx, gm = batch.gm;
     std::vector<int32_t> m_idx((size_t)gm);
     std::vector<double> m_avg((size_t)gm);
     // page-locked staging buffers are expensive to create: keep them (grow-only) across calls
@@ -1708,44 +1752,74 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
     int rc = KC_OK;
     if ((gv && (!h_codes || !h_win || !h_vmeta)) || (gx && (!h_vals || !h_value || !h_nmeta))) rc = KC_ENOMEM;
     if (!rc) {
-        parallel_for(n_records, threads, [&](int64_t r) {
-            const Record &rec = recs[(size_t)r];
-            if (rec.status) return;
-            for (size_t gi = 0; gi < rec.groups.size(); ++gi) {
-                const Group &g = rec.groups[gi];
-                const Tok *toks = &rec.cells[gi * (size_t)n];
-                if (g.kind == G_VOTE_STR || g.kind == G_VOTE_BOOL) encode_vote(g.kind, toks, n, h_codes + g.row * n);
-                else if (g.kind == G_NUMERIC) encode_numeric(toks, n, h_vals + g.row * n);
-            }
-        });
+        encode_batch(batch, h_codes, h_vals, threads);
         t3 = now();
         // one "field" per group: the two halves are independent calls of the host-buffer entry
         if (gv) rc = kc_consensus_host_i8(h_codes, 1, nullptr, nullptr, 0, gv, n, rel_eps, abs_eps, h_win, h_vmeta, nullptr, nullptr, device, nullptr);
         if (!rc && gx) rc = kc_consensus_host_i8(nullptr, 0, nullptr, h_vals, 1, gx, n, rel_eps, abs_eps, nullptr, nullptr, h_value, h_nmeta, device, nullptr);
         if (!rc && gm)
-            rc = kc_medoid_str_host(m_chars.data(), (int64_t)m_chars.size(), m_str_off.data(), m_grp_off.data(), gm, m_max_group, m_idx.data(),
-                                    m_avg.data(), device);
+            rc = kc_medoid_str_host(batch.m_chars.data(), (int64_t)batch.m_chars.size(), batch.m_str_off.data(), batch.m_grp_off.data(), gm,
+                                    batch.m_max_group, m_idx.data(), m_avg.data(), device);
     }
     t4 = now();
-    if (!rc) {
-        parallel_for(n_records, threads, [&](int64_t r) {
-            const Record &rec = recs[(size_t)r];
-            out_status[r] = rec.status;
-            out_content[r] = nullptr;
-            out_likelihoods[r] = nullptr;
-            if (rec.status) return;
-            std::string content, lik;
-            emit_record(rec, n, h_vmeta, h_value, h_nmeta, m_idx.data(), m_avg.data(), content, lik);
-            out_content[r] = dup_string(content);
-            out_likelihoods[r] = dup_string(lik);
-        });
-    }
+    if (!rc) emit_batch(batch, h_vmeta, h_value, h_nmeta, m_idx.data(), m_avg.data(), threads, out_content, out_likelihoods, out_status);
     const auto t5 = now();
     if (timing)
         fprintf(stderr, "kc_consolidate_json: parse+plan %.1f ms, rows+alloc %.1f ms, encode %.1f ms, gpu %.1f ms, emit %.1f ms (%d threads)\n",
                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5), threads);
     return rc;
 }
+
+// The same in two phases, for callers that run K1 / K2 / K4 themselves (their own streams, another device, a test that puts
+// a checker in their place): kc_json_plan parses, plans and encodes a batch into host arrays the handle owns; the caller
+// computes the result columns for them; kc_json_emit turns those into the consensus texts.  The candidate texts must stay
+// alive until kc_json_emit returns (cells are views into them).
+struct kc_json_batch {
+    Batch batch;
+    std::vector<int8_t> codes;
+    std::vector<double> vals;
+    int threads;
+};
+
+int kc_json_plan(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, int32_t threads, kc_json_batch **out) {
+    if (n < 2 || n > KC_MAX_CANDIDATES || n_records < 0 || !texts || !out) return KC_EINVAL;
+    if (threads <= 0) threads = default_threads();
+    kc_json_batch *h = new (std::nothrow) kc_json_batch;
+    if (!h) return KC_ENOMEM;
+    h->threads = threads;
+    plan_batch(h->batch, texts, lens, n_records, n, threads);
+    h->codes.resize((size_t)h->batch.gv * n);
+    h->vals.resize((size_t)h->batch.gx * n);
+    encode_batch(h->batch, h->codes.data(), h->vals.data(), threads);
+    *out = h;
+    return KC_OK;
+}
+
+int kc_json_inputs(const kc_json_batch *h, const int8_t **vote_cells, int64_t *n_vote_groups, const double **num_cells,
+                   int64_t *n_num_groups, const uint8_t **medoid_chars, const int32_t **medoid_str_off, const int32_t **medoid_grp_off,
+                   int64_t *n_medoid_groups, int32_t *max_medoid_group) {
+    if (!h) return KC_EINVAL;
+    if (vote_cells) *vote_cells = h->codes.data();
+    if (n_vote_groups) *n_vote_groups = h->batch.gv;
+    if (num_cells) *num_cells = h->vals.data();
+    if (n_num_groups) *n_num_groups = h->batch.gx;
+    if (medoid_chars) *medoid_chars = h->batch.m_chars.data();
+    if (medoid_str_off) *medoid_str_off = h->batch.m_str_off.data();
+    if (medoid_grp_off) *medoid_grp_off = h->batch.m_grp_off.data();
+    if (n_medoid_groups) *n_medoid_groups = h->batch.gm;
+    if (max_medoid_group) *max_medoid_group = h->batch.m_max_group;
+    return KC_OK;
+}
+
+int kc_json_emit(kc_json_batch *h, const uint32_t *vote_meta, const double *num_value, const uint32_t *num_meta, const int32_t *medoid_idx,
+                 const double *medoid_avg, char **out_content, char **out_likelihoods, uint8_t *out_status) {
+    if (!h || !out_content || !out_likelihoods || !out_status) return KC_EINVAL;
+    if ((h->batch.gv && !vote_meta) || (h->batch.gx && (!num_value || !num_meta)) || (h->batch.gm && (!medoid_idx || !medoid_avg))) return KC_EINVAL;
+    emit_batch(h->batch, vote_meta, num_value, num_meta, medoid_idx, medoid_avg, h->threads, out_content, out_likelihoods, out_status);
+    return KC_OK;
+}
+
+void kc_json_free(kc_json_batch *h) { delete h; }
 
 // H2: recursive_list_alignments(values, "embeddings", embed, client, min_support_ratio)[0] for ONE record of n candidate
 // values given as JSON texts (null = None): out_texts[c] = json.dumps of candidate c's aligned value (free with

@@ -79,3 +79,47 @@ def random_string_groups(rng, n_groups, max_k=16, long_frac=0.1):
             grp[int(rng.integers(0, k))] = " ".join(_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), 40))
         groups.append(grp)
     return groups
+
+
+def consolidate_json_with_oracle(records):
+    """kc_json_plan -> the C ORACLE in the place of K1 / K2 / K4 -> kc_json_emit: the host logic of the native JSON path
+    (H1) checked on a machine without a GPU.  Same return convention as _native.consolidate_json."""
+    import ctypes as c
+    from k_llms_b200 import _native as K
+    from oracle import columnar as OC
+    lib = K.load()
+    R = len(records)
+    if R == 0:
+        return []
+    n = len(records[0])
+    assert all(len(r) == n for r in records)
+    blobs = [t.encode("utf-8") for r in records for t in r]
+    texts = (c.c_char_p * (R * n))(*blobs)
+    lens = (c.c_int64 * (R * n))(*[len(b) for b in blobs])
+    h = c.c_void_p()
+    K.check(lib.kc_json_plan(c.cast(texts, c.c_void_p), c.cast(lens, c.c_void_p), R, n, 4, c.byref(h)))
+    try:
+        vc, nc, mc, so, go = c.c_void_p(), c.c_void_p(), c.c_void_p(), c.c_void_p(), c.c_void_p()
+        gv, gx, gm, mx = c.c_int64(), c.c_int64(), c.c_int64(), c.c_int32()
+        K.check(lib.kc_json_inputs(h, c.byref(vc), c.byref(gv), c.byref(nc), c.byref(gx), c.byref(mc), c.byref(so), c.byref(go),
+                                   c.byref(gm), c.byref(mx)))
+        vmeta = np.zeros(max(gv.value, 1), dtype=np.uint32)
+        nvalue, nmeta = np.zeros(max(gx.value, 1), dtype=np.float64), np.zeros(max(gx.value, 1), dtype=np.uint32)
+        midx, mavg = np.zeros(max(gm.value, 1), dtype=np.int32), np.zeros(max(gm.value, 1), dtype=np.float64)
+        if gv.value:
+            codes = np.ctypeslib.as_array(c.cast(vc, c.POINTER(c.c_int8)), shape=(gv.value, n)).astype(np.int32)
+            _, vmeta = OC.vote(codes, None)
+        if gx.value:
+            vals = np.ctypeslib.as_array(c.cast(nc, c.POINTER(c.c_double)), shape=(gx.value, n)).copy()
+            nvalue, nmeta = OC.numeric(vals)
+        if gm.value:
+            OC.lib().ko_medoid_str(mc, so, go, gm.value, midx.ctypes.data, mavg.ctypes.data)
+        out_c, out_l, status = (c.c_void_p * R)(), (c.c_void_p * R)(), (c.c_uint8 * R)()
+        K.check(lib.kc_json_emit(h, vmeta.ctypes.data, nvalue.ctypes.data, nmeta.ctypes.data, midx.ctypes.data, mavg.ctypes.data,
+                                 c.cast(out_c, c.c_void_p), c.cast(out_l, c.c_void_p), c.cast(status, c.c_void_p)))
+        res = [(c.string_at(out_c[i]).decode("ascii"), c.string_at(out_l[i]).decode("ascii")) if status[i] == 0 else None for i in range(R)]
+        lib.kc_free_strings(c.cast(out_c, c.c_void_p), R)
+        lib.kc_free_strings(c.cast(out_l, c.c_void_p), R)
+        return res
+    finally:
+        lib.kc_json_free(h)
