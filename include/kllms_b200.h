@@ -253,7 +253,7 @@ int kc_debug_similarity_json(const char *a, const char *b, double *out);
 int kc_debug_lsap(int32_t nr, int32_t nc, const double *cost, int32_t *row_ind, int32_t *col_ind);
 
 /*
- * H1 — native columnariser / decoder for records of scalars and nested objects: for each record, n candidate JSON texts in ->
+ * H1 — native columnariser / decoder for records of scalars, nested objects and lists: for each record, n candidate JSON texts in ->
  * consensus JSON text + likelihoods JSON text out, multi-threaded on the host with K1/K2 in between.  Replaces, for such
  * records, the Python around the hot path: _safe_parse_content (consolidation.py:25-38), the dict part of
  * recursive_list_alignments (consensus_utils.py:516-548: keys sorted, missing -> None), the dispatcher
@@ -261,7 +261,9 @@ int kc_debug_lsap(int32_t nr, int32_t nc, const double *cost, int32_t *row_ind, 
  *   texts   [n_records * n] candidate contents (record-major); lens [n_records * n] byte lengths or NULL (NUL-terminated)
  *   out_content / out_likelihoods [n_records] malloc'ed NUL-terminated strings (free with kc_free_strings), byte-identical
  *           to the reference's json.dumps output; out_status [n_records]: 0 = consolidated here, 1 = not expressible as
- *           groups for K1/K2/K4 (lists, a key mixing objects and scalars, non-ASCII, empty content, ...) -> caller uses the Python path
+ *           groups for K1/K2/K4 (a key mixing objects with other types, string pairs that need the embeddings service, non-ASCII,
+ *           empty content, ...) -> caller uses the Python path.  Implements the reference's DEFAULT settings (similarity method
+ *           "embeddings", min_support_ratio 0.51, Nones do not vote); other settings: Python path
  *   threads <= 0: min(32, hardware threads).  Blocks until done; callers are serialised (one staging pool per process).
  */
 int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n_records, int32_t n, double rel_eps,

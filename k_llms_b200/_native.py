@@ -293,7 +293,7 @@ def levenshtein(a: str, b: str) -> int:
 
 
 def consolidate_json(records, rel_eps: float = 0.03, abs_eps: float = 1e-6, device: int = 0, threads: int = 0):
-    """H1: native consolidation of records of scalars and nested objects (lists take the Python path).  records: list of lists of n candidate content strings.
+    """H1: native consolidation of records of scalars, nested objects and lists (default settings).  records: list of lists of n candidate content strings.
     Returns a list of (content_str, likelihoods_json_str) or None where the record needs the Python path."""
     lib = load()
     R = len(records)

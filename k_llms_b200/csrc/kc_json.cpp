@@ -5,11 +5,12 @@
 // Python around the hot path:
 //     _safe_parse_content            consolidation.py:25-38   (json.loads, or {"text": content})
 //     recursive_list_alignments      consensus_utils.py:516-548 (dict part: every candidate gets every key, keys SORTED)
-//     consensus_values dispatcher    consensus_utils.py:1376-1454 (scalar fields and nested objects)
+//     consensus_values dispatcher    consensus_utils.py:1376-1454 (scalar fields, nested objects, lists element-wise)
+//     lists_alignment                consensus_utils.py:185-430 + majority_sorting.py (H2 below; records with list fields)
 //     sanitize_value / `v or False`  consensus_utils.py:925-933, 956   -> local dictionary codes (int8 cells)
 //     _format_consensus_content      consolidation.py:41-60   (json.dumps of the consensus; {"text": s} -> s)
 //     similarity medoid              consensus_utils.py:1221-1237 for multi-word string fields (batched into one K4 launch)
-// Records it cannot express (lists, a key mixing objects and scalars, string groups outside K4's contract, non-ASCII
+// Records it cannot express (a key mixing objects with other types, string groups outside K4's contract, non-ASCII
 // text, mixed-type bool groups) are NOT guessed at: they get status 1 and the Python path handles them.
 //
 // Text formats follow CPython exactly: float -> float.__repr__ (shortest round-trip digits, exponent form outside
@@ -25,6 +26,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <string_view>
@@ -457,7 +459,8 @@ struct Group {
 struct Node {
     std::string_view key;
     int32_t group = -1;        // >= 0: leaf
-    std::vector<int32_t> kids; // dict: indices into Record::nodes
+    bool is_list = false;      // a list node: children are its columns, in order (no keys)
+    std::vector<int32_t> kids; // dict / list: indices into Record::nodes
 };
 
 struct Record {
@@ -467,6 +470,7 @@ struct Record {
     std::vector<Tok> cells;    // groups.size() * n tokens, group-major (T_MISSING / T_NULL count as None)
     std::string mchars;        // normalize_string() of the cells of the medoid groups, back to back
     std::vector<int32_t> mlen; // their lengths
+    std::shared_ptr<void> tree;  // records with lists: the aligned value tree the cells and keys point into
 };
 
 const double kF64None = [] { const uint64_t b = KC_F64_NONE_BITS; double d; memcpy(&d, &b, 8); return d; }();
@@ -590,7 +594,11 @@ void plan_dict(Record &rec, int32_t node, const std::vector<Item> *const *items,
         for (int c = 0; c < n && !first; ++c)
             if (cells[(size_t)c].type > T_NULL) first = &cells[(size_t)c];
         if (first && first->type == T_NESTED) {
-            if (*first->p != '{' || depth + 1 >= kMaxDepth) {  // lists need the alignment of cu:185-430: Python path
+            if (*first->p != '{') {  // a list: the whole record goes through the alignment pre-pass (tree path below)
+                rec.status = 2;
+                return;
+            }
+            if (depth + 1 >= kMaxDepth) {
                 rec.status = 1;
                 return;
             }
@@ -637,6 +645,8 @@ void plan_dict(Record &rec, int32_t node, const std::vector<Item> *const *items,
     }
 }
 
+void plan_record_tree(const char *const *texts, const int64_t *lens, int n, Record &rec);
+
 void plan_record(const char *const *texts, const int64_t *lens, int n, Record &rec) {
     thread_local std::vector<std::vector<Item>> cands;
     if ((int)cands.size() < n) cands.resize((size_t)n);
@@ -680,6 +690,7 @@ void plan_record(const char *const *texts, const int64_t *lens, int n, Record &r
     top.assign((size_t)n, nullptr);
     for (int c = 0; c < n; ++c) top[(size_t)c] = &cands[(size_t)c];
     plan_dict(rec, 0, top.data(), n, 0);
+    if (rec.status == 2) plan_record_tree(texts, lens, n, rec);  // list fields: align first (H2), then plan on the aligned tree
 }
 
 void encode_vote(GroupKind kind, const Tok *toks, int n, int8_t *cells) {
@@ -810,8 +821,8 @@ void emit_node(const EmitCtx &cx, int32_t ni, std::string &content, std::string 
         emit_leaf(cx, (size_t)node.group, content, lik);
         return;
     }
-    content += "{";
-    lik += "{";
+    content += node.is_list ? "[" : "{";
+    lik += node.is_list ? "[" : "{";
     bool first = true;
     for (int32_t kid : node.kids) {
         if (!first) {
@@ -819,15 +830,17 @@ void emit_node(const EmitCtx &cx, int32_t ni, std::string &content, std::string 
             lik += ", ";
         }
         first = false;
-        const std::string_view key = cx.rec.nodes[(size_t)kid].key;
-        json_string(key, content);
-        json_string(key, lik);
-        content += ": ";
-        lik += ": ";
+        if (!node.is_list) {
+            const std::string_view key = cx.rec.nodes[(size_t)kid].key;
+            json_string(key, content);
+            json_string(key, lik);
+            content += ": ";
+            lik += ": ";
+        }
         emit_node(cx, kid, content, lik);
     }
-    content += "}";
-    lik += "}";
+    content += node.is_list ? "]" : "}";
+    lik += node.is_list ? "]" : "}";
 }
 
 void emit_record(const Record &rec, int n, const uint32_t *vmeta, const double *nvalue, const uint32_t *nmeta, const int32_t *midx,
@@ -1644,6 +1657,138 @@ void align_values(AlignCtx &cx, std::vector<int32_t> &values, double min_support
     }
 }
 
+
+// ---------------------------------------------------------------- H1 for records with list fields: plan on the aligned tree
+
+Tok tok_of(const AVal &v) {  // a scalar of the tree as the token the leaf planner / encoders / emitters work on
+    static const char kBrace[] = "{";
+    Tok t;
+    switch (v.t) {
+        case A_NONE: t.type = T_NULL; break;
+        case A_BOOL: t.type = v.b ? T_TRUE : T_FALSE; break;
+        case A_INT: t.type = T_INT; t.p = v.s.data(); t.len = (uint32_t)v.s.size(); t.num = v.num; break;
+        case A_FLOAT: t.type = T_FLOAT; t.num = v.num; break;
+        case A_STR: t.type = T_STR; t.p = v.s.data(); t.len = (uint32_t)v.s.size(); break;  // already unescaped
+        default: t.type = T_NESTED; t.p = kBrace; t.len = 1; break;
+    }
+    return t;
+}
+
+// The dispatcher (cu:1376-1454) over ALIGNED candidates: after the pre-pass every candidate is a dict with the same sorted
+// keys at a dict node and a list of the same width at a list node (cu:516-548, 550-613), so parent_valid_frac stays 1 and a
+// node is a dict, a list or a scalar field.  Anything the pre-pass left unaligned (mixed types) goes to the Python path.
+void plan_tree_value(Record &rec, AlignCtx &cx, int32_t node, const std::vector<int32_t> &ids, int n, int depth, std::string &tmp) {
+    if (depth > 48) {
+        rec.status = 1;
+        return;
+    }
+    const AVal *first = nullptr;
+    for (int c = 0; c < n && !first; ++c)
+        if (cx.tr.v[(size_t)ids[(size_t)c]].t != A_NONE) first = &cx.tr.v[(size_t)ids[(size_t)c]];
+    if (first && (first->t == A_DICT || first->t == A_LIST)) {
+        const AType ft = first->t;
+        for (int c = 0; c < n; ++c)
+            if (cx.tr.v[(size_t)ids[(size_t)c]].t != ft) {  // not what the pre-pass produces from uniform input
+                rec.status = 1;
+                return;
+            }
+        std::vector<int32_t> child((size_t)n);
+        if (ft == A_DICT) {
+            const size_t width = first->kv.size();
+            for (int c = 0; c < n; ++c)
+                if (cx.tr.v[(size_t)ids[(size_t)c]].kv.size() != width) {
+                    rec.status = 1;
+                    return;
+                }
+            for (size_t k = 0; k < width; ++k) {
+                const std::string &key = cx.tr.v[(size_t)ids[0]].kv[k].first;
+                for (int c = 0; c < n; ++c) {
+                    const auto &e = cx.tr.v[(size_t)ids[(size_t)c]].kv[k];
+                    if (e.first != key) {
+                        rec.status = 1;
+                        return;
+                    }
+                    child[(size_t)c] = e.second;
+                }
+                if (key.find("reasoning___") != std::string::npos || key.find("source___") != std::string::npos) continue;  // cu:1292
+                const int32_t kid = (int32_t)rec.nodes.size();
+                rec.nodes.emplace_back();
+                rec.nodes[(size_t)kid].key = key;
+                rec.nodes[(size_t)node].kids.push_back(kid);
+                plan_tree_value(rec, cx, kid, child, n, depth + 1, tmp);
+                if (rec.status) return;
+            }
+        } else {
+            rec.nodes[(size_t)node].is_list = true;
+            const size_t width = first->items.size();
+            for (int c = 0; c < n; ++c)
+                if (cx.tr.v[(size_t)ids[(size_t)c]].items.size() != width) {
+                    rec.status = 1;
+                    return;
+                }
+            for (size_t k = 0; k < width; ++k) {
+                for (int c = 0; c < n; ++c) child[(size_t)c] = cx.tr.v[(size_t)ids[(size_t)c]].items[k];
+                const int32_t kid = (int32_t)rec.nodes.size();
+                rec.nodes.emplace_back();
+                rec.nodes[(size_t)node].kids.push_back(kid);
+                plan_tree_value(rec, cx, kid, child, n, depth + 1, tmp);
+                if (rec.status) return;
+            }
+        }
+        return;
+    }
+    // a scalar field (or all None)
+    const size_t base = rec.cells.size();
+    for (int c = 0; c < n; ++c) rec.cells.push_back(tok_of(cx.tr.v[(size_t)ids[(size_t)c]]));
+    Group g;
+    g.key = rec.nodes[(size_t)node].key;
+    if (!plan_leaf(rec, g, &rec.cells[base], n, tmp)) return;
+    rec.nodes[(size_t)node].group = (int32_t)rec.groups.size();
+    rec.groups.push_back(g);
+}
+
+void plan_record_tree(const char *const *texts, const int64_t *lens, int n, Record &rec) {
+    rec.status = 0;
+    rec.groups.clear();
+    rec.cells.clear();
+    rec.mchars.clear();
+    rec.mlen.clear();
+    rec.nodes.clear();
+    auto cxp = std::make_shared<AlignCtx>();
+    AlignCtx &cx = *cxp;
+    std::vector<int32_t> values((size_t)n);
+    for (int c = 0; c < n; ++c) {  // _safe_parse_content (consolidation.py:25-38); the caller already ruled out empty / non-ASCII text
+        const size_t len = lens ? (size_t)lens[c] : strlen(texts[c]);
+        Scanner sc{texts[c], texts[c] + len};
+        const size_t mark = cx.tr.v.size();
+        bool ok = aparse(sc, cx.tr, values[(size_t)c], 0);
+        if (ok) {
+            sc.ws();
+            ok = sc.p == sc.end;
+        }
+        if (ok && cx.tr.v[(size_t)values[(size_t)c]].t != A_DICT) {  // valid JSON but not an object: Python path (as the flat planner does)
+            rec.status = 1;
+            return;
+        }
+        if (!ok) {  // {"text": content}
+            cx.tr.v.resize(mark);
+            const int32_t str = cx.tr.add(A_STR);
+            cx.tr.v[(size_t)str].s.assign(texts[c], len);
+            const int32_t d = cx.tr.add(A_DICT);
+            cx.tr.v[(size_t)d].kv.emplace_back("text", str);
+            values[(size_t)c] = d;
+        }
+    }
+    align_values(cx, values, /*min_support_ratio=*/0.51, 0);  // ConsensusSettings default (cu:41); other settings: Python path
+    if (cx.needs_embeddings) {
+        rec.status = 1;
+        return;
+    }
+    thread_local std::string tmp;
+    rec.nodes.emplace_back();
+    plan_tree_value(rec, cx, 0, values, n, 0, tmp);
+    if (rec.status == 0) rec.tree = cxp;  // from here on nothing is added to the tree: cells and keys point into it
+}
 
 // ---------------------------------------------------------------- a batch of records: plan, encode, emit
 

@@ -200,12 +200,16 @@ def consolidate_contents_batch(records: List[List[str]], consensus_settings: Con
     `choice.message.content` strings in -> (consensus content string, likelihoods) out, exactly what the per-request
     functions above put into choices[0] and `likelihoods`.
 
-    Flat records go through the native path (kc_consolidate_json: C++ parse/encode/decode + K1/K2, no Python objects);
-    records it declines (nested values, multi-word strings, non-ASCII, ...) take the regular Python + GPU path."""
+    Records of scalars, nested objects and lists go through the native path (kc_consolidate_json: C++ parse / alignment
+    pre-pass / encode / decode + K1/K2/K4, no Python objects) when the settings are the ones it implements (the defaults);
+    records it declines (a key mixing objects with other types, string pairs that need the embeddings service, non-ASCII
+    text, ...) take the regular Python + GPU path."""
     from .. import _native
     default_eps = (consensus_settings.rel_eps, consensus_settings.abs_eps)
     native: List[Any] = [None] * len(records)
-    if not consensus_settings.allow_none_as_candidate:
+    native_settings = (not consensus_settings.allow_none_as_candidate and consensus_settings.string_similarity_method == "embeddings"
+                       and consensus_settings.string_consensus_method == "centroid" and consensus_settings.min_support_ratio == 0.51)
+    if native_settings:
         by_n: dict = {}
         for i, texts in enumerate(records):
             if len(texts) >= 2:

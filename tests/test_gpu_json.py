@@ -145,8 +145,53 @@ def test_native_json_nested_objects():
             exp = _expected(texts)
             assert got[0] == exp[0] and got[1] == exp[1], (texts, got, exp)
     assert native > 1200 and nested_native > 600
-    declined = [['{"a": {"b": 1}}', '{"a": 5}'], ['{"a": {"b": [1]}}', '{"a": {"b": [1]}}'], ['{"a": [{"b": 1}]}', '{"a": [{"b": 1}]}']]
+    declined = [['{"a": {"b": 1}}', '{"a": 5}'], ['{"a": {"b": 1}}', '{"a": [1]}']]  # a key mixing objects with other types
     assert K.consolidate_json(declined) == [None] * len(declined)
+
+
+def _expected_with_lists(texts):
+    """Client order incl. the list alignment: the Python pre-pass (pinned on the reference's alignment goldens) + the
+    object-level oracle for the consensus."""
+    import logging
+    from k_llms_b200.utils.consensus_utils import recursive_list_alignments
+    from k_llms_b200.utils.consolidation import _format_consensus_content, _safe_parse_content
+    contents = [_safe_parse_content(t) for t in texts if t]
+    logging.disable(logging.CRITICAL)
+    try:
+        aligned, _ = recursive_list_alignments(contents, "embeddings", raising_embeddings, None, 0.51)
+    finally:
+        logging.disable(logging.NOTSET)
+    value, conf = O.consensus([(d if isinstance(d, dict) else {}) for d in aligned], embed=raising_embeddings)
+    return _format_consensus_content(value), json.dumps(conf)
+
+
+def test_native_json_list_fields():
+    """Records with list fields stay native: the alignment pre-pass (H2) runs on the parsed tree, the merge is element-wise.
+    Checked against the reference's own client-order outputs (goldens) and against the Python pre-pass + oracle."""
+    from k_llms_b200 import _native as K
+    from oracle.gen_golden import _record_candidates, random_list_records
+    from tests.helpers import load_golden
+    from k_llms_b200.utils.consolidation import _format_consensus_content
+    by_n, native = {}, 0
+    for case in load_golden("client_order"):
+        if len(case["values"]) >= 2:
+            by_n.setdefault(len(case["values"]), []).append(([json.dumps(v) for v in case["values"]], case))
+    for n, items in by_n.items():
+        for (texts, case), got in zip(items, K.consolidate_json([t for t, _ in items])):
+            assert got is not None, texts
+            native += 1
+            assert got == (_format_consensus_content(case["value"]), json.dumps(case["conf"])), (texts, got)
+    assert native > 100
+    rng = random.Random(5)
+    recs = [[json.dumps(v) for v in r] for r in random_list_records(77, 400)]
+    for _ in range(200):
+        recs.append([json.dumps(c) for c in _record_candidates(rng, rng.choice([2, 3, 5, 8]), depth=3)])
+    by_n = {}
+    for r in recs:
+        by_n.setdefault(len(r), []).append(r)
+    for n, rs in by_n.items():
+        for texts, got in zip(rs, K.consolidate_json(rs)):
+            assert got is not None and got == _expected_with_lists(texts), texts
 
 
 def test_native_json_matches_reference_client_order():
@@ -192,7 +237,7 @@ def test_native_json_matches_reference_client_order():
 def test_native_json_declines_what_it_cannot_express():
     from k_llms_b200 import _native as K
     long1, long2 = " ".join(["payment"] * 9), " ".join(["transfer"] * 8)
-    recs = [['{"a": {"b": [1]}}', '{"a": {"b": [1]}}'], ['{"a": [1, 2]}', '{"a": [1]}'], ['{"a": "one two three"}', '{"a": 7}'],
+    recs = [['{"a": [1, 2]}', '{"a": {"b": 1}}'], ['{"a": "one two three"}', '{"a": 7}'],
             [json.dumps({"a": long1}), json.dumps({"a": long2})],  # two strings > 50 chars: an embeddings pair
             ['{"a": "caf\\u00e9"}', '{"a": "cafe"}'], ['[1, 2]', '{"a": 1}'], ['', '{"a": 1}'], ['{"a": true}', '{"a": 1}']]
     assert K.consolidate_json(recs) == [None] * len(recs)
@@ -204,7 +249,8 @@ def test_batch_helper_mixes_native_and_python_paths():
     from k_llms_b200.utils.consolidation import consolidate_contents_batch
     records = [
         ['{"a": "x", "n": 5}', '{"a": "X!", "n": 5}', '{"a": "y", "n": 50}'],                 # native
-        ['{"a": {"b": [1, 2]}}', '{"a": {"b": [1, 2]}}', '{"a": {"b": [2, 1]}}'],               # nested + list alignment: Python path
+        ['{"a": {"b": [1, 2]}}', '{"a": {"b": [1, 2]}}', '{"a": {"b": [2, 1]}}'],               # nested + list alignment: native (H2)
+        ['{"a": {"b": 1}}', '{"a": 5}', '{"a": {"b": 1}}'],                                     # object vs scalar under one key: Python path
         ['{"t": "the big cat"}', '{"t": "the big cat"}', '{"t": "the big dog"}'],               # multi-word: medoid on the host
         ['Yes', 'yes', 'No'],
     ]

@@ -24,3 +24,31 @@ def test_two_phase_native_json_matches_client_order_cpu():
             native += 1
             assert got == _expected(texts), texts
     assert native > 600
+
+
+def test_two_phase_native_json_list_records_cpu():
+    """Records with list fields through the native path (H2 alignment on the parsed tree + element-wise merge), the oracle in
+    the kernels' place: the reference's client-order goldens and random list records."""
+    import json
+
+    from oracle.gen_golden import random_list_records
+    from tests.helpers import load_golden
+    from tests.test_gpu_json import _expected_with_lists
+    from k_llms_b200.utils.consolidation import _format_consensus_content
+    by_n, native = {}, 0
+    for case in load_golden("client_order"):
+        if len(case["values"]) >= 2:
+            by_n.setdefault(len(case["values"]), []).append(([json.dumps(v) for v in case["values"]], case))
+    for _n, items in by_n.items():
+        for (texts, case), got in zip(items, consolidate_json_with_oracle([t for t, _ in items])):
+            assert got is not None, texts
+            native += 1
+            assert got == (_format_consensus_content(case["value"]), json.dumps(case["conf"])), (texts, got)
+    assert native > 100
+    recs = [[json.dumps(v) for v in r] for r in random_list_records(78, 200)]
+    by_n = {}
+    for r in recs:
+        by_n.setdefault(len(r), []).append(r)
+    for _n, rs in by_n.items():
+        for texts, got in zip(rs, consolidate_json_with_oracle(rs)):
+            assert got is not None and got == _expected_with_lists(texts), texts
