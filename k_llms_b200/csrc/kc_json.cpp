@@ -31,6 +31,7 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kllms_b200.h"
@@ -1274,24 +1275,37 @@ struct Idx {
 struct ListAligner {
     AlignCtx &cx;
     const std::vector<std::vector<int32_t>> &lists;  // per candidate: node ids of its elements
-    std::vector<std::vector<double>> memo;           // [flat a][flat b], NaN = not computed
+    std::vector<double> dense;                       // [flat a * total + flat b], NaN = not computed (small inputs)
+    std::unordered_map<uint64_t, double> sparse;     // the same for big inputs (only the pairs that are asked for)
     std::vector<int> base;                           // flat index of (li, 0)
+    size_t total = 0;
 
     ListAligner(AlignCtx &c, const std::vector<std::vector<int32_t>> &l) : cx(c), lists(l) {
-        int total = 0;
         for (auto &x : lists) {
-            base.push_back(total);
-            total += (int)x.size();
+            base.push_back((int)total);
+            total += x.size();
         }
-        memo.assign((size_t)total, std::vector<double>((size_t)total, NAN));
+        if (total <= 512) dense.assign(total * total, NAN);
     }
-    double sim(Idx a, Idx b) {  // _PairSims.get (cu:81-106)
-        const size_t fa = (size_t)(base[(size_t)a.li] + a.pos), fb = (size_t)(base[(size_t)b.li] + b.pos);
-        double &m = memo[fa][fb];
-        if (m != m) {
-            m = generic_similarity(cx, &cx.tr.v[(size_t)lists[(size_t)a.li][(size_t)a.pos]], &cx.tr.v[(size_t)lists[(size_t)b.li][(size_t)b.pos]]);
-            memo[fb][fa] = m;
+    double sim(Idx a, Idx b) {  // _PairSims.get (cu:81-106): a symmetric memo
+        size_t fa = (size_t)(base[(size_t)a.li] + a.pos), fb = (size_t)(base[(size_t)b.li] + b.pos);
+        auto compute = [&] {
+            return generic_similarity(cx, &cx.tr.v[(size_t)lists[(size_t)a.li][(size_t)a.pos]], &cx.tr.v[(size_t)lists[(size_t)b.li][(size_t)b.pos]]);
+        };
+        if (!dense.empty()) {
+            double &m = dense[fa * total + fb];
+            if (m != m) {
+                m = compute();
+                dense[fb * total + fa] = m;
+            }
+            return m;
         }
+        if (fa > fb) std::swap(fa, fb);
+        const uint64_t key = ((uint64_t)fa << 32) | (uint64_t)fb;
+        auto it = sparse.find(key);
+        if (it != sparse.end()) return it->second;
+        const double m = compute();
+        sparse.emplace(key, m);
         return m;
     }
 
