@@ -927,7 +927,7 @@ struct ATree {
 
 // json.loads of one value into the tree; false: not valid JSON / non-ASCII / nesting too deep
 bool aparse(Scanner &sc, ATree &tr, int32_t &out, int depth) {
-    if (depth > 64) return false;
+    if (depth > 200) return false;  // the same limit as Scanner::skip_nested: both parsers accept the same texts
     sc.ws();
     if (sc.p >= sc.end) return false;
     const char c = *sc.p;
@@ -1599,7 +1599,11 @@ struct ListAligner {
 
 // recursive_list_alignments (cu:458-613) on the tree: returns the aligned value of every candidate (node id, -1 == None)
 void align_values(AlignCtx &cx, std::vector<int32_t> &values, double min_support_ratio, int depth) {
-    if (values.empty() || depth > 48) return;
+    if (values.empty()) return;
+    if (depth > 100) {  // deeper than any real payload: leave it to the Python pre-pass
+        cx.needs_embeddings = true;
+        return;
+    }
     int first = -1;
     for (int32_t id : values)
         if (id >= 0 && cx.tr.v[(size_t)id].t != A_NONE) {
