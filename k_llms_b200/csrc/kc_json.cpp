@@ -1051,7 +1051,8 @@ constexpr double kSimFloor = 1e-8;  // SIMILARITY_SCORE_LOWER_BOUND, cu:78
 
 struct AlignCtx {
     ATree tr;
-    bool needs_embeddings = false;  // a pair of strings both longer than 50 characters (cu:813): not decidable here
+    bool decline = false;  // not decidable here: a pair of strings both longer than 50 characters (cu:813 asks the embeddings
+                           // service), or nesting beyond the recursion budget -> the record takes the Python path
     std::vector<int32_t> dp;        // edit-distance row
 };
 
@@ -1100,7 +1101,7 @@ bool py_isclose(double a, double b, double rel_tol) {  // math.isclose(a, b, rel
 }
 
 double string_similarity(AlignCtx &cx, const std::string &s1, const std::string &s2) {  // cu:797-824, method "embeddings"
-    if (s1.size() > 50 && s2.size() > 50) cx.needs_embeddings = true;  // the caller gives the record to the Python path
+    if (s1.size() > 50 && s2.size() > 50) cx.decline = true;  // the caller gives the record to the Python path
     thread_local std::string a, b;
     sanitize(s1, a);  // == normalize_string (cu:660-673) on ASCII
     sanitize(s2, b);
@@ -1601,7 +1602,7 @@ struct ListAligner {
 void align_values(AlignCtx &cx, std::vector<int32_t> &values, double min_support_ratio, int depth) {
     if (values.empty()) return;
     if (depth > 100) {  // deeper than any real payload: leave it to the Python pre-pass
-        cx.needs_embeddings = true;
+        cx.decline = true;
         return;
     }
     int first = -1;
@@ -1798,7 +1799,7 @@ void plan_record_tree(const char *const *texts, const int64_t *lens, int n, Reco
         }
     }
     align_values(cx, values, /*min_support_ratio=*/0.51, 0);  // ConsensusSettings default (cu:41); other settings: Python path
-    if (cx.needs_embeddings) {
+    if (cx.decline) {
         rec.status = 1;
         return;
     }
@@ -2004,7 +2005,7 @@ int kc_align_json(const char *const *texts, const int64_t *lens, int32_t n, doub
             if ((unsigned char)texts[c][i] >= 0x80) return 1;
     }
     align_values(cx, values, min_support_ratio, 0);
-    if (cx.needs_embeddings) return 1;
+    if (cx.decline) return 1;
     std::string out;
     for (int32_t c = 0; c < n; ++c) {
         out.clear();
@@ -2026,7 +2027,7 @@ int kc_debug_similarity_json(const char *a, const char *b, double *out) {
     if (sa.p != sa.end || sb.p != sb.end) return KC_EINVAL;
     // pointers into the vector: no insertion happens below
     *out = generic_similarity(cx, &cx.tr.v[(size_t)ia], &cx.tr.v[(size_t)ib]);
-    return cx.needs_embeddings ? 1 : 0;
+    return cx.decline ? 1 : 0;
 }
 
 // scipy.optimize.linear_sum_assignment(cost) restated (test hook): pairs sorted by row; returns their count or -1.
