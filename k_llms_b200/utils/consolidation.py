@@ -58,6 +58,36 @@ def _native_alignment(contents, settings):
     return _native.align_json(contents, settings.min_support_ratio)
 
 
+def _native_settings(settings) -> bool:
+    """The settings the native JSON path (H1, kc_consolidate_json) implements: the reference's defaults."""
+    return (not settings.allow_none_as_candidate and settings.string_similarity_method == "embeddings"
+            and settings.string_consensus_method == "centroid" and settings.min_support_ratio == 0.51)
+
+
+def _consensus_of_choices_native(choices, settings, embed):
+    """The whole per-request path in native code (H1): the n `choice.message.content` texts in -> (consensus value,
+    likelihoods), i.e. parse + alignment pre-pass + vote / numeric / medoid kernels + decode — or None when the request needs
+    the Python path (non-default settings, fewer than two non-empty contents, anything H1 declines; no embeddings callable:
+    the reference raises ValueError for primitive fields then, cu:1445-1446, and so does the Python path)."""
+    from .. import _native
+    if embed is None:
+        return None
+    texts = [c.message.content for c in choices if c.message.content]  # the filter of _contents_of (reference consolidation.py:92)
+    if len(texts) < 2 or len(texts) > _native.MAX_CANDIDATES or not _native_settings(settings):
+        return None
+    out = _native.consolidate_json([texts], settings.rel_eps, settings.abs_eps)[0]
+    if out is None:
+        return None
+    content_text, likelihoods_text = out
+    try:  # undo _format_consensus_content: a consensus that is not a JSON object is the unwrapped {"text": s}
+        value = json.loads(content_text)
+    except ValueError:
+        value = None
+    if not isinstance(value, dict):
+        value = {"text": content_text}
+    return value, json.loads(likelihoods_text)
+
+
 def _consensus_sync(contents, settings, embed, client):
     if len(contents) >= 2:  # reference consolidation.py:96-104
         aligned = _native_alignment(contents, settings)
@@ -108,15 +138,16 @@ def consolidate_chat_completions(
         assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
         if len(completion.choices) == 1:
             return KLLMsChatCompletion.model_validate(completion.model_dump())
-        content, likelihoods = _consensus_sync(_contents_of(completion.choices), consensus_settings,
-                                               get_openai_embeddings_from_text, client)
+        content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, get_openai_embeddings_from_text)
+                                or _consensus_sync(_contents_of(completion.choices), consensus_settings, get_openai_embeddings_from_text, client))
         return _assemble_plain(completion, list(completion.choices), content, likelihoods)
     completion_list = completions
     assert len(completion_list) > 0, "Cannot consolidate empty list of completions"
     if len(completion_list) == 1:
         return KLLMsChatCompletion.model_validate(completion_list[0].model_dump())
     firsts = [c.choices[0] for c in completion_list if c.choices]
-    content, likelihoods = _consensus_sync(_contents_of(firsts), consensus_settings, get_openai_embeddings_from_text, client)
+    content, likelihoods = (_consensus_of_choices_native(firsts, consensus_settings, get_openai_embeddings_from_text)
+                            or _consensus_sync(_contents_of(firsts), consensus_settings, get_openai_embeddings_from_text, client))
     return _assemble_plain(completion_list[0], firsts, content, likelihoods)
 
 
@@ -130,8 +161,9 @@ async def async_consolidate_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsChatCompletion.model_validate(completion.model_dump())
-    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                  async_get_openai_embeddings_from_text, client)
+    content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, async_get_openai_embeddings_from_text)
+                            or await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                      async_get_openai_embeddings_from_text, client))
     return _assemble_plain(completion, list(completion.choices), content, likelihoods)
 
 
@@ -172,8 +204,8 @@ def consolidate_parsed_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
-    content, likelihoods = _consensus_sync(_contents_of(completion.choices), consensus_settings,
-                                           get_openai_embeddings_from_text, client)
+    content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, get_openai_embeddings_from_text)
+                            or _consensus_sync(_contents_of(completion.choices), consensus_settings, get_openai_embeddings_from_text, client))
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=True)
 
 
@@ -188,8 +220,9 @@ async def async_consolidate_parsed_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
-    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                  async_get_openai_embeddings_from_text, client)
+    content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, async_get_openai_embeddings_from_text)
+                            or await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                      async_get_openai_embeddings_from_text, client))
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=False)
 
 
@@ -207,9 +240,7 @@ def consolidate_contents_batch(records: List[List[str]], consensus_settings: Con
     from .. import _native
     default_eps = (consensus_settings.rel_eps, consensus_settings.abs_eps)
     native: List[Any] = [None] * len(records)
-    native_settings = (not consensus_settings.allow_none_as_candidate and consensus_settings.string_similarity_method == "embeddings"
-                       and consensus_settings.string_consensus_method == "centroid" and consensus_settings.min_support_ratio == 0.51)
-    if native_settings:
+    if _native_settings(consensus_settings):
         by_n: dict = {}
         for i, texts in enumerate(records):
             if len(texts) >= 2:

@@ -52,3 +52,61 @@ def test_two_phase_native_json_list_records_cpu():
     for _n, rs in by_n.items():
         for texts, got in zip(rs, consolidate_json_with_oracle(rs)):
             assert got is not None and got == _expected_with_lists(texts), texts
+
+
+def test_per_request_client_path_goes_native_cpu(monkeypatch):
+    """consolidate_chat_completions / consolidate_parsed_chat_completions route a request through H1 (default settings): same
+    consensus message, likelihoods and parsed object as the reference's client order — here with the oracle in the kernels'
+    place; other settings and requests without an embeddings callable keep the Python path."""
+    import json
+
+    from openai.types.chat import ChatCompletion, ParsedChatCompletion
+    from pydantic import BaseModel
+
+    from k_llms_b200 import _native as K
+    from k_llms_b200.utils import consolidation as C
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings
+    from oracle.gen_golden import random_list_records
+    from tests.helpers import raising_embeddings
+    from tests.test_gpu_json import _expected_with_lists
+
+    calls = []
+
+    def fake_consolidate_json(records, *a, **k):
+        calls.append(len(records))
+        return consolidate_json_with_oracle(records)
+
+    monkeypatch.setattr(K, "consolidate_json", fake_consolidate_json)
+
+    def completion_of(texts, cls=ChatCompletion):
+        return cls.model_validate({"id": "x", "object": "chat.completion", "created": 0, "model": "m",
+                                   "choices": [{"index": i, "finish_reason": "stop", "message": {"role": "assistant", "content": t}}
+                                               for i, t in enumerate(texts)]})
+
+    payloads = [{"name": "John", "age": 30, "active": True, "city": "Paris", "tags": ["a", "b"]},
+                {"name": "John", "age": 30, "active": True, "city": "paris", "tags": ["b", "a"]},
+                {"name": "Jon", "age": 31, "active": False, "city": "Paris", "tags": ["a", "b", "c"]}]
+    cases = [[json.dumps(p) for p in payloads], ["Yes", "yes", "No"], ["the big cat sat", "the big cat sat", "a big cat sat"]]
+    cases += [[json.dumps(v) for v in r] for r in random_list_records(5, 60)]
+    for texts in cases:
+        out = C.consolidate_chat_completions(completion_of(texts), raising_embeddings, client=None)
+        exp_content, exp_lik = _expected_with_lists(texts)
+        assert out.choices[0].message.content == exp_content and json.dumps(out.likelihoods) == exp_lik, texts
+        assert [c.message.content for c in out.choices[1:]] == texts
+    assert len(calls) == len(cases)
+
+    class Person(BaseModel):
+        name: str
+        age: float
+        active: bool
+        city: str
+        tags: list
+
+    out = C.consolidate_parsed_chat_completions(completion_of(cases[0], ParsedChatCompletion), raising_embeddings, None,
+                                                response_format=Person)
+    assert out.choices[0].message.parsed == Person(name="John", age=30.0, active=True, city="Paris", tags=["a", "b"])
+    # non-default settings and a missing embeddings callable do not take the native route
+    n_calls = len(calls)
+    assert C._consensus_of_choices_native(completion_of(cases[0]).choices, ConsensusSettings(min_support_ratio=0.6), raising_embeddings) is None
+    assert C._consensus_of_choices_native(completion_of(cases[0]).choices, ConsensusSettings(), None) is None
+    assert len(calls) == n_calls
