@@ -6,6 +6,7 @@ near-identical bodies there share one implementation here.  The consensus itself
 """
 from __future__ import annotations
 
+import asyncio
 import json
 from typing import Any, List, Optional, Union
 
@@ -161,9 +162,10 @@ async def async_consolidate_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsChatCompletion.model_validate(completion.model_dump())
-    content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, async_get_openai_embeddings_from_text)
-                            or await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                      async_get_openai_embeddings_from_text, client))
+    native = await asyncio.to_thread(_consensus_of_choices_native, completion.choices, consensus_settings,
+                                     async_get_openai_embeddings_from_text)  # off the event loop: it waits for the GPU
+    content, likelihoods = native or await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                            async_get_openai_embeddings_from_text, client)
     return _assemble_plain(completion, list(completion.choices), content, likelihoods)
 
 
@@ -220,9 +222,10 @@ async def async_consolidate_parsed_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
-    content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, async_get_openai_embeddings_from_text)
-                            or await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                      async_get_openai_embeddings_from_text, client))
+    native = await asyncio.to_thread(_consensus_of_choices_native, completion.choices, consensus_settings,
+                                     async_get_openai_embeddings_from_text)
+    content, likelihoods = native or await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                            async_get_openai_embeddings_from_text, client)
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=False)
 
 
