@@ -110,3 +110,43 @@ def test_per_request_client_path_goes_native_cpu(monkeypatch):
     assert C._consensus_of_choices_native(completion_of(cases[0]).choices, ConsensusSettings(min_support_ratio=0.6), raising_embeddings) is None
     assert C._consensus_of_choices_native(completion_of(cases[0]).choices, ConsensusSettings(), None) is None
     assert len(calls) == n_calls
+
+
+def test_two_phase_native_json_mutated_texts_cpu():
+    """Candidate texts with random byte edits (broken JSON, stray tokens, escapes, non-ASCII): whatever the native path
+    accepts must equal the reference's client order; the rest it must decline."""
+    import json
+
+    from oracle.gen_golden import _record_candidates, random_list_records
+    from tests.test_gpu_json import _expected_with_lists
+    rng = random.Random(7)
+    alphabet = '{}[]",:0123456789.eE-+ntf \\n\\t\\\\u00e9abcxyz'
+
+    def mutate(text):
+        chars = list(text)
+        for _ in range(rng.randrange(1, 4)):
+            if not chars:
+                break
+            i, r = rng.randrange(len(chars)), rng.random()
+            if r < 0.4:
+                chars[i] = rng.choice(alphabet)
+            elif r < 0.7:
+                del chars[i]
+            else:
+                chars.insert(i, rng.choice(alphabet))
+        return "".join(chars)
+
+    src = [[json.dumps(v) for v in r] for r in random_list_records(21, 150)]
+    src += [[json.dumps(x) for x in _record_candidates(rng, rng.choice([2, 3, 5]), depth=2)] for _ in range(100)]
+    by_n = {}
+    for texts in src:
+        texts = [mutate(t) if rng.random() < 0.4 else t for t in texts]
+        if all(texts):
+            by_n.setdefault(len(texts), []).append(texts)
+    native = 0
+    for _n, rs in by_n.items():
+        for texts, got in zip(rs, consolidate_json_with_oracle(rs)):
+            if got is not None:
+                native += 1
+                assert got == _expected_with_lists(texts), texts
+    assert native > 150
