@@ -271,6 +271,55 @@ int kc_consolidate_json(const char *const *texts, const int64_t *lens, int64_t n
                         uint8_t *out_status);
 void kc_free_strings(char **arr, int64_t count);
 
+/*
+ * H1g — the same consolidation with the JSON work ON THE DEVICE (k_llms_b200/csrc/kc_jsongpu.cuh): the candidate texts are
+ * copied to the GPU as they are; kernels scan them (json.loads, consolidation.py:25-38), sort and check the keys (the dict part
+ * of recursive_list_alignments, consensus_utils.py:516-548), type the fields (dispatcher :1376-1454), build K1 cells by
+ * sanitised equality (sanitize_value :925-933) and K2 cells by exact decimal -> float64 conversion, run K1 / K2, and write the
+ * consensus and likelihoods texts (json.dumps, consolidation.py:41-60; float.__repr__ by shortest-digits conversion).  The host
+ * only moves bytes.  Records the device path does not model exactly (escapes, non-ASCII, nested values / lists, candidates with
+ * different key sequences, multi-word strings, NaN / Infinity, > 19 significant digits, ...) are consolidated by the host path
+ * (kc_consolidate_json) inside the same call; what that declines too is left to the caller's Python path.
+ *   h_text   all candidate texts back to back (ideally page-locked: kc_host_alloc)
+ *   h_off    int64[n_records * n + 1]  candidate c of record r is h_text[h_off[r*n+c] .. h_off[r*n+c+1])  (record-major)
+ *   flags    KC_JSON_DEVICE_ONLY: skip the host path (declined records keep status 1)
+ *   *out     result handle: one text blob + per-record spans (kc_json_result_view), released with kc_json_result_free
+ * status per record: 0 = consolidated on the device, 2 = consolidated by the host path, 1 = needs the Python path.
+ * Texts are byte-identical to the reference's json.dumps output.  Re-entrant (pooled per-call streams and buffers).
+ */
+#define KC_JSON_DEVICE_ONLY 1u
+typedef struct kc_json_result kc_json_result;
+typedef struct {
+    int64_t n_records, n_device, n_host, n_python; /* where the records were consolidated */
+    int64_t input_bytes, output_bytes;
+    int32_t chunks, streams;
+    /* device time by stage, summed over the chunks (CUDA events on each chunk's stream; chunks overlap, so the sum of the
+     * stages can exceed the wall time) */
+    double h2d_ms, plan_ms /* A0 + A1: scan, type, encode */, kernel_ms /* K1 + K2 */, emit_ms /* C0 + C1 */, d2h_ms;
+    double device_path_wall_ms, host_path_wall_ms, wall_ms;
+} kc_json_stats;
+int kc_consolidate_json_packed(const char *h_text, const int64_t *h_off, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
+                               int device, int32_t threads, uint32_t flags, kc_json_result **out);
+/* record r: content = text[content_off[r] .. +content_len[r]), likelihoods likewise; `why` = the device path's reason code for
+ * declining (0 = not declined; kc_jsoncore.cuh D_*).  Pointers stay valid until kc_json_result_free.  Any output may be NULL. */
+int kc_json_result_view(kc_json_result *res, const char **text, const int64_t **content_off, const int64_t **content_len,
+                        const int64_t **likelihoods_off, const int64_t **likelihoods_len, const uint8_t **status, const uint8_t **why,
+                        kc_json_stats *stats);
+void kc_json_result_free(kc_json_result *res);
+
+/* Test hooks of H1g: the device phases instantiated on the host (same source), in the two-phase shape of kc_json_plan /
+ * kc_json_emit, so the CPU tests can put the oracle in K1 / K2's place.  Not a product path. */
+typedef struct kc_debug_jsongpu kc_debug_jsongpu;
+int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_records, int32_t n, kc_debug_jsongpu **out);
+int kc_debug_jsongpu_inputs(const kc_debug_jsongpu *h, const int8_t **vote_cells, int64_t *n_vote_groups, const double **num_cells,
+                            int64_t *n_num_groups, const uint8_t **status);
+int kc_debug_jsongpu_emit(kc_debug_jsongpu *h, const uint32_t *vote_meta, const double *num_value, const uint32_t *num_meta,
+                          const char **content, const int64_t **content_off, const char **likelihoods, const int64_t **likelihoods_off);
+void kc_debug_jsongpu_free(kc_debug_jsongpu *h);
+int kc_debug_parse_doubles(const char *text, const int64_t *off, int64_t count, double *out, uint8_t *ok);
+int kc_debug_float_reprs(const double *xs, int64_t count, char *out /* [count][32] */, int32_t *lens);
+int kc_debug_round5(const double *xs, int64_t count, double *out);
+
 /* Host helper: unit-cost edit distance of two byte strings (python-Levenshtein `distance`, consensus_utils.py:759),
  * used by the host similarity medoid / list alignment.  -1 on bad arguments. */
 int32_t kc_levenshtein(const char *a, int32_t alen, const char *b, int32_t blen);

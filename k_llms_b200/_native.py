@@ -26,6 +26,8 @@ OUT_LOCAL, OUT_MULTIMEM, OUT_PEERS = 0, 1, 2
 EXPORTS = (
     "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
+    "kc_consolidate_json_packed", "kc_json_result_view", "kc_json_result_free", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
+    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5",
 )
 
 
@@ -90,6 +92,21 @@ def load() -> ctypes.CDLL:
     lib.kc_levenshtein.restype = i32
     lib.kc_free_strings.argtypes = [vp, i64]
     lib.kc_free_strings.restype = None
+    lib.kc_consolidate_json_packed.argtypes = [vp, vp, i64, i32, f64, f64, c.c_int, i32, c.c_uint32, c.POINTER(vp)]
+    lib.kc_json_result_view.argtypes = [vp] + [c.POINTER(vp)] * 7 + [vp]
+    lib.kc_json_result_free.argtypes = [vp]
+    lib.kc_json_result_free.restype = None
+    lib.kc_debug_jsongpu_plan.argtypes = [vp, vp, i64, i32, c.POINTER(vp)]
+    lib.kc_debug_jsongpu_inputs.argtypes = [vp] + [vp] * 5
+    lib.kc_debug_jsongpu_emit.argtypes = [vp, vp, vp, vp] + [c.POINTER(vp)] * 4
+    lib.kc_debug_jsongpu_free.argtypes = [vp]
+    lib.kc_debug_jsongpu_free.restype = None
+    lib.kc_debug_parse_doubles.argtypes = [vp, vp, i64, vp, vp]
+    lib.kc_debug_float_reprs.argtypes = [vp, i64, vp, vp]
+    lib.kc_debug_round5.argtypes = [vp, i64, vp]
+    for name in ("kc_consolidate_json_packed", "kc_json_result_view", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
+                 "kc_debug_jsongpu_emit", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5"):
+        getattr(lib, name).restype = c.c_int
     lib.kc_host_alloc.argtypes = [c.c_uint64]
     lib.kc_host_alloc.restype = vp
     lib.kc_host_free.argtypes = [vp]
@@ -335,3 +352,81 @@ def pinned_empty(shape, dtype):
     import weakref
     weakref.finalize(buf, lib.kc_host_free, ptr)
     return arr
+
+
+class JsonStats(ctypes.Structure):
+    """kc_json_stats (include/kllms_b200.h)."""
+    _fields_ = [(k, ctypes.c_int64) for k in ("n_records", "n_device", "n_host", "n_python", "input_bytes", "output_bytes")] + \
+               [("chunks", ctypes.c_int32), ("streams", ctypes.c_int32)] + \
+               [(k, ctypes.c_double) for k in ("h2d_ms", "plan_ms", "kernel_ms", "emit_ms", "d2h_ms", "device_path_wall_ms",
+                                               "host_path_wall_ms", "wall_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+JSON_DEVICE_ONLY = 1
+
+
+def pack_texts(records, pinned: bool = True):
+    """records: list of lists of n candidate content strings -> (blob uint8 array, off int64 array [R*n+1], n): the packed
+    form kc_consolidate_json_packed takes (blob in page-locked memory when `pinned`)."""
+    import numpy as np
+    R = len(records)
+    n = len(records[0]) if R else 0
+    assert all(len(r) == n for r in records), "every record needs the same number of candidates"
+    enc = [t.encode("utf-8") for r in records for t in r]
+    off = np.zeros(R * n + 1, dtype=np.int64)
+    if enc:
+        np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc)), out=off[1:])
+    total = int(off[-1])
+    blob = pinned_empty((max(total, 1),), np.uint8) if pinned else np.empty(max(total, 1), dtype=np.uint8)
+    if total:
+        blob[:total] = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    return blob, off, n
+
+
+class PackedResult:
+    """View of a kc_json_result: `content(r)` / `likelihoods(r)` are the texts of record r (None when status is 1)."""
+
+    def __init__(self, handle, R):
+        import numpy as np
+        self._h, self.R = handle, R
+        lib = load()
+        ptrs = [ctypes.c_void_p() for _ in range(7)]
+        self.stats = JsonStats()
+        check(lib.kc_json_result_view(handle, *[ctypes.byref(p) for p in ptrs], ctypes.addressof(self.stats)))
+        as_i64 = lambda p: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int64)), shape=(R,)) if R else np.zeros(0, np.int64)  # noqa: E731
+        as_u8 = lambda p: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(R,)) if R else np.zeros(0, np.uint8)  # noqa: E731
+        self._text = ptrs[0].value or 0
+        self.c_off, self.c_len, self.l_off, self.l_len = as_i64(ptrs[1]), as_i64(ptrs[2]), as_i64(ptrs[3]), as_i64(ptrs[4])
+        self.status, self.why = as_u8(ptrs[5]), as_u8(ptrs[6])
+
+    def content(self, r):
+        return None if self.status[r] == 1 else ctypes.string_at(self._text + int(self.c_off[r]), int(self.c_len[r])).decode("ascii")
+
+    def likelihoods(self, r):
+        return None if self.status[r] == 1 else ctypes.string_at(self._text + int(self.l_off[r]), int(self.l_len[r])).decode("ascii")
+
+    def pairs(self):
+        return [None if self.status[r] == 1 else (self.content(r), self.likelihoods(r)) for r in range(self.R)]
+
+    def close(self):
+        if self._h is not None:
+            load().kc_json_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def consolidate_json_packed(blob, off, n, rel_eps: float = 0.03, abs_eps: float = 1e-6, device: int = 0, threads: int = 0,
+                            flags: int = 0) -> PackedResult:
+    """H1g: the JSON-in / JSON-out consolidation with the JSON work on the device (kc_consolidate_json_packed).
+    blob uint8 array of all candidate texts, off int64 [R*n+1]; see pack_texts()."""
+    lib = load()
+    R = (len(off) - 1) // n if n else 0
+    h = ctypes.c_void_p()
+    check(lib.kc_consolidate_json_packed(blob.ctypes.data, off.ctypes.data, R, n, float(rel_eps), float(abs_eps), device, threads,
+                                         flags, ctypes.byref(h)))
+    return PackedResult(h, R)

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/kllms_b200.h"
+#include "kc_internal.h"
 #include "kc_common.cuh"
 #include "kc_extra.cuh"
 #include "kc_medoid.cuh"
@@ -33,6 +34,18 @@ int fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+
+}  // namespace
+
+int kc_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
 
 #define KC_CUDA(call)                                                                                         \
     do {                                                                                                      \

@@ -123,3 +123,49 @@ def consolidate_json_with_oracle(records):
         return res
     finally:
         lib.kc_json_free(h)
+
+
+def jsongpu_with_oracle(records):
+    """The DEVICE JSON path's phases (kc_jsongpu.cuh) instantiated on the host: kc_debug_jsongpu_plan -> the C ORACLE in the
+    place of K1 / K2 -> kc_debug_jsongpu_emit.  Returns (pairs, status): pairs[r] = (content, likelihoods) or None where the
+    device path declines the record (status[r] = its reason code)."""
+    import ctypes as c
+    from k_llms_b200 import _native as K
+    from oracle import columnar as OC
+    lib = K.load()
+    R = len(records)
+    if R == 0:
+        return [], []
+    blob, off, n = K.pack_texts(records, pinned=False)
+    h = c.c_void_p()
+    K.check(lib.kc_debug_jsongpu_plan(blob.ctypes.data, off.ctypes.data, R, n, c.byref(h)))
+    try:
+        vc, nc, st = c.c_void_p(), c.c_void_p(), c.c_void_p()
+        gv, gx = c.c_int64(), c.c_int64()
+        K.check(lib.kc_debug_jsongpu_inputs(h, c.byref(vc), c.byref(gv), c.byref(nc), c.byref(gx), c.byref(st)))
+        status = np.ctypeslib.as_array(c.cast(st, c.POINTER(c.c_uint8)), shape=(R,)).copy()
+        vmeta = np.zeros(max(gv.value, 1), dtype=np.uint32)
+        nvalue, nmeta = np.zeros(max(gx.value, 1), dtype=np.float64), np.zeros(max(gx.value, 1), dtype=np.uint32)
+        if gv.value:
+            codes = np.ctypeslib.as_array(c.cast(vc, c.POINTER(c.c_int8)), shape=(gv.value, n)).astype(np.int32)
+            _, vmeta = OC.vote(codes, None)
+        if gx.value:
+            vals = np.ctypeslib.as_array(c.cast(nc, c.POINTER(c.c_double)), shape=(gx.value, n)).copy()
+            nvalue, nmeta = OC.numeric(vals)
+        pc, po, pl, plo = c.c_void_p(), c.c_void_p(), c.c_void_p(), c.c_void_p()
+        K.check(lib.kc_debug_jsongpu_emit(h, vmeta.ctypes.data, nvalue.ctypes.data, nmeta.ctypes.data, c.byref(pc), c.byref(po),
+                                          c.byref(pl), c.byref(plo)))
+        # a record can still be declined while encoding (number range): re-read the statuses
+        status = np.ctypeslib.as_array(c.cast(st, c.POINTER(c.c_uint8)), shape=(R,)).copy()
+        co = np.ctypeslib.as_array(c.cast(po, c.POINTER(c.c_int64)), shape=(R + 1,))
+        lo = np.ctypeslib.as_array(c.cast(plo, c.POINTER(c.c_int64)), shape=(R + 1,))
+        pairs = []
+        for r in range(R):
+            if status[r]:
+                pairs.append(None)
+            else:
+                pairs.append((c.string_at(pc.value + int(co[r]), int(co[r + 1] - co[r])).decode("ascii"),
+                              c.string_at(pl.value + int(lo[r]), int(lo[r + 1] - lo[r])).decode("ascii")))
+        return pairs, list(status)
+    finally:
+        lib.kc_debug_jsongpu_free(h)
