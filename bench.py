@@ -11,12 +11,18 @@ buffer; --route multimem: NVSwitch multicast stores), --reassembly nccl runs a p
 One JSON line on stdout (rank 0).
 
 value      whole-job records/s, inputs resident in HBM, CUDA events, max over ranks, barrier + synchronize on both sides.
-e2e        same metric through the C-ABI call with HOST buffers (kc_consensus_host: pinned host -> H2D -> K1/K2 -> D2H),
-           timed with CUDA events inside the call (copies included), max over ranks.
+e2e        the reference's unit of work through the C ABI with HOST buffers: n candidate JSON TEXTS per record in (pinned host
+           memory) -> consensus JSON + likelihoods JSON texts out (host memory), kc_consolidate_json_packed (H1g: the JSON
+           work runs on the device), WALL CLOCK around the call, max over ranks; `stages` splits the device time into
+           H2D / plan (scan, type, encode) / kernels (K1 + K2) / emit / D2H.
+e2e_columnar  last round's leg: kc_consensus_host_i8 on pre-encoded pinned int8 / f64 columns (no JSON), CUDA events.
 roofline   dominant kernel: algorithmic bytes / its mean launch time, over MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline  the oracle port of the reference's per-record Python path on the host cores (bounded sample).
---impl reference  times that CPU path alone (the reference is pure Python and cannot travel to the GPU box; the oracle
-           port restates it — DESIGN.md).
+cpu_baseline  the CPU arm on a bounded sample (rank 0, N=1): the SAME boundary as e2e — json.loads of the n candidate texts,
+           alignment pre-pass, consensus, json.dumps — with the oracle port of the reference's Python path (the reference is
+           pure Python and cannot travel to the GPU box; measured in the build container the port is ~1.3x FASTER than the
+           unmodified reference, so the ratio is conservative), on every core the process may use (affinity and cgroup
+           quota); `consensus_only` repeats last round's parse-free variant (Python dicts in, no JSON) for continuity.
+--impl reference  times that CPU path alone.
 """
 from __future__ import annotations
 
@@ -56,12 +62,36 @@ def hbm_peak():
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
 
-def _cpu_worker(args):
-    """Build `count` S32 records as Python candidate dicts (untimed), then time the per-record consensus loop."""
-    seed, count, n = args
+def usable_cores() -> int:
+    """Cores this process may really use: the affinity mask, capped by the cgroup CPU quota (os.cpu_count() ignores both)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+            if q != "max":
+                quota = float(q) / float(per)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                per = float(f.read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
+def _s32_candidate_dicts(count, n, seed):
     import numpy as np  # noqa: F401
     from k_llms_b200 import synth
-    from oracle import consensus_py as O
     codes, none_code, vals = synth.s32_numpy(count, n, seed)
     vocab = ["alpha", "Bravo", "charlie", "DELTA", "echo", "foxtrot", "golf", "Hotel"]
     variants = [lambda w: w, lambda w: w.upper(), lambda w: w.lower() + "!", lambda w: " " + w]
@@ -81,26 +111,52 @@ def _cpu_worker(args):
                 d[f"f{24 + f:02d}"] = None if v != v else (int(v) if f < 6 else float(v))
             cands.append(d)
         records.append(cands)
+    return records
+
+
+def _cpu_worker(args):
+    """Build `count` S32 records (untimed), then time the per-record loop.  mode "json": the reference's unit of work —
+    n candidate TEXTS in, json.loads each (consolidation.py:25-38), alignment pre-pass + consensus (client order,
+    consolidation.py:333-349), json.dumps of the consensus and of the likelihoods.  mode "dicts": consensus only, Python
+    candidate dicts in (no parsing, no alignment, no output text)."""
+    seed, count, n, mode = args
+    import json as _json
+    from oracle import consensus_py as O
+    records = _s32_candidate_dicts(count, n, seed)
     embed = lambda texts: [[0.0] for _ in texts]  # noqa: E731
+    if mode == "json":
+        texts = [[_json.dumps(d) for d in cands] for cands in records]
+        del records
+        t0 = time.perf_counter()
+        for cand_texts in texts:
+            value, conf = O.client_order([_json.loads(t) for t in cand_texts], embed=embed)
+            _json.dumps(value), _json.dumps(conf)
+        return count, time.perf_counter() - t0
     t0 = time.perf_counter()
     for cands in records:
         O.consensus(cands, embed=embed)
     return count, time.perf_counter() - t0
 
 
-def cpu_baseline(n: int, per_worker: int, cores: int):
+def cpu_baseline(n: int, per_worker: int, cores: int, mode: str = "json"):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(20260921 + 2 + 1000 * i, per_worker, n) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(20260921 + 2 + 1000 * i, per_worker, n, mode) for i in range(cores)])
         wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return {"value": total / busy, "unit": "records/s", "cores": cores, "kind": "port",
-            "sample": f"{total} records ({per_worker}/core) of the S32 n={n} workload as Python candidate dicts, "
-                      f"oracle/consensus_py.consensus per record, multiprocessing.Pool({cores}); slowest worker {busy:.1f}s, "
+    what = ("n candidate JSON texts per record -> json.loads -> alignment pre-pass + consensus (oracle/consensus_py.client_order) -> "
+            "json.dumps of consensus and likelihoods" if mode == "json" else
+            "Python candidate dicts -> oracle/consensus_py.consensus (no parsing, no alignment, no output text)")
+    return {"value": total / busy, "unit": "records/s", "cores": cores, "kind": "port", "boundary": mode,
+            "sample": f"{total} records ({per_worker}/worker) of the S32 n={n} workload; {what}; multiprocessing.Pool({cores}) "
+                      f"= usable cores (affinity + cgroup quota; os.cpu_count() says {os.cpu_count()}); slowest worker {busy:.1f}s, "
                       f"wall incl. record construction {wall:.1f}s",
+            "per_core": total / busy / cores,
+            "note": "port of the reference's Python path; in the build container the unmodified reference ran 1.3x SLOWER than this port "
+                    "(892 vs 1181 records/s/core on S32, same outputs)",
             "cpu_model": _cpu_model()}
 
 
@@ -118,20 +174,22 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_worker = max(200, int(args.cpu_records_per_core))
+    cores = usable_cores()
+    per_worker = max(100, int(args.cpu_records_per_core))
     vals = []
     base = None
     for _ in range(max(1, min(args.steps, 3))):  # each step = one bounded sample; keep the whole arm within minutes
-        base = cpu_baseline(args.n, per_worker, cores)
+        base = cpu_baseline(args.n, per_worker, cores, "json")
         vals.append(base["value"])
     value = statistics.median(vals)
     base["value"] = value
+    base["consensus_only"] = cpu_baseline(args.n, per_worker, cores, "dicts")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "records/s", "n_gpus": args.gpus,
             "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * (per_worker * cores) / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "python objects (float64 / str)", "data": "synthetic",
             "config": {"workload": f"S32 schema (16 str-enum + 8 bool + 6 int + 2 float fields), n={args.n}, "
-                                   f"{per_worker * cores} records per step (bounded sample of the 1M-record batch)"},
+                                   f"{per_worker * cores} records per step (bounded sample of the 1M-record batch), JSON texts in -> "
+                                   "consensus + likelihoods JSON texts out (the boundary of the GPU arm's e2e)"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is pure Python and absent on the GPU box; this arm runs the oracle port of its per-record path"}
@@ -325,9 +383,56 @@ def run_gpu_arm(args):
     else:
         win, vmeta, value, nmeta = [torch.cat([sharded.my_views(c)[k] for c in range(chunks)]) for k in range(4)]
 
-    # --- end to end through the host-buffer C-ABI entry (rank-local shard, pinned host memory)
+    # --- end to end, the reference's unit of work: candidate JSON texts (pinned host memory) -> consensus / likelihoods texts
     e2e = None
     if not args.no_e2e:
+        Rj = int(args.e2e_records)
+        jblob, joff = K.s32_texts_packed(Rj, n, 20260921 + 2 + 7919 * rank)  # untimed: the batch a client would hand over
+        res = None
+        for _ in range(2):  # warm-up: staging pools, device buffers, the pinned output blob
+            res = K.consolidate_json_packed(jblob, joff, n, device=local_rank)
+            res.close()
+        e2e_steps = max(1, min(K_steps, args.e2e_steps))
+        barrier()
+        walls, stats = [], None
+        for _ in range(e2e_steps):
+            t0 = time.perf_counter()
+            res = K.consolidate_json_packed(jblob, joff, n, device=local_rank)
+            walls.append((time.perf_counter() - t0) * 1e3)
+            stats = res.stats.as_dict()
+            if _ + 1 < e2e_steps:
+                res.close()
+        barrier()
+        e2e_ms = max_over_ranks(statistics.mean(walls))
+        assert stats["n_device"] == Rj, f"only {stats['n_device']} of {Rj} S32 records stayed on the device path"
+        # the texts must be the reference's: a sample against the oracle's client order (outside the timed region)
+        if rank == 0:
+            import json as _json
+            from oracle import consensus_py as O
+            text = jblob[: int(joff[-1])].tobytes()
+            embed = lambda t: [[0.0] for _ in t]  # noqa: E731
+            for r in range(0, Rj, max(1, Rj // 64)):
+                cands = [_json.loads(text[joff[r * n + c]:joff[r * n + c + 1]]) for c in range(n)]
+                cv, cc = O.client_order(cands, embed=embed)
+                assert (res.content(r), res.likelihoods(r)) == (_json.dumps(cv), _json.dumps(cc)), f"e2e record {r} differs from the oracle"
+        res.close()
+        e2e = {"value": world * Rj / (e2e_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(stats["input_bytes"] + joff.nbytes),
+               "d2h_bytes_per_step": int(stats["output_bytes"] + 17 * Rj), "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "records_per_step_per_gpu": Rj, "json_GBps": world * stats["input_bytes"] / (e2e_ms / 1e3) / 1e9,
+               "timing": "wall clock (time.perf_counter) around the C-ABI call, host buffers in and out",
+               "path": "kc_consolidate_json_packed (C ABI): n candidate JSON texts per record in pinned host memory -> H2D -> scan / key "
+                       "sort / typing / sanitised-equality codes / exact decimal->f64 on the device -> K1 + K2 -> float repr + emit on the "
+                       "device -> D2H: consensus JSON + likelihoods JSON texts in host memory",
+               "stages": {"note": "device time per stage summed over the chunks (CUDA events per chunk; chunks overlap on "
+                                  f"{stats['streams']} streams, so the sum exceeds the wall time)",
+                          "h2d_ms": stats["h2d_ms"], "plan_ms": stats["plan_ms"], "kernel_ms": stats["kernel_ms"],
+                          "emit_ms": stats["emit_ms"], "d2h_ms": stats["d2h_ms"], "chunks": stats["chunks"]},
+               "pcie_floor_ms": stats["input_bytes"] / 55e9 * 1e3}
+        del jblob, joff
+
+    # --- last round's leg for continuity: pre-encoded columns through the host-buffer entry (no JSON)
+    e2e_columnar = None
+    if not args.no_e2e and args.e2e_columnar:
         # compact host cells: votes only need equality inside a group, so int8 codes are lossless (kc_consensus_host_i8)
         h_codes = K.pinned_empty((N, 24, n), np.int8 if args.e2e_cells == "i8" else np.int32)
         h_vals = K.pinned_empty((N, 8, n), np.float64)
@@ -336,23 +441,23 @@ def run_gpu_arm(args):
         h_none = none_code.cpu().numpy()
         out = {"win_code": K.pinned_empty((N, 24), np.int32), "vote_meta": K.pinned_empty((N, 24), np.uint32),
                "value": K.pinned_empty((N, 8), np.float64), "num_meta": K.pinned_empty((N, 8), np.uint32)}
-        e2e_steps = max(1, min(K_steps, args.e2e_steps))
+        col_steps = max(1, min(K_steps, args.e2e_steps))
         for _ in range(2):
             K.consensus_host(h_codes, h_none, h_vals, device=local_rank, out=out)
         barrier()
         ms = []
-        for _ in range(e2e_steps):
+        for _ in range(col_steps):
             r = K.consensus_host(h_codes, h_none, h_vals, device=local_rank, out=out)
             ms.append(r["device_ms"])
         barrier()
-        e2e_ms = max_over_ranks(statistics.mean(ms))
+        col_ms = max_over_ranks(statistics.mean(ms))
         # the host-buffer path must agree with the device-resident one
         assert np.array_equal(out["win_code"].reshape(-1), win.cpu().numpy()), "e2e result differs from device-resident result"
         assert np.array_equal(out["value"].reshape(-1).view(np.uint64), value.cpu().numpy().view(np.uint64))
-        e2e = {"value": world * N / (e2e_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(h_codes.nbytes + h_vals.nbytes),
-               "d2h_bytes_per_step": int(sum(a.nbytes for a in out.values())), "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "path": f"kc_consensus_host{'_i8' if args.e2e_cells == 'i8' else ''} (C ABI): pinned host buffers ({h_codes.dtype} vote cells, "
-                       "f64 numeric cells) -> chunked H2D -> K1/K2 -> D2H on 3 streams, per rank"}
+        e2e_columnar = {"value": world * N / (col_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(h_codes.nbytes + h_vals.nbytes),
+                        "d2h_bytes_per_step": int(sum(a.nbytes for a in out.values())), "ms_per_step": col_ms, "steps": col_steps,
+                        "path": f"kc_consensus_host{'_i8' if args.e2e_cells == 'i8' else ''} (C ABI): PRE-ENCODED pinned host columns "
+                                f"({h_codes.dtype} vote cells, f64 numeric cells; no JSON) -> chunked H2D -> K1/K2 -> D2H on 3 streams, per rank"}
 
     clocks = None
     if sampler is not None:
@@ -378,7 +483,9 @@ def run_gpu_arm(args):
                     "step_frac": (bytes_vote + bytes_num) / ((vote_ms + num_ms) / 1e3) / 1e9 / peak}
         base = None
         if world == 1 and not args.no_cpu:
-            base = cpu_baseline(n, int(args.cpu_records_per_core), os.cpu_count() or 1)
+            cores = usable_cores()
+            base = cpu_baseline(n, int(args.cpu_records_per_core), cores, "json")
+            base["consensus_only"] = cpu_baseline(n, int(args.cpu_records_per_core), cores, "dicts")
         line = {"metric": METRIC, "value": value_rps, "unit": "records/s", "n_gpus": world, "steps": K_steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 codes / f64 values",
                 "data": "synthetic",
@@ -395,7 +502,7 @@ def run_gpu_arm(args):
                                            + ((f"fused into the kernels ({'P2P stores to the peers' if fused.route == 'peers' else 'NVSwitch multicast stores'})")
                                               if fused is not None else "NCCL all-gather"))
                                           if world > 1 else "single GPU"},
-                "e2e": e2e, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
+                "e2e": e2e, "e2e_columnar": e2e_columnar, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
                                  "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
@@ -437,6 +544,8 @@ def main():
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--records", type=int, default=1_000_000, help="records per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-records", type=int, default=1_000_000, help="records per GPU of the JSON-texts e2e leg (8.2 KB of JSON each at n=16)")
+    ap.add_argument("--e2e-columnar", type=int, default=1, help="also run last round's pre-encoded-columns leg (0 to skip)")
     ap.add_argument("--e2e-cells", default="i8", choices=["i8", "i32"], help="host encoding of vote cells for the e2e leg")
     ap.add_argument("--chunks", type=int, default=8, help="N>1, NCCL reassembly: pipeline chunks of compute vs all-gather")
     ap.add_argument("--reassembly", default="auto", choices=["auto", "fused", "nccl"])
@@ -445,7 +554,7 @@ def main():
                          "192 B/record over NVLink) or as the full two words (288 B/record)")
     ap.add_argument("--route", default="peers", choices=["peers", "multimem"],
                     help="fused reassembly: P2P stores to every peer's copy, or one multicast store through the switch")
-    ap.add_argument("--cpu-records-per-core", type=int, default=1500)
+    ap.add_argument("--cpu-records-per-core", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

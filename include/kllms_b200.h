@@ -319,6 +319,9 @@ void kc_debug_jsongpu_free(kc_debug_jsongpu *h);
 int kc_debug_parse_doubles(const char *text, const int64_t *off, int64_t count, double *out, uint8_t *ok);
 int kc_debug_float_reprs(const double *xs, int64_t count, char *out /* [count][32] */, int32_t *lens);
 int kc_debug_round5(const double *xs, int64_t count, double *out);
+/* Bench / test input: n_records records of schema S32 as candidate texts, exactly as json.dumps prints them.
+ * Call with out == NULL to get the offsets (off[n_records*n] = bytes needed), then with a buffer of that size. */
+int kc_debug_s32_texts(uint64_t seed, int64_t n_records, int32_t n, int32_t threads, char *out, int64_t cap, int64_t *off);
 
 /* Host helper: unit-cost edit distance of two byte strings (python-Levenshtein `distance`, consensus_utils.py:759),
  * used by the host similarity medoid / list alignment.  -1 on bad arguments. */

@@ -27,7 +27,7 @@ EXPORTS = (
     "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
     "kc_consolidate_json_packed", "kc_json_result_view", "kc_json_result_free", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
-    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5",
+    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5", "kc_debug_s32_texts",
 )
 
 
@@ -104,6 +104,8 @@ def load() -> ctypes.CDLL:
     lib.kc_debug_parse_doubles.argtypes = [vp, vp, i64, vp, vp]
     lib.kc_debug_float_reprs.argtypes = [vp, i64, vp, vp]
     lib.kc_debug_round5.argtypes = [vp, i64, vp]
+    lib.kc_debug_s32_texts.argtypes = [c.c_uint64, i64, i32, i32, vp, i64, vp]
+    lib.kc_debug_s32_texts.restype = c.c_int
     for name in ("kc_consolidate_json_packed", "kc_json_result_view", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
                  "kc_debug_jsongpu_emit", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5"):
         getattr(lib, name).restype = c.c_int
@@ -430,3 +432,16 @@ def consolidate_json_packed(blob, off, n, rel_eps: float = 0.03, abs_eps: float 
     check(lib.kc_consolidate_json_packed(blob.ctypes.data, off.ctypes.data, R, n, float(rel_eps), float(abs_eps), device, threads,
                                          flags, ctypes.byref(h)))
     return PackedResult(h, R)
+
+
+def s32_texts_packed(n_records: int, n: int, seed: int, pinned: bool = True, threads: int = 0):
+    """Schema S32 as candidate TEXTS in packed form (blob uint8, off int64 [R*n+1]), generated natively
+    (kc_debug_s32_texts: exactly json.dumps' formatting; tests/test_jsongpu_host_logic.py checks that)."""
+    import numpy as np
+    lib = load()
+    off = np.zeros(n_records * n + 1, dtype=np.int64)
+    check(lib.kc_debug_s32_texts(seed, n_records, n, threads, None, 0, off.ctypes.data))
+    total = int(off[-1])
+    blob = pinned_empty((max(total, 1),), np.uint8) if pinned else np.empty(max(total, 1), dtype=np.uint8)
+    check(lib.kc_debug_s32_texts(seed, n_records, n, threads, blob.ctypes.data, total, off.ctypes.data))
+    return blob, off

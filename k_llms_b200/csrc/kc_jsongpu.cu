@@ -694,3 +694,123 @@ int kc_debug_round5(const double *xs, int64_t count, double *out) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- bench / test input: schema S32 as candidate texts
+
+namespace {
+
+struct SplitMix {
+    uint64_t s;
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+// One record of schema S32 (same distribution as k_llms_b200/synth.py): n candidate texts exactly as
+// json.dumps(dict) prints them.  f00-f15 string-enum (8 words, 4 spellings that sanitise alike), f16-f23 bool, f24-f29 int in
+// [1, 1e6), f30-f31 float U(1, 1e4); per field a truth, each candidate copies it w.p. p_agree, then is None w.p. p_none.
+void s32_record(uint64_t seed, int64_t r, int32_t n, kc::js::Sink &o, int64_t *off /* n+1 entries, relative to o.n at entry */) {
+    static const char *vocab[8] = {"alpha", "Bravo", "charlie", "DELTA", "echo", "foxtrot", "golf", "Hotel"};
+    SplitMix g{seed * 0x9E3779B97F4A7C15ull + (uint64_t)r * 0xD1B54A32D192ED03ull + 1};
+    const double p_agree = 0.8, p_none = 0.05;
+    int32_t truth_code[24];
+    double truth_num[8];
+    for (int f = 0; f < 24; ++f) truth_code[f] = (int32_t)(g.uni() * (f < 16 ? 8 : 2));
+    for (int f = 0; f < 8; ++f) truth_num[f] = f < 6 ? (double)(int64_t)(1 + g.uni() * (1e6 - 1)) : 1.0 + g.uni() * (1e4 - 1.0);
+    const int64_t base = o.n;
+    for (int32_t c = 0; c < n; ++c) {
+        off[c] = o.n - base;
+        o.put('{');
+        for (int f = 0; f < 32; ++f) {
+            if (f) o.lit(", ");
+            o.lit("\"f");
+            o.put((uint8_t)('0' + f / 10));
+            o.put((uint8_t)('0' + f % 10));
+            o.lit("\": ");
+            const bool agree = g.uni() < p_agree, none = g.uni() < p_none;
+            if (f < 24) {
+                const int32_t draw = (int32_t)(g.uni() * (f < 16 ? 8 : 2));
+                const int32_t k = agree ? truth_code[f] : draw;
+                if (none) {
+                    o.lit("null");
+                } else if (f >= 16) {
+                    o.lit(k ? "true" : "false");
+                } else {
+                    const char *w = vocab[k];
+                    const int variant = (int)((r + c + f) & 3);
+                    o.put('"');
+                    if (variant == 3) o.put(' ');
+                    for (const char *q = w; *q; ++q) {
+                        char ch = *q;
+                        if (variant == 1 && ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+                        if (variant == 2 && ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
+                        o.put((uint8_t)ch);
+                    }
+                    if (variant == 2) o.put('!');
+                    o.put('"');
+                }
+            } else {
+                const int k = f - 24;
+                const double draw = k < 6 ? (double)(int64_t)(1 + g.uni() * (1e6 - 1)) : 1.0 + g.uni() * (1e4 - 1.0);
+                const double v = agree ? truth_num[k] : draw;
+                if (none) {
+                    o.lit("null");
+                } else if (k < 6) {
+                    char buf[24];
+                    const int len = snprintf(buf, sizeof buf, "%lld", (long long)v);
+                    o.put((const uint8_t *)buf, (uint32_t)len);
+                } else {
+                    kc::js::float_repr(v, o);
+                }
+            }
+        }
+        o.put('}');
+    }
+    off[n] = o.n - base;
+}
+
+}  // namespace
+
+extern "C" int kc_debug_s32_texts(uint64_t seed, int64_t n_records, int32_t n, int32_t threads, char *out, int64_t cap, int64_t *off) {
+    if (n_records < 0 || n < 1 || n > KC_MAX_CANDIDATES || !off) return KC_EINVAL;
+    if (threads <= 0) threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const int64_t R = n_records;
+    const bool write = out != nullptr;
+    // pass 1 (out == NULL): lengths -> off[] (absolute, off[0] = 0); pass 2: the texts, at the offsets pass 1 left in off[]
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{0};
+    auto body = [&] {
+        std::vector<int64_t> rel((size_t)n + 1);
+        for (;;) {
+            const int64_t b = next.fetch_add(1024);
+            if (b >= R) return;
+            const int64_t e = std::min(R, b + 1024);
+            for (int64_t r = b; r < e; ++r) {
+                if (!write) {
+                    kc::js::Sink s{nullptr, 0};
+                    s32_record(seed, r, n, s, rel.data());
+                    for (int32_t c = 0; c < n; ++c) off[r * n + c + 1] = rel[(size_t)c + 1] - rel[(size_t)c];  // lengths for now
+                } else {
+                    if (off[(r + 1) * n] > cap) {
+                        bad = 1;
+                        return;
+                    }
+                    kc::js::Sink s{(uint8_t *)out + off[r * n], 0};
+                    s32_record(seed, r, n, s, rel.data());
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(body);
+    for (auto &t : pool) t.join();
+    if (!write) {
+        off[0] = 0;
+        for (int64_t i = 1; i <= R * n; ++i) off[i] += off[i - 1];
+    }
+    return bad ? KC_EINVAL : KC_OK;
+}

@@ -221,3 +221,11 @@ def test_exact_number_conversions_match_cpython():
     out = np.zeros(len(cs))
     K.check(lib.kc_debug_round5(cs.ctypes.data, len(cs), out.ctypes.data))
     assert all(round(float(x), 5) == o for x, o in zip(cs, out))
+
+
+def test_generated_s32_texts_are_json_dumps_output():
+    blob, off = K.s32_texts_packed(300, 5, 9, pinned=False)  # the bench's input generator
+    text = blob.tobytes()
+    for i in range(0, 1500, 7):
+        t = text[off[i]:off[i + 1]].decode()
+        assert json.dumps(json.loads(t)) == t
