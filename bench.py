@@ -247,7 +247,8 @@ def run_gpu_arm(args):
     import torch
     from k_llms_b200 import _native as K
     from k_llms_b200 import synth
-    from k_llms_b200.distributed import FusedShardedConsensus, OutputLayout, ShardedConsensus
+    from k_llms_b200.distributed import (FusedShardedConsensus, OutputLayout, PipelinedShardedConsensus, ShardedConsensus,
+                                         wire_pack_num, wire_pack_votes)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,12 +276,25 @@ def run_gpu_arm(args):
     codes, none_code, vals = synth.s32_torch(N, n, 20260921 + 2 + rank, dev)  # §8d: seed 20260921 + cfg, per-rank shard
     c2, v2 = codes.view(N * 24, n), vals.view(N * 8, n)
     # N > 1, fused P2P route: the gathered vote results travel packed (one word instead of two; full results stay local)
-    packed = world > 1 and args.results == "packed" and args.reassembly in ("auto", "fused") and args.route == "peers"
+    packed = world > 1 and args.results == "packed" and args.reassembly in ("auto", "fused") and args.route in ("peers", "push")
     layout = OutputLayout(N, 24, 8, packed_votes=packed)
     # N > 1: reassembly is fused into the kernels (multimem.st through NVSwitch) when the multicast mapping exists,
     # else the pipelined NCCL all-gather (--reassembly nccl forces it).
     fused = None
-    if world > 1 and args.reassembly in ("auto", "fused"):
+    pipelined = None
+    if world > 1 and args.reassembly in ("auto", "fused") and args.route == "push":
+        # default: full results stay local (fast kernels); a push kernel on a side stream packs chunk c into the wire format
+        # (128 B/record) and stores it into every peer's copy with 16-byte vectors while chunk c + 1 is computed
+        try:
+            pipelined = PipelinedShardedConsensus(N, 24, 8, dev, chunks=args.push_chunks, wide=n > 31, push_ctas=args.push_ctas)
+            if not pipelined.available():
+                pipelined = None
+        except Exception as exc:
+            print(f"pipelined push unavailable: {exc}", file=sys.stderr)
+            pipelined = None
+    if world > 1 and pipelined is None and args.reassembly in ("auto", "fused"):
+        if args.route == "push":
+            args.route = "peers"
         try:
             fused = FusedShardedConsensus(layout, dev, route=args.route)
             if not fused.available():
@@ -294,9 +308,11 @@ def run_gpu_arm(args):
         packed = False
         layout = OutputLayout(N, 24, 8)
     chunks = args.chunks if (world > 1 and fused is None) else 1  # NCCL path: pipeline depth of compute vs all-gather
+    if pipelined is not None:
+        chunks = args.push_chunks
     while N % chunks:
         chunks -= 1
-    sharded = ShardedConsensus(layout, dev, chunks=chunks) if fused is None else None
+    sharded = pipelined if pipelined is not None else (ShardedConsensus(layout, dev, chunks=chunks) if fused is None else None)
     R = N // chunks
     lib = K.load()
     K.check(lib.kc_set_device(local_rank))
@@ -370,6 +386,25 @@ def run_gpu_arm(args):
         g1.record()
         barrier()
         gather_ms = max_over_ranks(g0.elapsed_time(g1) / 5)
+    reassembly_check = None
+    if pipelined is not None:
+        # outside the timed region: EVERY rank's slot on THIS GPU must hold exactly the wire words of that rank's results —
+        # the expected words travel through an NCCL all-gather (an independent route) and are compared bit for bit
+        if pipelined.overflowed():
+            raise RuntimeError("a result does not fit the narrow wire words: rerun with n > 31 semantics (wide)")
+        L = pipelined.layout
+        mine = torch.zeros(L.nbytes, dtype=torch.uint8, device=dev)
+        ev, evalue, en = L.views(mine)
+        wt = torch.int32 if L.wide else torch.int16
+        ev.copy_(torch.from_numpy(wire_pack_votes(pipelined.win.cpu().numpy(), pipelined.vmeta.cpu().numpy().view(np.uint32), L.wide).view(np.int32 if L.wide else np.int16)).to(dev))
+        evalue.copy_(pipelined.value)
+        en.copy_(torch.from_numpy(wire_pack_num(pipelined.nmeta.cpu().numpy().view(np.uint32), L.wide).view(np.int32 if L.wide else np.int16)).to(dev))
+        expect = torch.empty((world, L.nbytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(expect.view(-1), mine)
+        torch.cuda.synchronize()
+        bad = [r for r in range(world) if not torch.equal(expect[r], pipelined.gathered[r])]
+        assert not bad, f"rank {rank}: gathered slots {bad} differ from the NCCL-gathered wire words"
+        reassembly_check = f"every slot of the gathered buffer equals the NCCL all-gather of the ranks' packed results, bit for bit ({world} x {L.nbytes} B per rank)"
     if fused is not None:
         win, vmeta, value, nmeta = fused.rank_views(rank)
         if layout.packed_votes:
@@ -493,21 +528,27 @@ def run_gpu_arm(args):
                                        f"n={n}, p_agree=0.8, p_none=0.05; {world} GPU(s), {world * N} records total",
                            "l2": f"inputs are {(bytes_vote + bytes_num) / 1e9:.2f} GB per step per GPU, > 126 MB L2: no flush needed",
                            "step": "K1 vote + K2 numeric" + ("" if world == 1 else
+                                   (f" in {chunks} chunks; chunk c's results are packed to the wire format (128 B/record) and stored into every "
+                                    "peer's copy by a push kernel (16-byte P2P stores over NVLink) on a side stream while chunk c+1 is "
+                                    "computed + one cross-GPU barrier") if pipelined is not None else
                                    ((" with every result also stored into the peers' copies (P2P over NVLink"
                                      + (", vote results as one packed word: 192 B/record" if layout.packed_votes else ", 288 B/record")
                                      + ") + one cross-GPU barrier" if fused.route == "peers" else
                                      " with results multimem.st-replicated to every GPU through NVSwitch + one cross-GPU barrier")
                                     if fused is not None else " + pipelined NCCL all-gather of the output columns")),
                            "parallelism": (f"records sharded {world}-way; reassembly "
-                                           + ((f"fused into the kernels ({'P2P stores to the peers' if fused.route == 'peers' else 'NVSwitch multicast stores'})")
+                                           + ("by a pipelined push kernel (P2P stores, wire format)" if pipelined is not None else
+                                              (f"fused into the kernels ({'P2P stores to the peers' if fused.route == 'peers' else 'NVSwitch multicast stores'})")
                                               if fused is not None else "NCCL all-gather"))
                                           if world > 1 else "single GPU"},
                 "e2e": e2e, "e2e_columnar": e2e_columnar, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
-                                 "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int(layout.nbytes * world),
-                                 "pipeline_chunks": chunks, "reassembly": ("none" if world == 1 else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
+                                 "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int((pipelined.layout.nbytes if pipelined is not None else layout.nbytes) * world),
+                                 "pipeline_chunks": chunks, "reassembly_check": reassembly_check,
+                                 "bound": ("NVLink ingress of the reassembly: every GPU receives (N-1) x its share" if world > 1 else "HBM"),
+                                 "reassembly": ("none" if world == 1 else "push-wire" + ("32" if pipelined.layout.wide else "16") if pipelined is not None else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
                                                 if fused is not None else "nccl"),
-                                 "nvlink_floor_ms": (world - 1) * layout.nbytes / 770e9 * 1e3 if world > 1 else 0.0}}
+                                 "nvlink_floor_ms": (world - 1) * (pipelined.layout.nbytes if pipelined is not None else layout.nbytes) / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -552,8 +593,11 @@ def main():
     ap.add_argument("--results", default="packed", choices=["packed", "full"],
                     help="N>1 with the fused P2P route: gathered vote results as one packed word (code:18|support:7|present:7, "
                          "192 B/record over NVLink) or as the full two words (288 B/record)")
-    ap.add_argument("--route", default="peers", choices=["peers", "multimem"],
-                    help="fused reassembly: P2P stores to every peer's copy, or one multicast store through the switch")
+    ap.add_argument("--route", default="push", choices=["push", "peers", "multimem"],
+                    help="reassembly without NCCL: push = results stay local, a push kernel packs and stores them into every peer's "
+                         "copy on a side stream (default); peers / multimem = stores fused into K1 / K2 (P2P / NVSwitch multicast)")
+    ap.add_argument("--push-chunks", type=int, default=4, help="route push: chunks of the shard (compute chunk c+1 overlaps the push of chunk c)")
+    ap.add_argument("--push-ctas", type=int, default=0, help="route push: CTAs of the push kernel (0 = 2 per SM)")
     ap.add_argument("--cpu-records-per-core", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -154,6 +154,28 @@ int kc_vote_i32_peers_packed(const int32_t *d_codes, int64_t n_groups, int32_t n
                              const int64_t *peer_delta_bytes, uint32_t *d_overflow, void *stream);
 
 /*
+ * Reassembly of a sharded batch in the WIRE format (k_llms_b200/csrc/kc_push.cuh).  K1 / K2 keep their full results in plain
+ * local arrays (fast local-store kernels); this call packs the results of one chunk of the shard and writes them — as whole
+ * 16-byte vectors — into this rank's slot of a gathered buffer that n_peers other GPUs map as well (symmetric memory), i.e. to
+ * d_wire_* and to d_wire_* + peer_delta_bytes[k] for every peer.  Launched on a second stream for chunk c while chunk c + 1 is
+ * computed, it overlaps the NVLink transfer with the kernels without slowing them down.
+ *   wide == 0 (n <= 31):  vote word u16 code:6 | support:5 | present:5;  numeric: f64 value + u16 kind:2 | payload:10
+ *                         (kind 0 value, payload support | nn<<5;  1 single cell, payload present;  2 no finite value, payload
+ *                         nn | present<<5;  3 no value, payload present) — 128 B per S32 record
+ *   wide == 1:            vote word u32 KC_PACKED_*;  numeric: f64 value + the u32 result word — 224 B per S32 record
+ * A result that does not fit the narrow words (winning code >= 64, a count > 31) sets *d_overflow (device uint32, zeroed by
+ * the caller); the caller repeats the step with wide = 1.  n_vote_groups and n_num_groups must be multiples of 8; every buffer
+ * and every peer_delta_bytes[k] 16-byte aligned.  max_ctas <= 0: twice the SM count.
+ */
+#define KC_WIRE_VOTE16_CODE(w) ((uint32_t)(w) & 63u)
+#define KC_WIRE_VOTE16_SUPPORT(w) (((uint32_t)(w) >> 6) & 31u)
+#define KC_WIRE_VOTE16_PRESENT(w) (((uint32_t)(w) >> 11) & 31u)
+#define KC_WIRE_NUM16_KIND(w) (((uint32_t)(w) >> 10) & 3u)
+int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
+                    const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
+                    int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream);
+
+/*
  * Confidences from result words, bit-exact with Python's round(x, 5) (cu:982,1178,1187,1219):
  *   vote    (numeric == 0): round(pvf * (support / present), 5)          cu:973,982
  *   numeric (numeric == 1): round(support / nn, 5); SINGLE: pvf * (1/present) unrounded (cu:1086,1444)

@@ -21,6 +21,7 @@
 #include "kc_extra.cuh"
 #include "kc_medoid.cuh"
 #include "kc_numeric.cuh"
+#include "kc_push.cuh"
 #include "kc_vote.cuh"
 
 namespace {
@@ -480,6 +481,46 @@ static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, 
     if (n < 16) return launch_vote_direct<16, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
     if (n < 32) return launch_vote_direct<32, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
     return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
+}
+
+int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
+                    const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
+                    int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream) {
+    if (n_vote_groups < 0 || n_num_groups < 0) return fail(KC_EINVAL, "kc_push_results: negative size");
+    if (n_vote_groups % 8 || n_num_groups % 8) return fail(KC_EINVAL, "kc_push_results: group counts must be multiples of 8 (whole 16-byte vectors)");
+    if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_delta_bytes)) return fail(KC_EINVAL, "kc_push_results: n_peers=%d outside [0,7] or NULL deltas", n_peers);
+    if ((n_vote_groups && (!d_win_code || !d_vote_meta || !d_wire_votes)) || (n_num_groups && (!d_value || !d_num_meta || !d_wire_value || !d_wire_num_meta)))
+        return fail(KC_EINVAL, "kc_push_results: NULL buffer");
+    for (const void *p : {(const void *)d_win_code, (const void *)d_vote_meta, (const void *)d_value, (const void *)d_num_meta,
+                          (const void *)d_wire_votes, (const void *)d_wire_value, (const void *)d_wire_num_meta})
+        if (!aligned16(p)) return fail(KC_EINVAL, "kc_push_results: buffers must be 16-byte aligned");
+    if (n_vote_groups == 0 && n_num_groups == 0) return KC_OK;
+    kc::PushArgs a{};
+    a.win = d_win_code;
+    a.vmeta = d_vote_meta;
+    a.gv = n_vote_groups;
+    a.value = d_value;
+    a.nmeta = d_num_meta;
+    a.gx = n_num_groups;
+    a.wire_votes = static_cast<uint8_t *>(d_wire_votes);
+    a.wire_value = static_cast<uint8_t *>(d_wire_value);
+    a.wire_nmeta = static_cast<uint8_t *>(d_wire_num_meta);
+    a.n_peers = n_peers;
+    for (int k = 0; k < n_peers; ++k) {
+        if (peer_delta_bytes[k] % 16 != 0) return fail(KC_EINVAL, "kc_push_results: peer_delta_bytes[%d] is not a multiple of 16", k);
+        a.delta[k] = (long long)peer_delta_bytes[k];
+    }
+    a.wide = wide ? 1 : 0;
+    a.overflow = d_overflow;
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int64_t units = n_vote_groups / (wide ? 4 : 8) + n_num_groups / 2 + n_num_groups / (wide ? 4 : 8);
+    int64_t grid = (units + 255) / 256;
+    grid = std::min<int64_t>(grid, max_ctas > 0 ? max_ctas : info.sm_count * 2);
+    kc::push_kernel<<<(int)std::max<int64_t>(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
 }
 
 int kc_vote_i8(const int8_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,

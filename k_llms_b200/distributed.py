@@ -191,3 +191,190 @@ class FusedShardedConsensus:
         launch(self)
         self.handle.barrier(channel=0)
         return self.gathered
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Wire format + pipelined push (round 2): K1 / K2 keep their full results local; a hand-written copy kernel
+# (kc_push_results, csrc/kc_push.cuh) packs chunk c and stores it into every peer's copy of the gathered buffer with
+# 16-byte vectors on a second stream while chunk c + 1 is computed.
+
+
+@dataclass
+class WireLayout:
+    """One rank's slot of the gathered buffer in the wire format: vote words | numeric values | numeric words.
+    narrow (n <= 31): u16 vote word code:6|support:5|present:5, f64 value, u16 numeric word kind:2|payload:10 — 128 B per
+    S32 record; wide: u32 vote word code:18|support:7|present:7, f64 value, the u32 result word — 224 B per S32 record."""
+    n_records: int
+    n_vote_fields: int
+    n_num_fields: int
+    wide: bool = False
+
+    @property
+    def gv(self) -> int:
+        return self.n_records * self.n_vote_fields
+
+    @property
+    def gx(self) -> int:
+        return self.n_records * self.n_num_fields
+
+    @property
+    def word_bytes(self) -> int:
+        return 4 if self.wide else 2
+
+    @property
+    def off_value(self) -> int:
+        return (self.gv * self.word_bytes + 15) // 16 * 16
+
+    @property
+    def off_nmeta(self) -> int:
+        return self.off_value + self.gx * 8
+
+    @property
+    def nbytes(self) -> int:
+        return (self.off_nmeta + self.gx * self.word_bytes + 15) // 16 * 16
+
+    def views(self, buf):
+        """(vote words, values, numeric words) of one slot (a 1-D uint8 tensor of nbytes)."""
+        import torch
+        wt = torch.int32 if self.wide else torch.int16
+        votes = buf[0:self.gv * self.word_bytes].view(wt)
+        value = buf[self.off_value:self.off_value + self.gx * 8].view(torch.float64)
+        nwords = buf[self.off_nmeta:self.off_nmeta + self.gx * self.word_bytes].view(wt)
+        return votes, value, nwords
+
+
+def wire_pack_votes(win, vmeta, wide: bool):
+    """The wire vote words of full K1 results (numpy int32 win, uint32 meta): what kc_push_results writes."""
+    import numpy as np
+    win = np.asarray(win).astype(np.uint32)
+    m = np.asarray(vmeta).astype(np.uint32)
+    support, present = (m >> 6) & 0x7F, (m >> 20) & 0x7F
+    if wide:
+        return ((win & 0x3FFFF) | (support << 18) | (present << 25)).astype(np.uint32)
+    return ((win & 63) | ((support & 31) << 6) | ((present & 31) << 11)).astype(np.uint16)
+
+
+def wire_pack_num(nmeta, wide: bool):
+    import numpy as np
+    m = np.asarray(nmeta).astype(np.uint32)
+    if wide:
+        return m
+    support, nn, present, flags = (m >> 6) & 0x7F, (m >> 13) & 0x7F, (m >> 20) & 0x7F, m >> 27
+    has, single, nofin = (flags & 1) != 0, (flags & 2) != 0, (flags & 8) != 0
+    w = np.where(has & single, (1 << 10) | (present & 31),
+                 np.where(has, (support & 31) | ((nn & 31) << 5),
+                          np.where(nofin, (2 << 10) | (nn & 31) | ((present & 31) << 5), (3 << 10) | (present & 31))))
+    return w.astype(np.uint16)
+
+
+def wire_confidences(vote_words, num_words, wide: bool):
+    """Confidences a remote consumer derives from the wire words (numpy; pvf = 1): votes round(support / present, 5);
+    numeric by kind (kc_push.cuh).  Returns (vote_conf, num_conf) float64 arrays."""
+    import numpy as np
+    v = np.asarray(vote_words).astype(np.uint32)
+    if wide:
+        vs, vp = (v >> 18) & 0x7F, (v >> 25) & 0x7F
+    else:
+        vs, vp = (v >> 6) & 31, (v >> 11) & 31
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vconf = np.where(vs > 0, np.round(vs / np.maximum(vp, 1), 5), np.where(vp == 0, 1.0, 0.0))
+    w = np.asarray(num_words).astype(np.uint32)
+    if wide:
+        support, nn, present, flags = (w >> 6) & 0x7F, (w >> 13) & 0x7F, (w >> 20) & 0x7F, w >> 27
+        kind = np.where((flags & 1) != 0, np.where((flags & 2) != 0, 1, 0), np.where((flags & 8) != 0, 2, 3))
+    else:
+        kind = (w >> 10) & 3
+        support, nn = w & 31, (w >> 5) & 31
+        present = np.where(kind == 2, (w >> 5) & 31, w & 31)
+        nn = np.where(kind == 2, w & 31, nn)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nconf = np.where(kind == 0, np.round(support / np.maximum(nn, 1), 5),
+                         np.where(kind == 1, 1.0 / np.maximum(present, 1),
+                                  np.where(kind == 2, nn / np.maximum(present, 1), np.where(present == 0, 1.0, 0.0))))
+    return vconf, nconf
+
+
+class PipelinedShardedConsensus:
+    """Default multi-GPU route of round 2.  Per rank: the shard is cut into `chunks` record ranges; K1 / K2 write chunk c's FULL
+    results into plain local arrays (the fast kernels, no routing in their epilogues); a push kernel on a side stream then
+    packs chunk c into the wire format and stores it into this rank's slot of EVERY GPU's copy of the gathered buffer
+    (torch symmetric memory; 16-byte P2P stores over NVLink) while the main stream computes chunk c + 1.  One cross-GPU
+    barrier closes the step.  No NCCL collective on the data path.
+
+    compute(c, views) launches K1 / K2 for chunk c on the current stream; views = (win, vote_meta, value, num_meta) of the
+    chunk (local, full results).  After step(), rank_wire_views(r) gives any rank's wire words on this GPU."""
+
+    def __init__(self, n_records: int, n_vote_fields: int, n_num_fields: int, device, group=None, chunks: int = 4,
+                 wide: bool = False, push_ctas: int = 0):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        assert dist.is_initialized(), "PipelinedShardedConsensus needs an initialised process group"
+        assert n_records % chunks == 0 and (n_records // chunks) % 8 == 0 or chunks == 1, "chunks must cut the shard into multiples of 8 records"
+        self.device, self.chunks, self.push_ctas = device, chunks, push_ctas
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.layout = WireLayout(n_records, n_vote_fields, n_num_fields, wide)
+        self.full = OutputLayout(n_records, n_vote_fields, n_num_fields)
+        self.chunk_records = n_records // chunks
+        self.flat = symm_mem.empty(self.world * self.layout.nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.flat, self.group)
+        self.gathered = self.flat.view(self.world, self.layout.nbytes)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.n_peers = self.world - 1
+        self.peer_deltas = (ctypes.c_int64 * max(self.n_peers, 1))(*[ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank])
+        gv, gx = self.full.gv, self.full.gx
+        self.win = torch.empty(gv, dtype=torch.int32, device=device)
+        self.vmeta = torch.empty(gv, dtype=torch.int32, device=device)
+        self.value = torch.empty(gx, dtype=torch.float64, device=device)
+        self.nmeta = torch.empty(gx, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self.done = [torch.cuda.Event() for _ in range(chunks)]
+        self.pushed = torch.cuda.Event()
+
+    def available(self) -> bool:
+        return 1 <= self.n_peers <= 7
+
+    def my_views(self, c: int = 0):
+        r = self.chunk_records
+        fv, fx = self.full.n_vote_fields, self.full.n_num_fields
+        return (self.win[c * r * fv:(c + 1) * r * fv], self.vmeta[c * r * fv:(c + 1) * r * fv],
+                self.value[c * r * fx:(c + 1) * r * fx], self.nmeta[c * r * fx:(c + 1) * r * fx])
+
+    def rank_wire_views(self, r: int):
+        return self.layout.views(self.gathered[r])
+
+    def push(self, c: int, stream_ptr: int) -> None:
+        """Enqueue the pack + replicate of chunk c on the given stream."""
+        import ctypes
+        from . import _native as K
+        win, vmeta, value, nmeta = self.my_views(c)
+        L = self.layout
+        base = self.flat.data_ptr() + self.rank * L.nbytes
+        r = self.chunk_records
+        g0v, g0x = c * r * L.n_vote_fields, c * r * L.n_num_fields
+        K.check(K.load().kc_push_results(win.data_ptr(), vmeta.data_ptr(), win.numel(), value.data_ptr(), nmeta.data_ptr(), value.numel(),
+                                         base + g0v * L.word_bytes, base + L.off_value + g0x * 8, base + L.off_nmeta + g0x * L.word_bytes,
+                                         1 if L.wide else 0, self.n_peers, ctypes.addressof(self.peer_deltas), self.overflow.data_ptr(),
+                                         self.push_ctas, stream_ptr))
+
+    def step(self, compute: Callable, gather: bool = True):
+        import torch
+        main = torch.cuda.current_stream()
+        for c in range(self.chunks):
+            compute(c, self.my_views(c))
+            if gather:
+                self.done[c].record(main)
+                self.side.wait_event(self.done[c])
+                self.push(c, int(self.side.cuda_stream))
+        if gather:
+            self.pushed.record(self.side)
+            main.wait_event(self.pushed)
+            self.handle.barrier(channel=0)
+        return self.gathered
+
+    def overflowed(self) -> bool:
+        """True if some result did not fit the narrow wire words since construction (rebuild with wide=True).  Synchronises."""
+        return int(self.overflow.item()) != 0
