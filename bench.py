@@ -242,6 +242,32 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- GPU arm
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so that the page-locked host buffers it allocates
+    (first touch) are local to the GPU's PCIe root: with 8 ranks streaming ~50 GB/s each, remote-node memory would put half
+    of the traffic on the socket interconnect.  Returns the node or None (single node / information unavailable)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(gpu_index).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(gpu_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -255,6 +281,7 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned host buffers land on the GPU's own memory node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -282,11 +309,21 @@ def run_gpu_arm(args):
     # else the pipelined NCCL all-gather (--reassembly nccl forces it).
     fused = None
     pipelined = None
+    if args.push_mode == "auto":
+        # measured on this pool (profiles/r2_push_sweep_n{2,8}.txt): at 2 GPUs the step is compute-bound and K1 storing its words
+        # remotely itself while copy engines ship K2's results wins (0.58 ms); from 4 GPUs on the step is NVLink-ingress-bound
+        # and the push kernel's 16-byte stores use the link best (1.67 ms at 8 GPUs vs 2.19 ms for round 1's fused scalar stores)
+        args.push_mode = "hybrid" if world <= 2 else "wire"
+        if args.push_chunks <= 0:
+            args.push_chunks = 1 if world <= 2 else 4
+    if args.push_chunks <= 0:
+        args.push_chunks = 4
     if world > 1 and args.reassembly in ("auto", "fused") and args.route == "push":
         # default: full results stay local (fast kernels); a push kernel on a side stream packs chunk c into the wire format
         # (128 B/record) and stores it into every peer's copy with 16-byte vectors while chunk c + 1 is computed
         try:
-            pipelined = PipelinedShardedConsensus(N, 24, 8, dev, chunks=args.push_chunks, wide=n > 31, push_ctas=args.push_ctas)
+            pipelined = PipelinedShardedConsensus(N, 24, 8, dev, chunks=args.push_chunks, wide=n > 31, push_ctas=args.push_ctas,
+                                                  mode=args.push_mode)
             if not pipelined.available():
                 pipelined = None
         except Exception as exc:
@@ -325,10 +362,16 @@ def run_gpu_arm(args):
         if kernel_events is not None and timing[0]:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
-        K.check(lib.kc_vote_i32(cc.data_ptr(), R * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
+        if pipelined is not None:
+            pipelined.vote(c, cc.data_ptr(), R * 24, n, none_code.data_ptr(), 24, sp)
+        else:
+            K.check(lib.kc_vote_i32(cc.data_ptr(), R * 24, n, none_code.data_ptr(), 24, win.data_ptr(), vmeta.data_ptr(), sp))
         if timing[0]:
             e[1].record()
-        K.check(lib.kc_numeric_f64(vv.data_ptr(), R * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
+        if pipelined is not None:
+            pipelined.numeric(c, vv.data_ptr(), R * 8, n, 0.03, 1e-6, sp)
+        else:
+            K.check(lib.kc_numeric_f64(vv.data_ptr(), R * 8, n, 0.03, 1e-6, value.data_ptr(), nmeta.data_ptr(), sp))
         if timing[0]:
             e[2].record()
             kernel_events.append(e)
@@ -345,9 +388,32 @@ def run_gpu_arm(args):
             e[2].record()
             kernel_events.append(e)
 
+    def compute_numeric(c, views):  # mode hybrid: K2 of the chunk on its own (its values / words then travel by copy engine ...)
+        vv = v2[c * R * 8:(c + 1) * R * 8]
+        if timing[0]:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[2].record()
+            split_events.append(e)
+        pipelined.numeric(c, vv.data_ptr(), R * 8, n, 0.03, 1e-6, sp)
+        if timing[0]:
+            e[3].record()
+
+    def compute_vote(c, views):  # ... while K1 stores its wire words into the peers' copies itself
+        cc = c2[c * R * 24:(c + 1) * R * 24]
+        if timing[0]:
+            e = split_events[-1]
+            e[0].record()
+        pipelined.vote(c, cc.data_ptr(), R * 24, n, none_code.data_ptr(), 24, sp)
+        if timing[0]:
+            e[1].record()
+
+    split_events = []  # (vote start, vote end, numeric start, numeric end) per chunk, hybrid mode
+
     def one_step():
         if fused is not None:
             fused.step(fused_launch)
+        elif pipelined is not None and args.push_mode == "hybrid":
+            pipelined.step(compute, compute_numeric=compute_numeric, compute_vote=compute_vote)
         else:
             sharded.step(compute)
 
@@ -374,6 +440,9 @@ def run_gpu_arm(args):
     ms_step = ms_total / K_steps
     vote_ms = sum(e[0].elapsed_time(e[1]) for e in kernel_events) / K_steps   # per step (all chunks)
     num_ms = sum(e[1].elapsed_time(e[2]) for e in kernel_events) / K_steps
+    if split_events:
+        vote_ms = sum(e[0].elapsed_time(e[1]) for e in split_events) / K_steps
+        num_ms = sum(e[2].elapsed_time(e[3]) for e in split_events) / K_steps
     compute_ms = max_over_ranks(vote_ms + num_ms)
     value_rps = world * N / (ms_step / 1e3)
     gather_ms = 0.0
@@ -544,9 +613,9 @@ def run_gpu_arm(args):
                 "e2e": e2e, "e2e_columnar": e2e_columnar, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int((pipelined.layout.nbytes if pipelined is not None else layout.nbytes) * world),
-                                 "pipeline_chunks": chunks, "reassembly_check": reassembly_check,
+                                 "pipeline_chunks": chunks, "numa_node": numa, "reassembly_check": reassembly_check,
                                  "bound": ("NVLink ingress of the reassembly: every GPU receives (N-1) x its share" if world > 1 else "HBM"),
-                                 "reassembly": ("none" if world == 1 else "push-wire" + ("32" if pipelined.layout.wide else "16") if pipelined is not None else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
+                                 "reassembly": ("none" if world == 1 else f"push-{args.push_mode}-wire" + ("32" if pipelined.layout.wide else "16") if pipelined is not None else (f"fused-{fused.route}" + ("-packed" if layout.packed_votes else ""))
                                                 if fused is not None else "nccl"),
                                  "nvlink_floor_ms": (world - 1) * (pipelined.layout.nbytes if pipelined is not None else layout.nbytes) / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
@@ -596,8 +665,12 @@ def main():
     ap.add_argument("--route", default="push", choices=["push", "peers", "multimem"],
                     help="reassembly without NCCL: push = results stay local, a push kernel packs and stores them into every peer's "
                          "copy on a side stream (default); peers / multimem = stores fused into K1 / K2 (P2P / NVSwitch multicast)")
-    ap.add_argument("--push-chunks", type=int, default=4, help="route push: chunks of the shard (compute chunk c+1 overlaps the push of chunk c)")
+    ap.add_argument("--push-chunks", type=int, default=0, help="route push: chunks of the shard (compute chunk c+1 overlaps the push of chunk c)")
     ap.add_argument("--push-ctas", type=int, default=0, help="route push: CTAs of the push kernel (0 = 2 per SM)")
+    ap.add_argument("--push-mode", default="auto", choices=["auto", "hybrid", "wire", "pack", "dma"],
+                    help="route push: hybrid = K1 stores its wire words into the peers' copies itself, K2's values / words travel by copy engine; "
+                         "wire = K1 writes the wire words locally, a push kernel replicates; pack = the push kernel packs the full results; "
+                         "dma = copy engines replicate the whole slot")
     ap.add_argument("--cpu-records-per-core", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -162,7 +162,7 @@ int kc_vote_i32_peers_packed(const int32_t *d_codes, int64_t n_groups, int32_t n
  *   wide == 0 (n <= 31):  vote word u16 code:6 | support:5 | present:5;  numeric: f64 value + u16 kind:2 | payload:10
  *                         (kind 0 value, payload support | nn<<5;  1 single cell, payload present;  2 no finite value, payload
  *                         nn | present<<5;  3 no value, payload present) — 128 B per S32 record
- *   wide == 1:            vote word u32 KC_PACKED_*;  numeric: f64 value + the u32 result word — 224 B per S32 record
+ *   wide == 1:            vote word u32 KC_PACKED_*;  numeric: f64 value + the u32 result word — 192 B per S32 record
  * A result that does not fit the narrow words (winning code >= 64, a count > 31) sets *d_overflow (device uint32, zeroed by
  * the caller); the caller repeats the step with wide = 1.  n_vote_groups and n_num_groups must be multiples of 8; every buffer
  * and every peer_delta_bytes[k] 16-byte aligned.  max_ctas <= 0: twice the SM count.
@@ -171,6 +171,13 @@ int kc_vote_i32_peers_packed(const int32_t *d_codes, int64_t n_groups, int32_t n
 #define KC_WIRE_VOTE16_SUPPORT(w) (((uint32_t)(w) >> 6) & 31u)
 #define KC_WIRE_VOTE16_PRESENT(w) (((uint32_t)(w) >> 11) & 31u)
 #define KC_WIRE_NUM16_KIND(w) (((uint32_t)(w) >> 10) & 3u)
+/* K1 that also writes the wire word of every group (u16, or u32 when wide) to d_wire_words — this rank's slot of the gathered
+ * buffer — next to the full local result, and (n_peers > 0: fused reassembly) to d_wire_words + peer_delta_bytes[k] in every
+ * peer's copy; with n_peers == 0, kc_push_results(d_win_code = NULL, ...) replicates the words afterwards.  K2 needs no twin:
+ * point its d_value into the slot and pass the same pointer as d_value and d_wire_value to kc_push_results. */
+int kc_vote_i32_wire(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                     int32_t *d_win_code, uint32_t *d_meta, void *d_wire_words, int32_t wide, int32_t n_peers,
+                     const int64_t *peer_delta_bytes, uint32_t *d_overflow, void *stream);
 int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
                     const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
                     int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream);

@@ -138,11 +138,12 @@ __device__ __forceinline__ int4 ldg_nc_v4(const void *p) {
 //             consumer needs for the value and its confidence, goes to `packed` (local + peers): 4 instead of 8 bytes per
 //             vote field over NVLink.  A winning code >= 2^18 sets *overflow (the caller then falls back to PEERS).
 struct OutRoute {
-    uint32_t mode;       // KC_OUT_LOCAL / KC_OUT_MULTIMEM / KC_OUT_PEERS / 3 = PEERS_PACKED
+    uint32_t mode;       // KC_OUT_LOCAL / KC_OUT_MULTIMEM / KC_OUT_PEERS / 3 = PEERS_PACKED / 4 = WIRE (full result + local wire word, kc_push.cuh)
     int32_t n_peers;     // PEERS*, only
     long long delta[7];  // byte offsets local address -> the same address in peer k's mapping
     uint32_t *packed;    // PEERS_PACKED: local address (inside the shared buffer) of the packed vote words
-    uint32_t *overflow;  // PEERS_PACKED: device flag
+    uint32_t *overflow;  // PEERS_PACKED / WIRE: device flag
+    uint32_t wire_wide;  // WIRE (mode 4): 0 = u16 words code:6|support:5|present:5, 1 = u32 words code:18|support:7|present:7
     __host__ __device__ bool local() const { return mode == 0; }
 };
 
@@ -173,6 +174,25 @@ __device__ __forceinline__ void store_out_u32(void *p, uint32_t v, const OutRout
 }
 // K1's two result words of group g, routed
 __device__ __forceinline__ void store_vote_result(int32_t *win, uint32_t *meta, int64_t g, int32_t w, uint32_t m, const OutRoute &r) {
+    if (r.mode == 4u) {  // full result locally + the wire word in this rank's slot (a push kernel replicates the slot)
+        store_local_u32(win + g, (uint32_t)w);
+        store_local_u32(meta + g, m);
+        const uint32_t support = (m >> 6) & 0x7Fu, present = (m >> 20) & 0x7Fu;
+        if (r.wire_wide) {
+            if (support != 0 && (uint32_t)w >= (1u << 18)) atomicOr(r.overflow, 1u);
+            const uint32_t word = ((uint32_t)w & 0x3FFFFu) | (support << 18) | (present << 25);
+            store_local_u32(r.packed + g, word);
+            if (r.n_peers) store_peers_u32(r.packed + g, word, r);
+        } else {
+            if (support > 31u || present > 31u || (support != 0 && (uint32_t)w > 63u)) atomicOr(r.overflow, 1u);
+            const uint16_t word = (uint16_t)(((uint32_t)w & 63u) | ((support & 31u) << 6) | ((present & 31u) << 11));
+            uint16_t *p = reinterpret_cast<uint16_t *>(r.packed) + g;
+            asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"(word) : "memory");
+            for (int k = 0; k < r.n_peers; ++k)  // fused reassembly: a warp's 32 words are one 64-byte store per peer
+                asm volatile("st.global.u16 [%0], %1;" ::"l"(reinterpret_cast<char *>(p) + r.delta[k]), "h"(word) : "memory");
+        }
+        return;
+    }
     if (r.mode != 3u) {
         store_out_u32(win + g, (uint32_t)w, r);
         store_out_u32(meta + g, m, r);

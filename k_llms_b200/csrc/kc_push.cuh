@@ -17,10 +17,10 @@
 namespace kc {
 
 struct PushArgs {
-    const int32_t *win;     // K1 results of the chunk (local, full)
+    const int32_t *win;     // K1 results of the chunk (local, full); NULL: K1 already wrote the wire words (kc_vote_i32_wire)
     const uint32_t *vmeta;
     int64_t gv;
-    const double *value;    // K2 results of the chunk (local, full)
+    const double *value;    // K2 results of the chunk (local, full); == wire_value: K2 wrote its values straight into the slot
     const uint32_t *nmeta;
     int64_t gx;
     uint8_t *wire_votes;    // local addresses of the chunk's part of this rank's slot in the gathered buffer
@@ -40,9 +40,12 @@ __device__ __forceinline__ uint4 ld_v4(const void *p) {
 __device__ __forceinline__ void st_v4(void *p, uint4 v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_peers(uint8_t *p, uint4 v, const PushArgs &a) {
+    for (int k = 0; k < a.n_peers; ++k) st_v4(p + a.delta[k], v);
+}
 __device__ __forceinline__ void st_all(uint8_t *p, uint4 v, const PushArgs &a) {
     st_v4(p, v);
-    for (int k = 0; k < a.n_peers; ++k) st_v4(p + a.delta[k], v);
+    st_peers(p, v, a);
 }
 
 __host__ __device__ __forceinline__ uint32_t wire_vote16(int32_t win, uint32_t meta, uint32_t &bad) {
@@ -70,12 +73,19 @@ __host__ __device__ __forceinline__ uint32_t wire_num16(uint32_t meta, uint32_t 
 // One 16-byte output vector per thread and round; the three segments of the chunk are walked with one flat index.
 __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushArgs a) {
     const int64_t per_v = a.wide ? 4 : 8;                 // vote results per vector
-    const int64_t uv = a.gv / per_v, ux = a.gx / 2, um = a.wide ? a.gx / 4 : a.gx / 8;
+    // segments with nothing to do (already in the slot and no peer to copy to) are skipped
+    const int64_t uv = (!a.win && a.n_peers == 0) ? 0 : a.gv / per_v;
+    const int64_t ux = (reinterpret_cast<const uint8_t *>(a.value) == a.wire_value && a.n_peers == 0) ? 0 : a.gx / 2;
+    const int64_t um = a.wide ? a.gx / 4 : a.gx / 8;
     const int64_t total = uv + ux + um, stride = (int64_t)gridDim.x * blockDim.x;
     uint32_t bad = 0;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
         if (u < uv) {
             uint4 o;
+            if (!a.win) {
+                st_peers(a.wire_votes + u * 16, ld_v4(a.wire_votes + u * 16), a);
+                continue;
+            }
             if (a.wide) {
                 const uint4 w = ld_v4(a.win + u * 4), m = ld_v4(a.vmeta + u * 4);
                 o.x = wire_vote32((int32_t)w.x, m.x, bad);
@@ -93,7 +103,9 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
             st_all(a.wire_votes + u * 16, o, a);
         } else if (u < uv + ux) {
             const int64_t k = u - uv;
-            st_all(a.wire_value + k * 16, ld_v4(a.value + k * 2), a);
+            const uint4 v = ld_v4(a.value + k * 2);
+            if (reinterpret_cast<const uint8_t *>(a.value) == a.wire_value) st_peers(a.wire_value + k * 16, v, a);
+            else st_all(a.wire_value + k * 16, v, a);
         } else {
             const int64_t k = u - uv - ux;
             uint4 o;

@@ -483,13 +483,29 @@ static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, 
     return launch_vote_direct<64, false>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
 }
 
+int kc_vote_i32_wire(const int32_t *d_codes, int64_t n_groups, int32_t n, const int32_t *d_none_code, int32_t n_fields,
+                     int32_t *d_win_code, uint32_t *d_meta, void *d_wire_words, int32_t wide, int32_t n_peers,
+                     const int64_t *peer_delta_bytes, uint32_t *d_overflow, void *stream) {
+    if (!d_wire_words || !d_overflow) return fail(KC_EINVAL, "kc_vote_i32_wire: NULL d_wire_words / d_overflow");
+    kc::OutRoute mc{};
+    if (n_peers) {
+        int rc = make_peer_route("kc_vote_i32_wire", n_peers, peer_delta_bytes, mc);
+        if (rc) return rc;
+    }
+    mc.mode = 4u;
+    mc.packed = static_cast<uint32_t *>(d_wire_words);
+    mc.overflow = d_overflow;
+    mc.wire_wide = wide ? 1u : 0u;
+    return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
+}
+
 int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
                     const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
                     int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream) {
     if (n_vote_groups < 0 || n_num_groups < 0) return fail(KC_EINVAL, "kc_push_results: negative size");
     if (n_vote_groups % 8 || n_num_groups % 8) return fail(KC_EINVAL, "kc_push_results: group counts must be multiples of 8 (whole 16-byte vectors)");
     if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_delta_bytes)) return fail(KC_EINVAL, "kc_push_results: n_peers=%d outside [0,7] or NULL deltas", n_peers);
-    if ((n_vote_groups && (!d_win_code || !d_vote_meta || !d_wire_votes)) || (n_num_groups && (!d_value || !d_num_meta || !d_wire_value || !d_wire_num_meta)))
+    if ((n_vote_groups && (((!d_win_code) != (!d_vote_meta)) || !d_wire_votes)) || (n_num_groups && (!d_value || !d_num_meta || !d_wire_value || !d_wire_num_meta)))
         return fail(KC_EINVAL, "kc_push_results: NULL buffer");
     for (const void *p : {(const void *)d_win_code, (const void *)d_vote_meta, (const void *)d_value, (const void *)d_num_meta,
                           (const void *)d_wire_votes, (const void *)d_wire_value, (const void *)d_wire_num_meta})

@@ -305,7 +305,7 @@ class PipelinedShardedConsensus:
     chunk (local, full results).  After step(), rank_wire_views(r) gives any rank's wire words on this GPU."""
 
     def __init__(self, n_records: int, n_vote_fields: int, n_num_fields: int, device, group=None, chunks: int = 4,
-                 wide: bool = False, push_ctas: int = 0):
+                 wide: bool = False, push_ctas: int = 0, mode: str = "wire"):
         import ctypes
         import torch
         import torch.distributed as dist
@@ -324,15 +324,21 @@ class PipelinedShardedConsensus:
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.n_peers = self.world - 1
         self.peer_deltas = (ctypes.c_int64 * max(self.n_peers, 1))(*[ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank])
+        assert mode in ("wire", "pack", "dma", "hybrid")
+        if mode in ("dma", "hybrid"):  # every peer's copy of the gathered buffer as a tensor, for copy-engine transfers
+            self.peer_bufs = {p: self.handle.get_buffer(p, (self.world, self.layout.nbytes), torch.uint8) for p in range(self.world) if p != self.rank}
         gv, gx = self.full.gv, self.full.gx
         self.win = torch.empty(gv, dtype=torch.int32, device=device)
         self.vmeta = torch.empty(gv, dtype=torch.int32, device=device)
-        self.value = torch.empty(gx, dtype=torch.float64, device=device)
+        # K2 writes its values straight into this rank's slot (they travel as they are); K1 writes wire words there too
+        self.value = self.layout.views(self.gathered[self.rank])[1]
         self.nmeta = torch.empty(gx, dtype=torch.int32, device=device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
-        self.side = torch.cuda.Stream(device=device)
+        # high priority: the push kernel's CTAs take the SM slots the compute kernels' first wave frees, ahead of their second wave
+        self.side = torch.cuda.Stream(device=device, priority=-1)
         self.done = [torch.cuda.Event() for _ in range(chunks)]
         self.pushed = torch.cuda.Event()
+        self.mode = mode  # "wire": K1 writes the wire words itself; "pack": the push kernel packs the full K1 results; "dma": copy engines
 
     def available(self) -> bool:
         return 1 <= self.n_peers <= 7
@@ -346,29 +352,94 @@ class PipelinedShardedConsensus:
     def rank_wire_views(self, r: int):
         return self.layout.views(self.gathered[r])
 
-    def push(self, c: int, stream_ptr: int) -> None:
-        """Enqueue the pack + replicate of chunk c on the given stream."""
-        import ctypes
-        from . import _native as K
-        win, vmeta, value, nmeta = self.my_views(c)
+    def _slot_ptrs(self, c: int):
         L = self.layout
         base = self.flat.data_ptr() + self.rank * L.nbytes
         r = self.chunk_records
         g0v, g0x = c * r * L.n_vote_fields, c * r * L.n_num_fields
-        K.check(K.load().kc_push_results(win.data_ptr(), vmeta.data_ptr(), win.numel(), value.data_ptr(), nmeta.data_ptr(), value.numel(),
-                                         base + g0v * L.word_bytes, base + L.off_value + g0x * 8, base + L.off_nmeta + g0x * L.word_bytes,
-                                         1 if L.wide else 0, self.n_peers, ctypes.addressof(self.peer_deltas), self.overflow.data_ptr(),
-                                         self.push_ctas, stream_ptr))
+        return base + g0v * L.word_bytes, base + L.off_value + g0x * 8, base + L.off_nmeta + g0x * L.word_bytes
 
-    def step(self, compute: Callable, gather: bool = True):
+    def vote(self, c: int, codes_ptr: int, n_groups: int, n: int, none_ptr: int, n_fields: int, stream_ptr: int) -> None:
+        """K1 for chunk c: full results into the local arrays (+ the wire words into the slot in mode "wire" / "dma")."""
+        from . import _native as K
+        win, vmeta, _, _ = self.my_views(c)
+        assert win.numel() == n_groups
+        if self.mode == "pack":
+            K.check(K.load().kc_vote_i32(codes_ptr, n_groups, n, none_ptr, n_fields, win.data_ptr(), vmeta.data_ptr(), stream_ptr))
+        else:
+            import ctypes
+            fused = self.mode == "hybrid"  # K1 stores its wire words into the peers' copies itself
+            K.check(K.load().kc_vote_i32_wire(codes_ptr, n_groups, n, none_ptr, n_fields, win.data_ptr(), vmeta.data_ptr(), self._slot_ptrs(c)[0],
+                                              1 if self.layout.wide else 0, self.n_peers if fused else 0,
+                                              ctypes.addressof(self.peer_deltas) if fused else None, self.overflow.data_ptr(), stream_ptr))
+
+    def numeric(self, c: int, vals_ptr: int, n_groups: int, n: int, rel_eps: float, abs_eps: float, stream_ptr: int) -> None:
+        """K2 for chunk c: values straight into the slot, result words into the local array."""
+        from . import _native as K
+        _, _, value, nmeta = self.my_views(c)
+        assert value.numel() == n_groups
+        K.check(K.load().kc_numeric_f64(vals_ptr, n_groups, n, rel_eps, abs_eps, value.data_ptr(), nmeta.data_ptr(), stream_ptr))
+
+    def push(self, c: int, stream_ptr: int) -> None:
+        """Enqueue the replication of chunk c's part of the slot into every peer's copy on the given stream."""
+        import ctypes
+        from . import _native as K
+        win, vmeta, value, nmeta = self.my_views(c)
+        wv, wx, wm = self._slot_ptrs(c)
+        K.check(K.load().kc_push_results(win.data_ptr() if self.mode == "pack" else None, vmeta.data_ptr() if self.mode == "pack" else None,
+                                         win.numel(), value.data_ptr(), nmeta.data_ptr(), value.numel(), wv, wx, wm,
+                                         1 if self.layout.wide else 0, 0 if self.mode in ("dma", "hybrid") else self.n_peers,
+                                         ctypes.addressof(self.peer_deltas), self.overflow.data_ptr(), self.push_ctas, stream_ptr))
+
+    def _dma(self, c: int) -> None:
+        """The copy engines replicate chunk c's slot segments into every peer's copy (no SM work): all three in mode "dma",
+        the two numeric ones in mode "hybrid" (K1 stores its words remotely itself)."""
+        import torch
+        L = self.layout
+        r = self.chunk_records
+        segs = [(c * r * L.n_vote_fields * L.word_bytes, r * L.n_vote_fields * L.word_bytes),
+                (L.off_value + c * r * L.n_num_fields * 8, r * L.n_num_fields * 8),
+                (L.off_nmeta + c * r * L.n_num_fields * L.word_bytes, r * L.n_num_fields * L.word_bytes)]
+        if self.mode == "hybrid":
+            segs = segs[1:]
+        mine = self.gathered[self.rank]
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            dst = self.peer_bufs[p][self.rank]
+            for o, nb in segs:
+                dst[o:o + nb].copy_(mine[o:o + nb], non_blocking=True)
+
+    def step(self, compute: Callable, gather: bool = True, compute_numeric: Optional[Callable] = None, compute_vote: Optional[Callable] = None):
+        """compute(c, views) launches K1 + K2 of chunk c.  Mode "hybrid" wants them separately (compute_numeric, compute_vote):
+        K2 of chunk c first, then the copy engines ship its values / words while K1 of chunk c (which stores its own words into
+        the peers' copies) and K2 of chunk c + 1 run."""
         import torch
         main = torch.cuda.current_stream()
+        if self.mode == "hybrid" and compute_numeric is not None and compute_vote is not None:
+            for c in range(self.chunks):
+                compute_numeric(c, self.my_views(c))
+                if gather:
+                    self.push(c, int(main.cuda_stream))  # packs the numeric words into the slot (no peers: a few microseconds)
+                    self.done[c].record(main)
+                    self.side.wait_event(self.done[c])
+                    with torch.cuda.stream(self.side):
+                        self._dma(c)
+                compute_vote(c, self.my_views(c))
+            if gather:
+                self.pushed.record(self.side)
+                main.wait_event(self.pushed)
+                self.handle.barrier(channel=0)
+            return self.gathered
         for c in range(self.chunks):
             compute(c, self.my_views(c))
             if gather:
                 self.done[c].record(main)
                 self.side.wait_event(self.done[c])
-                self.push(c, int(self.side.cuda_stream))
+                self.push(c, int(self.side.cuda_stream))  # mode "dma": packs the numeric words only (n_peers = 0)
+                if self.mode == "dma":
+                    with torch.cuda.stream(self.side):
+                        self._dma(c)
         if gather:
             self.pushed.record(self.side)
             main.wait_event(self.pushed)
