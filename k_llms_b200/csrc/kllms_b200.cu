@@ -186,18 +186,13 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     const kc::FieldMap fm = make_field_map(none_code, n_fields);
     static const bool prefetch = [] { const char *e = getenv("KC_VOTE_PREFETCH"); return !e || e[0] != '0'; }();
     constexpr bool kCanPrefetch = VEC && NP >= 4 && NP <= 16;
-    if (kCanPrefetch && prefetch) {
-        if (none_code)
-            kc::vote_direct_kernel<NP, VEC, true, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
-        else
-            kc::vote_direct_kernel<NP, VEC, false, kCanPrefetch><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
-    } else if (none_code) {
-        kc::vote_direct_kernel<NP, VEC, true, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
-    } else {
-        kc::vote_direct_kernel<NP, VEC, false, false><<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
-    }
-    KC_CUDA(cudaGetLastError());
-    return KC_OK;
+    auto go = [&](auto kernel) -> int {
+        kernel<<<grid, threads, 0, st>>>(codes, G, n, fm, win, meta, mc);
+        KC_CUDA(cudaGetLastError());
+        return KC_OK;
+    };
+    if (kCanPrefetch && prefetch) return none_code ? go(kc::vote_direct_kernel<NP, VEC, true, kCanPrefetch>) : go(kc::vote_direct_kernel<NP, VEC, false, kCanPrefetch>);
+    return none_code ? go(kc::vote_direct_kernel<NP, VEC, true, false>) : go(kc::vote_direct_kernel<NP, VEC, false, false>);
 }
 
 template <int NP, bool VEC>
@@ -499,9 +494,9 @@ int kc_vote_i32_wire(const int32_t *d_codes, int64_t n_groups, int32_t n, const 
     return vote_i32_routed(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, mc, stream);
 }
 
-int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
-                    const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
-                    int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream) {
+static int fill_push_args(kc::PushArgs &a, const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
+                          const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
+                          int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow) {
     if (n_vote_groups < 0 || n_num_groups < 0) return fail(KC_EINVAL, "kc_push_results: negative size");
     if (n_vote_groups % 8 || n_num_groups % 8) return fail(KC_EINVAL, "kc_push_results: group counts must be multiples of 8 (whole 16-byte vectors)");
     if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_delta_bytes)) return fail(KC_EINVAL, "kc_push_results: n_peers=%d outside [0,7] or NULL deltas", n_peers);
@@ -510,8 +505,7 @@ int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int6
     for (const void *p : {(const void *)d_win_code, (const void *)d_vote_meta, (const void *)d_value, (const void *)d_num_meta,
                           (const void *)d_wire_votes, (const void *)d_wire_value, (const void *)d_wire_num_meta})
         if (!aligned16(p)) return fail(KC_EINVAL, "kc_push_results: buffers must be 16-byte aligned");
-    if (n_vote_groups == 0 && n_num_groups == 0) return KC_OK;
-    kc::PushArgs a{};
+    a = kc::PushArgs{};
     a.win = d_win_code;
     a.vmeta = d_vote_meta;
     a.gv = n_vote_groups;
@@ -528,8 +522,19 @@ int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int6
     }
     a.wide = wide ? 1 : 0;
     a.overflow = d_overflow;
+    return KC_OK;
+}
+
+int kc_push_results(const int32_t *d_win_code, const uint32_t *d_vote_meta, int64_t n_vote_groups, const double *d_value,
+                    const uint32_t *d_num_meta, int64_t n_num_groups, void *d_wire_votes, void *d_wire_value, void *d_wire_num_meta,
+                    int32_t wide, int32_t n_peers, const int64_t *peer_delta_bytes, uint32_t *d_overflow, int32_t max_ctas, void *stream) {
+    kc::PushArgs a;
+    int rc = fill_push_args(a, d_win_code, d_vote_meta, n_vote_groups, d_value, d_num_meta, n_num_groups, d_wire_votes, d_wire_value,
+                            d_wire_num_meta, wide, n_peers, peer_delta_bytes, d_overflow);
+    if (rc) return rc;
+    if (n_vote_groups == 0 && n_num_groups == 0) return KC_OK;
     DeviceInfo info;
-    int rc = device_info(info);
+    rc = device_info(info);
     if (rc) return rc;
     const int64_t units = n_vote_groups / (wide ? 4 : 8) + n_num_groups / 2 + n_num_groups / (wide ? 4 : 8);
     int64_t grid = (units + 255) / 256;

@@ -91,11 +91,11 @@ def main():
 
     if args.sweep:
         wide = n > 31
-        for mode, chunks, ctas in [("wire", 4, 0), ("wire", 4, 148), ("wire", 4, 64), ("wire", 4, 32), ("wire", 4, 16), ("wire", 2, 32), ("wire", 8, 32),
+        for mode, chunks, ctas in [("wire", 4, 0), ("wire", 4, 148), ("wire", 4, 64), ("wire", 4, 32), ("wire", 4, 16), ("wire", 2, 0), ("wire", 2, 32), ("wire", 8, 32),
                                    ("wire", 1, 32), ("pack", 4, 32), ("dma", 4, 0), ("dma", 2, 0), ("dma", 8, 0), ("hybrid", 1, 0), ("hybrid", 2, 0), ("hybrid", 4, 0), ("hybrid", 8, 0)]:
             if N % (chunks * 8):
                 continue
-            if args.short and (mode, chunks, ctas) not in (("wire", 4, 0), ("dma", 2, 0), ("dma", 4, 0), ("hybrid", 1, 0), ("hybrid", 2, 0), ("hybrid", 4, 0)):
+            if args.short and (mode, chunks, ctas) not in (("wire", 4, 0), ("wire", 2, 0), ("hybrid", 1, 0), ("hybrid", 2, 0)):
                 continue
             pipe = PipelinedShardedConsensus(N, 24, 8, dev, chunks=chunks, wide=wide, mode=mode, push_ctas=ctas)
             R = N // chunks
