@@ -578,7 +578,7 @@ def run_gpu_arm(args):
         ach = kernels[dom]["bytes"] / (kernels[dom]["ms"] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"vote": f"kc::vote_*_kernel<{n}>", "numeric": f"kc::numeric_*_kernel<{n}>"}[dom],
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic(dom) if (n == 16 and N == 1_000_000 and chunks == 1) else None,
+                    "traffic": ncu_traffic(dom) if (world == 1 and n == 16 and N == 1_000_000 and chunks == 1) else None,
                     "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full of this workload; bytes per launch)",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
@@ -672,9 +672,11 @@ def main():
                          "wire = K1 writes the wire words locally, a push kernel replicates; pack = the push kernel packs the full results; "
                          "dma = copy engines replicate the whole slot")
     ap.add_argument("--cpu-records-per-core", type=int, default=1000)
+    ap.add_argument("--sweep", default="", help="comma-separated candidate counts, e.g. 2,4,8,16,32,64: one JSON line per n (configs[4])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    args.sweep_push_mode, args.sweep_push_chunks = args.push_mode, args.push_chunks
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world and world == 1 and args.gpus > 1 and args.impl == "b200":
         # convenience: spawn torchrun ourselves when asked for N GPUs outside a launcher
@@ -684,6 +686,13 @@ def main():
     _capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.sweep:
+        # BASELINE configs[4]: one line per n (device-resident step incl. the multi-GPU reassembly; no e2e / CPU legs)
+        args.no_e2e, args.no_cpu = True, True
+        for nn in [int(x) for x in args.sweep.split(",")]:
+            args.n = nn
+            args.push_mode, args.push_chunks = args.sweep_push_mode, args.sweep_push_chunks
+            run_gpu_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -242,6 +242,76 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
     }
 }
 
+// Small rows (n = 2, 4, 8): one group per thread leaves 8-32 bytes in flight per thread and a fixed cost per group that the
+// few cells cannot amortise (round 1: 0.54 / 0.49 / 0.63 of the HBM peak at n = 2 / 4 / 8).  Here a thread owns GPT
+// CONSECUTIVE groups = 64 bytes of cells (the access pattern of the n = 16 kernel: four 16-byte loads per thread, a warp
+// covers 2 KB contiguous), the next 64 bytes are requested before these are processed, and the GPT results leave as 16-byte
+// (GPT >= 4) or 8-byte vectors.  n_groups must be a multiple of GPT (the launcher sends the remainder to vote_direct_kernel).
+template <int NP, int GPT, bool HAS_NC>
+__global__ void __launch_bounds__(256) vote_multi_kernel(const int32_t *__restrict__ codes, int64_t n_units, FieldMap fm,
+                                                         int32_t *__restrict__ win, uint32_t *__restrict__ meta) {
+    static_assert(NP * GPT == 16, "a thread's unit is 64 bytes of cells");
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t f = 0, fstep = 0;
+    if constexpr (HAS_NC) {
+        f = (uint32_t)((u * GPT) % fm.n_fields);
+        fstep = (uint32_t)((stride * GPT) % fm.n_fields);
+    }
+    int32_t raw[16];
+    auto load = [&](int64_t unit, int32_t (&dst)[16]) {
+        const int4 *p = reinterpret_cast<const int4 *>(codes) + unit * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int4 t = ldg_nc_v4(p + q);
+            dst[4 * q + 0] = t.x;
+            dst[4 * q + 1] = t.y;
+            dst[4 * q + 2] = t.z;
+            dst[4 * q + 3] = t.w;
+        }
+    };
+    if (u < n_units) load(u, raw);
+    for (; u < n_units; u += stride) {
+        int32_t nxt[16];
+        if (u + stride < n_units) load(u + stride, nxt);
+        int32_t w[GPT];
+        uint32_t m[GPT];
+#pragma unroll
+        for (int j = 0; j < GPT; ++j) {
+            int32_t x[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) x[i] = raw[j * NP + i];
+            int32_t nc = KC_CODE_NONE;
+            if constexpr (HAS_NC) {
+                uint32_t fj = f + (uint32_t)j;  // consecutive groups are consecutive fields
+                fj = fj >= fm.n_fields ? fm.mod_small(fj) : fj;
+                nc = __ldg(fm.none_code + fj);
+            }
+            vote_core<NP, HAS_NC>(x, row_min<NP>(x), nc, w[j], m[j]);
+        }
+        if constexpr (HAS_NC) {
+            f += fstep;
+            f = f >= fm.n_fields ? f - fm.n_fields : f;
+        }
+        if constexpr (GPT >= 4) {
+#pragma unroll
+            for (int q = 0; q < GPT / 4; ++q) {
+                asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(win + u * GPT + 4 * q), "r"(w[4 * q]), "r"(w[4 * q + 1]),
+                             "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                             : "memory");
+                asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(meta + u * GPT + 4 * q), "r"(m[4 * q]), "r"(m[4 * q + 1]),
+                             "r"(m[4 * q + 2]), "r"(m[4 * q + 3])
+                             : "memory");
+            }
+        } else {
+            asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(win + u * GPT), "r"(w[0]), "r"(w[1]) : "memory");
+            asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(meta + u * GPT), "r"(m[0]), "r"(m[1]) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) raw[i] = nxt[i];
+    }
+}
+
 // ---------------------------------------------------------------- compact cells (int8)
 
 // Votes only need equality INSIDE a group, so a group can always be re-coded with local codes 0..n-1 (< 64): one

@@ -195,6 +195,38 @@ int launch_vote_direct(const int32_t *codes, int64_t G, int n, const int32_t *no
     return none_code ? go(kc::vote_direct_kernel<NP, VEC, true, false>) : go(kc::vote_direct_kernel<NP, VEC, false, false>);
 }
 
+// small rows, local results: GPT consecutive groups per thread (kc::vote_multi_kernel); the remainder (< GPT groups) and every
+// routed mode go through the one-group-per-thread kernel
+template <int NP>
+int launch_vote_multi(const int32_t *codes, int64_t G, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
+                      cudaStream_t st) {
+    constexpr int GPT = 16 / NP;
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const int64_t units = G / GPT;
+    if (units > 0) {
+        const int threads = 256;
+        const int grid = (int)std::min<int64_t>((units + threads - 1) / threads, (int64_t)info.sm_count * 8);
+        const kc::FieldMap fm = make_field_map(none_code, n_fields);
+        if (none_code) kc::vote_multi_kernel<NP, GPT, true><<<grid, threads, 0, st>>>(codes, units, fm, win, meta);
+        else kc::vote_multi_kernel<NP, GPT, false><<<grid, threads, 0, st>>>(codes, units, fm, win, meta);
+        KC_CUDA(cudaGetLastError());
+    }
+    const int64_t done = units * GPT;
+    if (done < G) {  // the last few groups: their field phase continues where the units stopped
+        kc::OutRoute local{};
+        if (!none_code) return launch_vote_direct<NP, true>(codes + done * NP, G - done, NP, nullptr, 1, win + done, meta + done, st, local);
+        // rotate the field table so that group `done` sees its own field first: simplest is one group per launch (< GPT of them)
+        for (int64_t g = done; g < G; ++g) {
+            const int f = (int)(g % n_fields);
+            rc = launch_vote_direct<NP, true>(codes + g * NP, 1, NP, none_code + f, 1, win + g, meta + g, st, local);
+            if (rc) return rc;
+        }
+    }
+    return KC_OK;
+}
+
 template <int NP, bool VEC>
 int launch_vote_i8(const int8_t *codes, int64_t G, int n, const int32_t *none_code, int n_fields, int32_t *win, uint32_t *meta,
                    cudaStream_t st) {
@@ -449,6 +481,12 @@ static int vote_i32_routed(const int32_t *d_codes, int64_t n_groups, int32_t n, 
     if (!aligned16(d_codes)) return fail(KC_EINVAL, "kc_vote_i32: d_codes must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // measured on B200 (profiles/README.md): the direct front-end wins up to n = 16, the TMA pipeline from n = 32
+    static const bool multi = [] { const char *e = getenv("KC_VOTE_MULTI"); return !e || e[0] != '0'; }();
+    if (multi && mc.local() && !force_tma() && (n == 2 || n == 4 || n == 8)) {
+        if (n == 2) return launch_vote_multi<2>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        if (n == 4) return launch_vote_multi<4>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+        return launch_vote_multi<8>(d_codes, n_groups, d_none_code, n_fields, d_win_code, d_meta, st);
+    }
     if (force_direct() || (!force_tma() && n <= 16)) {
         switch (n) {
             case 1: return launch_vote_direct<1, true>(d_codes, n_groups, n, d_none_code, n_fields, d_win_code, d_meta, st, mc);
