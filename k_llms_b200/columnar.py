@@ -34,16 +34,24 @@ _F64_ABSENT = np.array([_native.F64_ABSENT_BITS], dtype=np.uint64).view(np.float
 
 # ----------------------------------------------------------------------------- sanitising (cu:925-933)
 
-try:  # the reference needs `unidecode`; it is optional here (ASCII input never reaches it)
+try:  # a dependency of the package (pyproject.toml), as of the reference (requirements.txt); ASCII input never reaches it
     from unidecode import unidecode as _unidecode  # type: ignore
 except Exception:  # pragma: no cover - depends on the image
     _unidecode = None
 
 
 def _fold_non_ascii(s: str) -> str:
+    """unidecode(s) (cu:931).  Without the Unidecode package the vote classes of non-ASCII text would differ from the
+    reference's ('Straße' / 'Strasse' share a class under unidecode), so this fails loudly instead of guessing — unless
+    KLLMS_B200_ALLOW_NFKD=1 opts into NFKD folding (a documented deviation: combining marks are dropped, ß ø æ CJK are not
+    transliterated)."""
     if _unidecode is not None:
         return _unidecode(s)
-    import unicodedata  # documented deviation: NFKD + drop combining marks when `unidecode` is not installed
+    import os
+    if os.environ.get("KLLMS_B200_ALLOW_NFKD") != "1":
+        raise ImportError("non-ASCII text needs the Unidecode package (a dependency of k_llms_b200, see pyproject.toml) to be "
+                          "sanitised like the reference does; install it, or set KLLMS_B200_ALLOW_NFKD=1 to accept NFKD folding")
+    import unicodedata
     return "".join(ch for ch in unicodedata.normalize("NFKD", s) if not unicodedata.combining(ch))
 
 
@@ -111,9 +119,14 @@ class _ListNode:
 class Plan:
     """Leaf groups of one or many records, ready for one K1, one K2 and one K4 launch."""
 
-    def __init__(self, n: int, allow_none_as_candidate: bool, rel_eps: float, abs_eps: float, host_primitive: Callable):
+    def __init__(self, n: int, allow_none_as_candidate: bool, rel_eps: float, abs_eps: float, host_primitive: Callable,
+                 numeric_branch: bool = True):
         if n > MAX_CANDIDATES:
-            raise NotImplementedError(f"{n} candidates per field: the CUDA path supports at most {MAX_CANDIDATES}")
+            raise ValueError(f"{n} candidates per request: k_llms_b200 consolidates at most {MAX_CANDIDATES} (one kernel row per "
+                             "field holds every candidate; the package has no CPU path to fall back to)")
+        # False: the reference's ASYNC dispatcher, whose primitive has no numeric clustering (cu:1638-1688): numbers take the
+        # similarity medoid like any other non-enum value
+        self.numeric_branch = numeric_branch
         self.n = max(n, 1)
         self.allow_none = allow_none_as_candidate
         self.rel_eps, self.abs_eps = rel_eps, abs_eps
@@ -194,7 +207,7 @@ class Plan:
             numeric_like = isinstance(type(head)(), (int, float))  # cu:1099
         except Exception:
             numeric_like = False
-        if numeric_like or all(isinstance(v, (int, float)) for v in live):
+        if self.numeric_branch and (numeric_like or all(isinstance(v, (int, float)) for v in live)):
             # the kernel applies the None-stripping and len(values) bookkeeping of cu:1444 / cu:1082-1086 itself
             return self._numeric(values, pvf)
         sub = pvf * (len(live) / len(values))  # cu:1444

@@ -21,7 +21,12 @@ _SAMPLING_KEYS = ("temperature", "max_tokens", "top_p", "frequency_penalty", "pr
 _EMBED_MODEL, _EMBED_BATCH = "text-embedding-3-small", 2048
 
 
+MAX_N = 64  # _native.MAX_CANDIDATES: one kernel row per field holds every candidate; there is no CPU path to fall back to
+
+
 def _call_params(base: dict, sampling: dict, n: Optional[int], extra: dict) -> dict:
+    if n is not None and n > MAX_N:  # fail BEFORE the (paid) API call: the n choices could not be consolidated
+        raise ValueError(f"n={n}: k_llms_b200 consolidates at most {MAX_N} candidates per request (README.md, Limits)")
     params = dict(base)
     params.update({k: v for k, v in sampling.items() if v is not None})
     params.update(extra)

@@ -56,8 +56,9 @@ def _host_primitive(settings: ConsensusSettings):
     return run
 
 
-def _plan_for(n: int, settings: ConsensusSettings) -> columnar.Plan:
-    plan = columnar.Plan(n, settings.allow_none_as_candidate, settings.rel_eps, settings.abs_eps, _host_primitive(settings))
+def _plan_for(n: int, settings: ConsensusSettings, numeric_branch: bool = True) -> columnar.Plan:
+    plan = columnar.Plan(n, settings.allow_none_as_candidate, settings.rel_eps, settings.abs_eps, _host_primitive(settings),
+                         numeric_branch=numeric_branch)
     plan.string_method = settings.string_similarity_method if settings.string_consensus_method == "centroid" else "host"
     return plan
 
@@ -68,9 +69,10 @@ def consensus_values(
     sync_get_openai_embeddings_from_text: SYNC_GET_OPENAI_EMBEDDINGS_FROM_TEXT_TYPE,
     client: Any,
     parent_valid_frac: float = 1.0,
+    _numeric_branch: bool = True,
 ) -> Tuple[Any, Any]:
     """(consensus value, confidence) for one record's n candidate values — cu:1376-1454."""
-    plan = _plan_for(len(values), consensus_settings)
+    plan = _plan_for(len(values), consensus_settings, _numeric_branch)
     root = plan.add(values, parent_valid_frac, sync_get_openai_embeddings_from_text)
     res = plan.run() if (plan.vote_rows or plan.num_rows or plan.medoid_groups) else {}
     return plan.materialise(root, res)
@@ -103,8 +105,10 @@ async def async_consensus_values(
     client: Any,
     parent_valid_frac: float = 1.0,
 ) -> Tuple[Any, Any]:
-    """Async twin (cu:1916).  The reference's async path has no numeric clustering and runs
-    its CPU work on the event loop; here both clients share the same GPU backend, off the loop."""
+    """Async twin (cu:1779-1860).  The reference's async primitive has NO numeric clustering (cu:1638-1688):
+    a non-unanimous numeric field takes the similarity medoid — [10, 10, 11] gives (10, 0.5) here and (10.0, 0.66667) in the
+    sync path.  That difference is part of the reference's behaviour and is reproduced; votes still run on the GPU, off the
+    event loop."""
     loop = asyncio.get_running_loop()
 
     def embed(texts):
@@ -113,7 +117,7 @@ async def async_consensus_values(
 
     return await asyncio.to_thread(consensus_values, values, consensus_settings,
                                    embed if async_get_openai_embeddings_from_text is not None else None, client,
-                                   parent_valid_frac)
+                                   parent_valid_frac, False)
 
 
 # ----------------------------------------------------------------------------- alignment pre-pass

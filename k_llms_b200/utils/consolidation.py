@@ -76,7 +76,7 @@ def _consensus_of_choices_native(choices, settings, embed):
     texts = [c.message.content for c in choices if c.message.content]  # the filter of _contents_of (reference consolidation.py:92)
     if len(texts) < 2 or len(texts) > _native.MAX_CANDIDATES or not _native_settings(settings):
         return None
-    out = _native.consolidate_json([texts], settings.rel_eps, settings.abs_eps)[0]
+    out = _native_consolidate([texts], settings.rel_eps, settings.abs_eps)[0]
     if out is None:
         return None
     content_text, likelihoods_text = out
@@ -87,6 +87,26 @@ def _consensus_of_choices_native(choices, settings, embed):
     if not isinstance(value, dict):
         value = {"text": content_text}
     return value, json.loads(likelihoods_text)
+
+
+def _native_consolidate(records, rel_eps, abs_eps, device: int = 0):
+    """records of n candidate texts -> [(content, likelihoods text) or None]: the device JSON path (H1g,
+    kc_consolidate_json_packed: scan / key sort / typing / encode / K1 + K2 / emit on the GPU; re-entrant, pooled streams), which
+    hands what it does not model to the host path (H1, kc_consolidate_json) inside the same call."""
+    from .. import _native
+    blob, off, n = _native.pack_texts(records, pinned=len(records) >= 256)  # page-locking only pays for batches
+    res = _native.consolidate_json_packed(blob, off, n, rel_eps, abs_eps, device)
+    try:
+        return res.pairs()
+    finally:
+        res.close()
+
+
+def _check_candidates(n: int) -> None:
+    from .. import _native
+    if n > _native.MAX_CANDIDATES:
+        raise ValueError(f"{n} candidates in one request: k_llms_b200 consolidates at most {_native.MAX_CANDIDATES} "
+                         "(README.md, Limits)")
 
 
 def _consensus_sync(contents, settings, embed, client):
@@ -139,6 +159,7 @@ def consolidate_chat_completions(
         assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
         if len(completion.choices) == 1:
             return KLLMsChatCompletion.model_validate(completion.model_dump())
+        _check_candidates(len(completion.choices))
         content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, get_openai_embeddings_from_text)
                                 or _consensus_sync(_contents_of(completion.choices), consensus_settings, get_openai_embeddings_from_text, client))
         return _assemble_plain(completion, list(completion.choices), content, likelihoods)
@@ -146,10 +167,17 @@ def consolidate_chat_completions(
     assert len(completion_list) > 0, "Cannot consolidate empty list of completions"
     if len(completion_list) == 1:
         return KLLMsChatCompletion.model_validate(completion_list[0].model_dump())
-    firsts = [c.choices[0] for c in completion_list if c.choices]
-    content, likelihoods = (_consensus_of_choices_native(firsts, consensus_settings, get_openai_embeddings_from_text)
-                            or _consensus_sync(_contents_of(firsts), consensus_settings, get_openai_embeddings_from_text, client))
-    return _assemble_plain(completion_list[0], firsts, content, likelihoods)
+    _check_candidates(len(completion_list))
+    # choices[i + 1] keeps the index of completion i and completion_list[0] lends its head fields (reference consolidation.py:
+    # 176-216); a completion without choices contributes nothing
+    firsts = [(i, c.choices[0]) for i, c in enumerate(completion_list) if c.choices]
+    heads = [c for _, c in firsts]
+    content, likelihoods = (_consensus_of_choices_native(heads, consensus_settings, get_openai_embeddings_from_text)
+                            or _consensus_sync(_contents_of(heads), consensus_settings, get_openai_embeddings_from_text, client))
+    out = _assemble_plain(completion_list[0], heads, content, likelihoods)
+    for k, (i, _) in enumerate(firsts):
+        out.choices[k + 1].index = i + 1
+    return out
 
 
 async def async_consolidate_chat_completions(
@@ -162,10 +190,11 @@ async def async_consolidate_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsChatCompletion.model_validate(completion.model_dump())
-    native = await asyncio.to_thread(_consensus_of_choices_native, completion.choices, consensus_settings,
-                                     async_get_openai_embeddings_from_text)  # off the event loop: it waits for the GPU
-    content, likelihoods = native or await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                            async_get_openai_embeddings_from_text, client)
+    _check_candidates(len(completion.choices))
+    # the native JSON paths implement the SYNC semantics; the reference's async dispatcher differs on numeric fields
+    # (cu:1638-1688: no clustering), so the async entry points plan in Python (async_consensus_values) — votes still on the GPU
+    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                  async_get_openai_embeddings_from_text, client)
     return _assemble_plain(completion, list(completion.choices), content, likelihoods)
 
 
@@ -206,6 +235,7 @@ def consolidate_parsed_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
+    _check_candidates(len(completion.choices))
     content, likelihoods = (_consensus_of_choices_native(completion.choices, consensus_settings, get_openai_embeddings_from_text)
                             or _consensus_sync(_contents_of(completion.choices), consensus_settings, get_openai_embeddings_from_text, client))
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=True)
@@ -222,10 +252,9 @@ async def async_consolidate_parsed_chat_completions(
     assert len(completion.choices) > 0, "Cannot consolidate empty list of choices"
     if len(completion.choices) == 1:
         return KLLMsParsedChatCompletion.model_validate(completion.model_dump())
-    native = await asyncio.to_thread(_consensus_of_choices_native, completion.choices, consensus_settings,
-                                     async_get_openai_embeddings_from_text)
-    content, likelihoods = native or await _consensus_async(_contents_of(completion.choices), consensus_settings,
-                                                            async_get_openai_embeddings_from_text, client)
+    _check_candidates(len(completion.choices))
+    content, likelihoods = await _consensus_async(_contents_of(completion.choices), consensus_settings,
+                                                  async_get_openai_embeddings_from_text, client)
     return _assemble_parsed(completion, content, likelihoods, response_format, keep_usage=False)
 
 
@@ -236,10 +265,11 @@ def consolidate_contents_batch(records: List[List[str]], consensus_settings: Con
     `choice.message.content` strings in -> (consensus content string, likelihoods) out, exactly what the per-request
     functions above put into choices[0] and `likelihoods`.
 
-    Records of scalars, nested objects and lists go through the native path (kc_consolidate_json: C++ parse / alignment
-    pre-pass / encode / decode + K1/K2/K4, no Python objects) when the settings are the ones it implements (the defaults);
-    records it declines (a key mixing objects with other types, string pairs that need the embeddings service, non-ASCII
-    text, ...) take the regular Python + GPU path."""
+    With the default settings the batch goes to the device JSON path (H1g, kc_consolidate_json_packed: the texts are copied to
+    the GPU as they are; scan / key sort / typing / encode / K1 + K2 / emit run there); records that path does not model
+    (nested objects, lists, multi-word strings, escapes, ...) are consolidated by the native host path (H1: C++ parse /
+    alignment pre-pass / encode / decode + K1/K2/K4) inside the same call, and what that declines too (a key mixing objects
+    with other types, string pairs that need the embeddings service, non-ASCII text, ...) takes the Python + GPU path."""
     from .. import _native
     default_eps = (consensus_settings.rel_eps, consensus_settings.abs_eps)
     native: List[Any] = [None] * len(records)
@@ -249,9 +279,8 @@ def consolidate_contents_batch(records: List[List[str]], consensus_settings: Con
             if len(texts) >= 2:
                 by_n.setdefault(len(texts), []).append(i)
         for n, idxs in by_n.items():
-            if n > _native.MAX_CANDIDATES:
-                continue
-            outs = _native.consolidate_json([records[i] for i in idxs], default_eps[0], default_eps[1], device)
+            _check_candidates(n)
+            outs = _native_consolidate([records[i] for i in idxs], default_eps[0], default_eps[1], device)
             for i, o in zip(idxs, outs):
                 native[i] = o
     results = []
@@ -261,9 +290,11 @@ def consolidate_contents_batch(records: List[List[str]], consensus_settings: Con
             results.append((nat[0], json.loads(nat[1])))
             continue
         contents = [_safe_parse_content(t) for t in texts if t]
-        if len(contents) == 1:  # single choice: nothing to consolidate (consolidation.py:85-87)
+        _check_candidates(len(contents))
+        if len(texts) == 1:  # a single choice is returned as it is (reference consolidation.py:85-87)
             results.append((texts[0], None))
             continue
+        # one non-empty content among several choices still goes through consensus_values, like the per-request path
         value, likelihoods = _consensus_sync(contents, consensus_settings, embed, client)
         results.append((_format_consensus_content(value), likelihoods))
     return results

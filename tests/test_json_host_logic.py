@@ -76,7 +76,7 @@ def test_per_request_client_path_goes_native_cpu(monkeypatch):
         calls.append(len(records))
         return consolidate_json_with_oracle(records)
 
-    monkeypatch.setattr(K, "consolidate_json", fake_consolidate_json)
+    monkeypatch.setattr(C, "_native_consolidate", fake_consolidate_json)  # the seam in front of kc_consolidate_json_packed
 
     def completion_of(texts, cls=ChatCompletion):
         return cls.model_validate({"id": "x", "object": "chat.completion", "created": 0, "model": "m",
