@@ -256,11 +256,8 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
                                                               int32_t *__restrict__ win, uint32_t *__restrict__ meta,
                                                               float *__restrict__ weight) {
     using M = typename MaskOf<NP>::type;
-    extern __shared__ float wts[];  // [records of the tile][NP], then the codes as a [cell][thread] plane
+    extern __shared__ float wts[];  // [records of the tile][NP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int max_recs = T / (int)fm.n_fields + 2;
-    int32_t *heavy = reinterpret_cast<int32_t *>(wts + (size_t)max_recs * NP);  // [records of the tile]
-    int32_t *plane = heavy + max_recs;  // the codes, [cell][thread]: data-dependent cell index, no bank conflicts
     const int64_t n_tiles = (n_groups + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t g0 = tile * T, g1 = min(g0 + T, n_groups);
@@ -274,9 +271,6 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             float *w = wts + (r - r0) * NP;
             if (lane < NP) w[lane] = kexp(__fadd_rn(s_lo, -smax));
             if (NP > 32) w[lane + 32] = kexp(__fadd_rn(s_hi, -smax));
-            // the heaviest candidate (first of equals): its class is visited first, which usually ends the class walk at once
-            const uint32_t is_lo = __ballot_sync(0xFFFFFFFFu, s_lo == smax), is_hi = __ballot_sync(0xFFFFFFFFu, s_hi == smax);
-            if (lane == 0) heavy[r - r0] = is_lo ? __ffs((int)is_lo) - 1 : 32 + __ffs((int)is_hi) - 1;
         }
         __syncthreads();
         const int64_t g = g0 + tid;
@@ -287,23 +281,30 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             const uint32_t field = fpos - rec_local * fm.n_fields;
             const int32_t nc = has_nc ? __ldg(fm.none_code + field) : KC_CODE_NONE;
             const float *w = wts + rec_local * NP;
+            // (requesting the row BEFORE the weights phase was tried: it keeps 32 more registers live across the barrier,
+            // 67 -> 94, and the lost occupancy cost more than the overlap gained: 0.357 -> 0.379 ms)
             int32_t x[NP], rawrow[NP];
             if (n == NP) load_row<NP, true>(codes, g, n, rawrow);
             else load_row<NP, false>(codes, g, n, rawrow);
             M live = 0;
             int present = 0;
-            float total = 0.0f;
+            float total = 0.0f, wmax = -1.0f;
+            int32_t cmax = KC_CODE_NONE;  // the code of this group's heaviest VOTING cell (first of equals)
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 const int32_t raw = rawrow[i];
                 int32_t c = (raw == KC_CODE_NONE) ? nc : raw;  // None votes as none_code where it is >= 0
                 c = c < KC_CODE_NONE ? KC_CODE_NONE : c;        // absent cells never vote
                 x[i] = c;
-                plane[i * T + tid] = c;
                 present += raw < KC_CODE_NONE ? 0 : 1;
                 if (c >= 0) {
                     live |= M(1) << i;
-                    total = __fadd_rn(total, w[i]);
+                    const float wi = w[i];
+                    total = __fadd_rn(total, wi);
+                    if (wi > wmax) {
+                        wmax = wi;
+                        cmax = c;
+                    }
                 }
             }
             const int voters = popc_m(live);
@@ -312,26 +313,34 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             int32_t best_code = KC_CODE_NONE;
             bool tie = false;
             float consumed = 0.0f;
-            // Order of the walk: the class of the record's heaviest candidate first (if it votes here), then first-seen
-            // order.  The outcome does not depend on the order: the heaviest class wins, equal weights go to the class seen
-            // first (smaller first index), `tie` says whether another class equals the winner.
-            int first_pick = heavy[rec_local];
-            if (!((live >> first_pick) & 1)) first_pick = -1;
+            // Order of the walk: always the class of the heaviest cell still waiting (the first one: this group's heaviest
+            // voting cell).  The outcome does not depend on the order (the heaviest class wins, equal weights go to the class
+            // seen first = smaller first index, `tie` says whether another class equals the winner), but the COST does: a warp
+            // loops until its slowest lane is done.  The heaviest voter's class usually holds more than half of the weight and
+            // ends the walk at once; where it does not, going by weight makes the remainder shrink fastest.  (Round 1 walked
+            // in first-seen order after the record's heaviest candidate: 4.3 class passes per warp, and it parked every
+            // group's codes in a shared-memory plane to fetch the next class's code by a data-dependent index; here the pass
+            // over the cells finds the next class itself — no shared memory for the codes at all.)
+            int32_t c = cmax;
             while (live) {
                 // Every class still waiting sums a subset of the unconsumed weights, so its fp32 sum is at most
                 // (total - consumed) up to rounding (< 32 * 2^-23 relative on each side); 5e-5 * total is a safe slack.
-                // Below best_w it can neither win nor tie: stop.  (An agreeing majority ends the loop after one class.)
+                // Below best_w it can neither win nor tie: stop.
                 if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;
-                const int pick = first_pick >= 0 ? first_pick : ffs_mask(live) - 1;
-                first_pick = -1;
-                const int32_t c = plane[pick * T + tid];
                 M eq = 0;
-                float cw = 0.0f;
+                float cw = 0.0f, nw = -1.0f;
+                int32_t nc2 = KC_CODE_NONE;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const bool e = x[j] == c;  // cells before i with this code were consumed with their class
+                    const bool e = x[j] == c;  // cells with this code that came earlier were consumed with their class
+                    const float wj = w[j];
                     eq |= e ? (M(1) << j) : M(0);
-                    cw = e ? __fadd_rn(cw, w[j]) : cw;
+                    cw = e ? __fadd_rn(cw, wj) : cw;
+                    const bool waiting = !e && ((live >> j) & 1);
+                    if (waiting && wj > nw) {  // heaviest cell of the classes still waiting (first of equals)
+                        nw = wj;
+                        nc2 = x[j];
+                    }
                 }
                 const int i = ffs_mask(eq) - 1;  // the class's first cell
                 if (cw > best_w) {
@@ -350,6 +359,7 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
                 }
                 consumed = __fadd_rn(consumed, cw);
                 live &= ~eq;
+                c = nc2;
             }
             win[g] = best_code;
             meta[g] = pack_meta(best_idx, best_cnt, voters, present, voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);

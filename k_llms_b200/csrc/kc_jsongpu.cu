@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include "../../include/kllms_b200.h"
 #include "kc_internal.h"
@@ -139,11 +140,18 @@ PinnedBlob acquire_blob(size_t need) {
 void release_blob(PinnedBlob b) {
     if (!b.p) return;
     std::lock_guard<std::mutex> lock(g_pool_mu);
-    if (g_blob_pool.size() >= 4) {  // keep the largest four
-        int smallest = 0;
-        for (int i = 1; i < (int)g_blob_pool.size(); ++i)
-            if (g_blob_pool[i].cap < g_blob_pool[smallest].cap) smallest = i;
-        if (g_blob_pool[smallest].cap >= b.cap) {
+    // small blobs (single requests, many callers at once) are cheap to keep: up to 64 of them; of the large ones the largest four
+    size_t n_small = 0, n_large = 0;
+    for (auto &x : g_blob_pool) (x.cap <= ((size_t)4 << 20) ? n_small : n_large)++;
+    if (b.cap <= ((size_t)4 << 20) && n_small < 64) {
+        g_blob_pool.push_back(b);
+        return;
+    }
+    if (n_large >= 4 || b.cap <= ((size_t)4 << 20)) {
+        int smallest = -1;
+        for (int i = 0; i < (int)g_blob_pool.size(); ++i)
+            if (g_blob_pool[i].cap > ((size_t)4 << 20) && (smallest < 0 || g_blob_pool[i].cap < g_blob_pool[smallest].cap)) smallest = i;
+        if (smallest < 0 || g_blob_pool[smallest].cap >= b.cap) {
             cudaFreeHost(b.p);
             return;
         }
@@ -222,10 +230,13 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     ch.len_c = w.len_c.as<int64_t>();
     ch.len_l = w.len_l.as<int64_t>();
 
+    nvtxRangePushA("kc_json: H2D texts");
     KC_CUDA_I(cudaEventRecord(w.ev[0], s));
     KC_CUDA_I(cudaMemcpyAsync(w.text.p, h_text + b0, bytes, cudaMemcpyHostToDevice, s));
     KC_CUDA_I(cudaMemcpyAsync(w.off.p, h_off + r0 * n, (size_t)(Rc * n + 1) * 8, cudaMemcpyHostToDevice, s));
     KC_CUDA_I(cudaEventRecord(w.ev[1], s));
+    nvtxRangePop();
+    nvtxRangePushA("kc_json: plan (A0 count, A1 scan/type/encode)");
 
     const int team = team_size(n);
     const int tpw = 32 / team;
@@ -279,10 +290,14 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
         gx = (int64_t)h_cnt[1];
     }
     KC_CUDA_I(cudaEventRecord(w.ev[2], s));
+    nvtxRangePop();
+    nvtxRangePushA("kc_json: K1 vote + K2 numeric");
     // K1 / K2: the same kernels as the columnar path (one "field" per group: local codes, no none_code table)
     if (gv) R_(kc_vote_i8(ch.vcells, gv, n, nullptr, 1, w.win.as<int32_t>(), w.vmeta.as<uint32_t>(), s));
     if (gx) R_(kc_numeric_f64(ch.xcells, gx, n, rel_eps, abs_eps, w.xvalue.as<double>(), w.xmeta.as<uint32_t>(), s));
     KC_CUDA_I(cudaEventRecord(w.ev[3], s));
+    nvtxRangePop();
+    nvtxRangePushA("kc_json: emit (C0 lengths, C1 write)");
     // C0: piece lengths and record lengths, then record offsets in the two output blobs
     KC_CUDA_I(cudaMemsetAsync(ch.len_c + Rc, 0, 8, s));
     KC_CUDA_I(cudaMemsetAsync(ch.len_l + Rc, 0, 8, s));
@@ -312,6 +327,8 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
         KC_CUDA_I(cudaGetLastError());
     }
     KC_CUDA_I(cudaEventRecord(w.ev[4], s));
+    nvtxRangePop();
+    nvtxRangePushA("kc_json: D2H texts");
     // the chunk's region of the result blob
     const int64_t need = out_c_bytes + out_l_bytes;
     const int64_t pos = res.used.fetch_add(need);
@@ -327,6 +344,7 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     if (out_l_bytes) KC_CUDA_I(cudaMemcpyAsync(res.blob.p + pos + out_c_bytes, ch.out_l, (size_t)out_l_bytes, cudaMemcpyDeviceToHost, s));
     KC_CUDA_I(cudaEventRecord(w.ev[5], s));
     KC_CUDA_I(cudaStreamSynchronize(s));
+    nvtxRangePop();
     for (int64_t i = 0; i < Rc; ++i) {
         const int64_t r = r0 + i;
         res.status[(size_t)r] = h_status[i] ? 1 : 0;
@@ -381,7 +399,7 @@ int kc_consolidate_json_packed(const char *h_text, const int64_t *h_off, int64_t
     const int64_t total_bytes = R ? h_off[R * n] - h_off[0] : 0;
     // The consensus of a record is about one candidate long and its likelihoods about as long again (numbers can grow:
     // "5" -> "5.0", 17-digit means).  A chunk whose output does not fit what is left is handed to the host path.
-    res->blob = acquire_blob((size_t)(total_bytes / n * 3 + (1 << 20)));
+    res->blob = acquire_blob((size_t)(total_bytes / n * 3 + (1 << 20)));  // small requests all ask for ~1 MiB: the pool's blobs fit
     if (!res->blob.p) {
         delete res;
         cudaSetDevice(prev);

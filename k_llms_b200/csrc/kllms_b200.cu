@@ -15,6 +15,8 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/kllms_b200.h"
 #include "kc_internal.h"
 #include "kc_common.cuh"
@@ -741,7 +743,7 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
     if (per_record && n >= 8) {  // weights once per record, codes in a shared-memory plane
         const int max_recs = threads / n_fields + 2;
         auto launch = [&](auto kernel, int NP) -> int {
-            const size_t smem = (size_t)max_recs * NP * 4 + (size_t)max_recs * 4 + (size_t)NP * threads * 4;
+            const size_t smem = (size_t)max_recs * NP * 4;  // the candidate weights of the tile's records
             KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
@@ -934,6 +936,7 @@ static int consensus_host_impl(const void *h_codes_v, int code_bytes, int32_t n_
         cudaStream_t st = cx.streams[s];
         const int64_t nr = std::min(chunk, n_records - r0);
         cudaError_t e = cudaSuccess;
+        nvtxRangePushA("kc_consensus_host: chunk (H2D, K1, K2, D2H)");
         if (n_vote_fields) {
             const int64_t G = nr * n_vote_fields;
             e = cudaMemcpyAsync(cx.codes[s].p, h_codes + (size_t)r0 * n_vote_fields * n * code_bytes, (size_t)G * n * code_bytes,
@@ -942,7 +945,7 @@ static int consensus_host_impl(const void *h_codes_v, int code_bytes, int32_t n_
                 rc = code_bytes == 1
                          ? kc_vote_i8(cx.codes[s].as<int8_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st)
                          : kc_vote_i32(cx.codes[s].as<int32_t>(), G, n, d_none, n_vote_fields, cx.win[s].as<int32_t>(), cx.vmeta[s].as<uint32_t>(), st);
-                if (rc) break;
+                if (rc) { nvtxRangePop(); break; }
                 e = cudaMemcpyAsync(h_win_code + r0 * n_vote_fields, cx.win[s].as<int32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
             }
             if (e == cudaSuccess)
@@ -953,12 +956,13 @@ static int consensus_host_impl(const void *h_codes_v, int code_bytes, int32_t n_
             e = cudaMemcpyAsync(cx.vals[s].as<double>(), h_vals + r0 * n_num_fields * n, (size_t)G * n * 8, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) {
                 rc = kc_numeric_f64(cx.vals[s].as<double>(), G, n, rel_eps, abs_eps, cx.value[s].as<double>(), cx.nmeta[s].as<uint32_t>(), st);
-                if (rc) break;
+                if (rc) { nvtxRangePop(); break; }
                 e = cudaMemcpyAsync(h_value + r0 * n_num_fields, cx.value[s].as<double>(), (size_t)G * 8, cudaMemcpyDeviceToHost, st);
             }
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(h_num_meta + r0 * n_num_fields, cx.nmeta[s].as<uint32_t>(), (size_t)G * 4, cudaMemcpyDeviceToHost, st);
         }
+        nvtxRangePop();
         if (e != cudaSuccess) rc = fail(KC_ECUDA, "kc_consensus_host: %s", cudaGetErrorString(e));
     }
     if (device_ms) {

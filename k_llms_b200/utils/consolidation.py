@@ -76,7 +76,7 @@ def _consensus_of_choices_native(choices, settings, embed):
     texts = [c.message.content for c in choices if c.message.content]  # the filter of _contents_of (reference consolidation.py:92)
     if len(texts) < 2 or len(texts) > _native.MAX_CANDIDATES or not _native_settings(settings):
         return None
-    out = _native_consolidate([texts], settings.rel_eps, settings.abs_eps)[0]
+    out = _combiner.run(texts, settings.rel_eps, settings.abs_eps)
     if out is None:
         return None
     content_text, likelihoods_text = out
@@ -100,6 +100,60 @@ def _native_consolidate(records, rel_eps, abs_eps, device: int = 0):
         return res.pairs()
     finally:
         res.close()
+
+
+class _Combiner:
+    """Per-request consolidations that arrive while another one is on the GPU are COMBINED into one batched call (flat
+    combining: the thread that holds the device runs its own request, then everything that queued up meanwhile as one
+    kc_consolidate_json_packed call, and hands the results back).  An idle caller pays nothing (it takes the device and runs
+    directly); under load the cost per request falls from one launch sequence each (~0.5 ms) towards the batched rate
+    (tools/latency.py: tens of thousands of requests per second)."""
+
+    def __init__(self):
+        import threading
+        self._device = threading.Lock()
+        self._qlock = threading.Lock()
+        self._queue: list = []
+
+    def _drain(self):
+        while True:
+            with self._qlock:
+                batch, self._queue = self._queue, []
+            if not batch:
+                return
+            groups: dict = {}
+            for item in batch:
+                groups.setdefault((len(item["texts"]), item["eps"]), []).append(item)
+            for (_n, eps), items in groups.items():
+                try:
+                    outs = _native_consolidate([it["texts"] for it in items], eps[0], eps[1])
+                    for it, o in zip(items, outs):
+                        it["out"] = o
+                except BaseException as exc:  # hand the failure to every waiter of the group
+                    for it in items:
+                        it["err"] = exc
+                for it in items:
+                    it["done"].set()
+
+    def run(self, texts, rel_eps, abs_eps):
+        import threading
+        item = {"texts": texts, "eps": (rel_eps, abs_eps), "done": threading.Event(), "out": None, "err": None}
+        with self._qlock:
+            self._queue.append(item)
+        while not item["done"].is_set():
+            if self._device.acquire(blocking=False):
+                try:
+                    self._drain()
+                finally:
+                    self._device.release()
+            else:
+                item["done"].wait(0.0005)
+        if item["err"] is not None:
+            raise item["err"]
+        return item["out"]
+
+
+_combiner = _Combiner()
 
 
 def _check_candidates(n: int) -> None:

