@@ -421,6 +421,82 @@ __device__ __forceinline__ void numeric_core(const uint32_t (&hi)[N], const Row 
     meta = pack_meta(0, support, nn, present, flags);
 }
 
+// ---------------------------------------------------------------- n = 2: the whole algorithm by cases
+//
+// Two cells leave a handful of outcomes (cu:1082-1219 restated for n = 2; oracle/consensus_oracle.c is the spec):
+//   no non-None cell          -> no value                                   one non-None cell -> that cell (SINGLE)
+//   two non-None, none finite -> NO_FINITE                                   one finite        -> 0.0 + v, support 1 of 2
+//   two finite, close         -> ((-0.0 + lo) + hi + 0.0) / 2, support 2     two finite, far   -> tie of two singletons: the larger
+//                                                                               |value| (the smaller on equal magnitudes), TIE
+// The generic kernels pay ~470 instructions per group for their census / sort / queue machinery whatever n is (round 1: 0.21 of
+// the HBM peak at n = 2); this is ~60.  A thread owns FOUR consecutive groups = 64 bytes of cells (four 16-byte loads, the next
+// 64 bytes requested first) and writes its results as vectors.
+__device__ __forceinline__ void numeric_pair(uint2 a, uint2 b, double rel_eps, double abs_eps, double &value, uint32_t &meta) {
+    const bool a_abs = a.y == kAbsentHi, b_abs = b.y == kAbsentHi;
+    const bool a_nn = !a_abs && a.y != kNoneHi, b_nn = !b_abs && b.y != kNoneHi;
+    const bool a_fin = a_nn && (a.y & 0x7FF00000u) != 0x7FF00000u, b_fin = b_nn && (b.y & 0x7FF00000u) != 0x7FF00000u;
+    const uint32_t present = (a_abs ? 0u : 1u) + (b_abs ? 0u : 1u), nn = (a_nn ? 1u : 0u) + (b_nn ? 1u : 0u);
+    const double va = __hiloint2double((int)a.y, (int)a.x), vb = __hiloint2double((int)b.y, (int)b.x);
+    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+    if (nn == 0) {
+        value = qnan;
+        meta = pack_meta(0, 0, 0, present, 0);
+    } else if (nn == 1) {  // the original object, untouched (cu:1085-1086)
+        value = a_nn ? va : vb;
+        meta = pack_meta(a_nn ? 0u : 1u, 1, 1, present, KC_FLAG_HAS_VALUE | KC_FLAG_SINGLE);
+    } else if (!a_fin && !b_fin) {  // cu:1115-1116
+        value = qnan;
+        meta = pack_meta(0, 0, 2, present, KC_FLAG_NO_FINITE);
+    } else if (a_fin != b_fin) {  // one finite value: its own cluster, np.mean of one element
+        value = __dadd_rn(0.0, __dadd_rn(-0.0, a_fin ? va : vb));
+        meta = pack_meta(0, 1, 2, present, KC_FLAG_HAS_VALUE);
+    } else {
+        const bool swap = va > vb;  // xs.sort(): ascending, equal elements keep their order
+        const double lo = swap ? vb : va, hi = swap ? va : vb;
+        if (is_close(lo, hi, rel_eps, abs_eps)) {
+            value = __ddiv_rn(__dadd_rn(0.0, __dadd_rn(__dadd_rn(-0.0, lo), hi)), 2.0);
+            meta = pack_meta(0, 2, 2, present, KC_FLAG_HAS_VALUE);
+        } else {  // two singleton clusters tie: equal support and spread, the larger |center| wins, else the first (lower) one
+            const double c_lo = __dadd_rn(0.0, __dadd_rn(-0.0, lo)), c_hi = __dadd_rn(0.0, __dadd_rn(-0.0, hi));
+            value = fabs(c_hi) > fabs(c_lo) ? c_hi : c_lo;
+            meta = pack_meta(0, 1, 2, present, KC_FLAG_HAS_VALUE | KC_FLAG_TIE);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) numeric_pairs_kernel(const double *__restrict__ vals, int64_t n_units, double rel_eps, double abs_eps,
+                                                            double *__restrict__ out_value, uint32_t *__restrict__ out_meta) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int4 cur[4];
+    if (u < n_units) {
+        const int4 *p = reinterpret_cast<const int4 *>(vals) + u * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = ldg_nc_v4(p + q);
+    }
+    for (; u < n_units; u += stride) {
+        int4 nxt[4];
+        if (u + stride < n_units) {
+            const int4 *p = reinterpret_cast<const int4 *>(vals) + (u + stride) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nxt[q] = ldg_nc_v4(p + q);
+        }
+        double v[4];
+        uint32_t m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            numeric_pair(make_uint2((uint32_t)cur[q].x, (uint32_t)cur[q].y), make_uint2((uint32_t)cur[q].z, (uint32_t)cur[q].w), rel_eps, abs_eps,
+                         v[q], m[q]);
+        double *ov = out_value + u * 4;
+        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(ov), "d"(v[0]), "d"(v[1]) : "memory");
+        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(ov + 2), "d"(v[2]), "d"(v[3]) : "memory");
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out_meta + u * 4), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+                     : "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+    }
+}
+
 // ---------------------------------------------------------------- direct front-end (any n <= NP)
 
 template <int NP, int T, bool PREFETCH>

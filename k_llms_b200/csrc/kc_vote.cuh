@@ -242,6 +242,52 @@ __global__ void __launch_bounds__(256) vote_direct_kernel(const int32_t *__restr
     }
 }
 
+// The same result as vote_core for very small groups, without guess / scan control flow: all pairwise equalities, the size
+// of every cell's class, then the first-seen rule (a later class must be STRICTLY larger, cu:958,969) over the first cells of
+// the classes.  Branch-free; N (N - 1) / 2 compares.  At n = 2 the HBM roofline leaves ~46 thread-instructions per group: the
+// generic core's fixed cost (guess, equality pass, majority test, fall-through scan) is what bounded the small-n kernels.
+template <int N, bool HAS_NC>
+__device__ __forceinline__ void vote_core_small(const int32_t (&raw)[N], int32_t none_code, int32_t &win_code, uint32_t &meta) {
+    const uint32_t flip = (HAS_NC && none_code >= 0) ? ~(uint32_t)none_code : 0u;
+    int32_t x[N];
+    uint32_t v[N], cnt[N], later[N];  // votes?  class size;  has an equal voting cell BEFORE it (not the class's first cell)
+    uint32_t present = 0, voters = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool absent = raw[i] < KC_CODE_NONE;
+        const int32_t t = HAS_NC ? (int32_t)((uint32_t)raw[i] ^ ((uint32_t)(raw[i] >> 31) & flip)) : raw[i];
+        x[i] = absent ? KC_CODE_NONE : t;
+        v[i] = x[i] >= 0 ? 1u : 0u;
+        cnt[i] = v[i];
+        later[i] = 0;
+        present += absent ? 0u : 1u;
+        voters += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            const uint32_t e = (x[i] == x[j]) ? (v[i] & v[j]) : 0u;
+            cnt[i] += e;
+            cnt[j] += e;
+            later[j] |= e;
+        }
+    uint32_t best_cnt = 0, best_idx = 0, ties = 0;  // ties: classes (first cells) whose size equals the current best
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t c = later[i] ? 0u : cnt[i];  // only the first cell of a class competes
+        const bool gt = c > best_cnt;
+        ties = gt ? 0u : ties + ((c == best_cnt && c != 0u) ? 1u : 0u);
+        best_idx = gt ? (uint32_t)i : best_idx;
+        best_cnt = gt ? c : best_cnt;
+    }
+    int32_t w = KC_CODE_NONE;
+#pragma unroll
+    for (int i = 0; i < N; ++i) w = (best_cnt != 0u && best_idx == (uint32_t)i) ? x[i] : w;
+    win_code = w;
+    meta = pack_meta(best_idx, best_cnt, voters, present, best_cnt ? (KC_FLAG_HAS_VALUE | (ties ? KC_FLAG_TIE : 0u)) : 0u);
+}
+
 // Small rows (n = 2, 4, 8): one group per thread leaves 8-32 bytes in flight per thread and a fixed cost per group that the
 // few cells cannot amortise (round 1: 0.54 / 0.49 / 0.63 of the HBM peak at n = 2 / 4 / 8).  Here a thread owns GPT
 // CONSECUTIVE groups = 64 bytes of cells (the access pattern of the n = 16 kernel: four 16-byte loads per thread, a warp
@@ -287,7 +333,8 @@ __global__ void __launch_bounds__(256) vote_multi_kernel(const int32_t *__restri
                 fj = fj >= fm.n_fields ? fm.mod_small(fj) : fj;
                 nc = __ldg(fm.none_code + fj);
             }
-            vote_core<NP, HAS_NC>(x, row_min<NP>(x), nc, w[j], m[j]);
+            if constexpr (NP <= 4) vote_core_small<NP, HAS_NC>(x, nc, w[j], m[j]);
+            else vote_core<NP, HAS_NC>(x, row_min<NP>(x), nc, w[j], m[j]);
         }
         if constexpr (HAS_NC) {
             f += fstep;

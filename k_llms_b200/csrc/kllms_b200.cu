@@ -680,6 +680,21 @@ static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n,
         if (n == 8) return launch_fast(kc::numeric_direct_fast_kernel<8, 128>, 8);
         return launch_fast(kc::numeric_direct_fast_kernel<4, 128>, 4);
     }
+    static const bool pairs = [] { const char *e = getenv("KC_NUM_PAIRS"); return !e || e[0] != '0'; }();
+    if (n == 2 && pairs && mc.local() && !force_direct()) {  // the n = 2 case analysis, four groups per thread; the last < 4 groups below
+        DeviceInfo info;
+        int rc = device_info(info);
+        if (rc) return rc;
+        const int64_t units = n_groups / 4;
+        if (units > 0) {
+            const int grid = (int)std::min<int64_t>((units + 255) / 256, (int64_t)info.sm_count * 8);
+            kc::numeric_pairs_kernel<<<grid, 256, 0, st>>>(d_vals, units, rel_eps, abs_eps, d_value, d_meta);
+            KC_CUDA(cudaGetLastError());
+        }
+        const int64_t done = units * 4;
+        if (done == n_groups) return KC_OK;
+        return launch_numeric_direct<2, 128>(d_vals + done * 2, n_groups - done, n, rel_eps, abs_eps, d_value + done, d_meta + done, st, mc);
+    }
     if (n <= 2) return launch_numeric_direct<2, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
     if (n <= 4) return launch_numeric_direct<4, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
     if (n <= 8) return launch_numeric_direct<8, 128>(d_vals, n_groups, n, rel_eps, abs_eps, d_value, d_meta, st, mc);
