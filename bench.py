@@ -285,7 +285,8 @@ def run_gpu_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():  # --sweep runs several n in one process group
+            dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if dist is not None:
@@ -490,7 +491,8 @@ def run_gpu_arm(args):
     # --- end to end, the reference's unit of work: candidate JSON texts (pinned host memory) -> consensus / likelihoods texts
     e2e = None
     if not args.no_e2e:
-        Rj = int(args.e2e_records)
+        # N > 1: a quarter-million records per rank (2.1 GB of texts each) keeps 8 ranks' page-locked buffers and generation time modest
+        Rj = int(args.e2e_records) if world == 1 else min(int(args.e2e_records), 262144)
         jblob, joff = K.s32_texts_packed(Rj, n, 20260921 + 2 + 7919 * rank)  # untimed: the batch a client would hand over
         res = None
         for _ in range(2):  # warm-up: staging pools, device buffers, the pinned output blob
@@ -619,7 +621,7 @@ def run_gpu_arm(args):
                                                 if fused is not None else "nccl"),
                                  "nvlink_floor_ms": (world - 1) * (pipelined.layout.nbytes if pipelined is not None else layout.nbytes) / 770e9 * 1e3 if world > 1 else 0.0}}
         emit(line)
-    if dist is not None:
+    if dist is not None and not getattr(args, "keep_group", False):
         dist.destroy_process_group()
 
 
@@ -689,9 +691,11 @@ def main():
     elif args.sweep:
         # BASELINE configs[4]: one line per n (device-resident step incl. the multi-GPU reassembly; no e2e / CPU legs)
         args.no_e2e, args.no_cpu = True, True
-        for nn in [int(x) for x in args.sweep.split(",")]:
+        ns = [int(x) for x in args.sweep.split(",")]
+        for i, nn in enumerate(ns):
             args.n = nn
             args.push_mode, args.push_chunks = args.sweep_push_mode, args.sweep_push_chunks
+            args.keep_group = i + 1 < len(ns)
             run_gpu_arm(args)
     else:
         run_gpu_arm(args)
