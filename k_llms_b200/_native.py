@@ -295,6 +295,25 @@ def align_json(values, min_support_ratio: float):
     n = len(values)
     if n == 0:
         return None
+    # Precondition: the values look like json.loads output as far as OBJECT IDENTITY goes.  The reference's majority ordering
+    # finds an aligned cell's source position by id() (majority_sorting.py:14-17), and the native code restates CPython's
+    # behaviour for freshly parsed values (True / False / ints in [-5, 256] / one-character strings are shared objects,
+    # everything else is distinct).  A list holding the SAME longer string / float / big int object twice (built in Python, or
+    # deep-copied) breaks that: leave such records to the Python pre-pass, which sees the real identities.
+    def shared_identity(v) -> bool:
+        if isinstance(v, dict):
+            return any(shared_identity(x) for x in v.values())
+        if isinstance(v, list):
+            seen = set()
+            for x in v:
+                if (isinstance(x, str) and len(x) > 1) or isinstance(x, float) or (isinstance(x, int) and not isinstance(x, bool) and not -5 <= x <= 256):
+                    if id(x) in seen:
+                        return True
+                    seen.add(id(x))
+            return any(shared_identity(x) for x in v)
+        return False
+    if any(shared_identity(v) for v in values):
+        return None
     try:
         texts = (ctypes.c_char_p * n)(*[json.dumps(v).encode("ascii") for v in values])
     except (TypeError, ValueError):

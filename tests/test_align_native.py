@@ -69,7 +69,8 @@ def test_alignment_matches_python_port_on_random_structures():
             vals.append({"tags": lst} if rng.random() < 0.6 else lst)
         cases.append(vals)
     for values in cases:
-        got = K.align_json(values, 0.51)
+        values = json.loads(json.dumps(values))  # what consolidation.py passes: freshly parsed values (align_json declines lists
+        got = K.align_json(values, 0.51)         # that hold one longer string / float object twice: object identity matters upstream)
         assert got is not None
         assert json.dumps(got) == json.dumps(_python_align(values)), values
 
@@ -148,3 +149,15 @@ def test_consolidation_uses_the_native_prepass_with_identical_results():
         assert json.dumps(native) == json.dumps(_python_align(contents))
     assert used > 100
     assert _native_alignment([{"a": [1]}, {"a": [1]}], ConsensusSettings(string_similarity_method="jaccard")) is None
+
+
+def test_align_json_declines_values_with_shared_object_identity():
+    """the native alignment assumes json.loads-like object identity; a list holding the same string object twice
+    (built in Python) goes to the Python pre-pass instead of being aligned on that assumption."""
+    import json
+    from k_llms_b200 import _native as K
+    w = "gadget"
+    shared = [{"items": [w, "widget", w]}, {"items": ["widget", w]}]  # the SAME str object twice in one list
+    assert K.align_json(shared, 0.51) is None
+    fresh = [json.loads(json.dumps(v)) for v in shared]                # what consolidation.py passes: freshly parsed
+    assert K.align_json(fresh, 0.51) is not None
