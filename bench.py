@@ -456,6 +456,22 @@ def run_gpu_arm(args):
         g1.record()
         barrier()
         gather_ms = max_over_ranks(g0.elapsed_time(g1) / 5)
+    kernels_in_step_ms = compute_ms  # K1 + K2 event times INSIDE the step (they share the GPU with the transfer at N > 1)
+    if pipelined is not None:
+        # compute_only proper: the same launches with the reassembly switched off (no pushes, no barrier), device events, max over ranks
+        timing[0] = False
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(5, min(K_steps, 50))
+        c0.record()
+        for _ in range(reps):
+            if args.push_mode == "hybrid":
+                pipelined.step(compute, gather=False, compute_numeric=compute_numeric, compute_vote=compute_vote)
+            else:
+                pipelined.step(compute, gather=False)
+        c1.record()
+        barrier()
+        compute_ms = max_over_ranks(c0.elapsed_time(c1) / reps)
     reassembly_check = None
     if pipelined is not None:
         # outside the timed region: EVERY rank's slot on THIS GPU must hold exactly the wire words of that rank's results —
@@ -614,6 +630,8 @@ def run_gpu_arm(args):
                                           if world > 1 else "single GPU"},
                 "e2e": e2e, "e2e_columnar": e2e_columnar, "gpu_launches": 2 * chunks * K_steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": base,
                 "compute_only": {"value": world * N / (compute_ms / 1e3), "ms_per_step": compute_ms,
+                                 "note": "the step's kernel launches with the reassembly switched off" if pipelined is not None else "K1 + K2 event times inside the step",
+                                 "kernels_inside_step_ms": kernels_in_step_ms,
                                  "all_gather_alone_ms": gather_ms, "gathered_bytes_per_rank": int((pipelined.layout.nbytes if pipelined is not None else layout.nbytes) * world),
                                  "pipeline_chunks": chunks, "numa_node": numa, "reassembly_check": reassembly_check,
                                  "bound": ("NVLink ingress of the reassembly: every GPU receives (N-1) x its share" if world > 1 else "HBM"),

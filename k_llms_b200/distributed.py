@@ -338,6 +338,7 @@ class PipelinedShardedConsensus:
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self.done = [torch.cuda.Event() for _ in range(chunks)]
         self.pushed = torch.cuda.Event()
+        self._gather = True
         self.mode = mode  # "wire": K1 writes the wire words itself; "pack": the push kernel packs the full K1 results; "dma": copy engines
 
     def available(self) -> bool:
@@ -368,7 +369,7 @@ class PipelinedShardedConsensus:
             K.check(K.load().kc_vote_i32(codes_ptr, n_groups, n, none_ptr, n_fields, win.data_ptr(), vmeta.data_ptr(), stream_ptr))
         else:
             import ctypes
-            fused = self.mode == "hybrid"  # K1 stores its wire words into the peers' copies itself
+            fused = self.mode == "hybrid" and self._gather  # K1 stores its wire words into the peers' copies itself
             K.check(K.load().kc_vote_i32_wire(codes_ptr, n_groups, n, none_ptr, n_fields, win.data_ptr(), vmeta.data_ptr(), self._slot_ptrs(c)[0],
                                               1 if self.layout.wide else 0, self.n_peers if fused else 0,
                                               ctypes.addressof(self.peer_deltas) if fused else None, self.overflow.data_ptr(), stream_ptr))
@@ -416,6 +417,7 @@ class PipelinedShardedConsensus:
         the peers' copies) and K2 of chunk c + 1 run."""
         import torch
         main = torch.cuda.current_stream()
+        self._gather = gather  # gather=False: the same launches with no remote stores, no pushes, no barrier (compute only)
         if self.mode == "hybrid" and compute_numeric is not None and compute_vote is not None:
             for c in range(self.chunks):
                 compute_numeric(c, self.my_views(c))
