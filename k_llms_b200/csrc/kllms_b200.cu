@@ -676,35 +676,6 @@ static int numeric_f64_routed(const double *d_vals, int64_t n_groups, int32_t n,
         if (done == n_groups) return KC_OK;
         return launch_numeric_direct<4, 128>(d_vals + done * 4, n_groups - done, n, rel_eps, abs_eps, d_value + done, d_meta + done, st, mc);
     }
-    static const bool quads = [] { const char *e = getenv("KC_NUM_QUADS"); return !e || e[0] != '0'; }();
-    if (n == 4 && quads && mc.local() && !force_direct() && !force_tma()) {  // the n = 4 pattern analysis, two groups per thread
-        DeviceInfo info;
-        int rc = device_info(info);
-        if (rc) return rc;
-        const int64_t units = n_groups / 2;
-        if (units > 0) {
-            const int grid = (int)std::min<int64_t>((units + 255) / 256, (int64_t)info.sm_count * 8);
-            kc::numeric_quads_kernel<<<grid, 256, 0, st>>>(d_vals, units, rel_eps, abs_eps, d_value, d_meta);
-            KC_CUDA(cudaGetLastError());
-        }
-        const int64_t done = units * 2;
-        if (done == n_groups) return KC_OK;
-        return launch_numeric_direct<4, 128>(d_vals + done * 4, n_groups - done, n, rel_eps, abs_eps, d_value + done, d_meta + done, st, mc);
-    }
-    static const bool octs = [] { const char *e = getenv("KC_NUM_OCTS"); return !e || e[0] != '0'; }();
-    if (n == 8 && octs && mc.local() && !force_direct() && !force_tma()) {  // n = 8: sorted in registers, runs of seven bits
-        DeviceInfo info;
-        int rc = device_info(info);
-        if (rc) return rc;
-        const size_t smem = (size_t)8 * 128 * 8;
-        int per_sm = 0;
-        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc::numeric_octs_kernel, 128, smem));
-        if (per_sm < 1) return fail(KC_ECUDA, "numeric_octs_kernel does not fit");
-        const int grid = (int)std::min<int64_t>((n_groups + 127) / 128, (int64_t)info.sm_count * per_sm);
-        kc::numeric_octs_kernel<<<grid, 128, smem, st>>>(d_vals, n_groups, rel_eps, abs_eps, d_value, d_meta);
-        KC_CUDA(cudaGetLastError());
-        return KC_OK;
-    }
     if (numeric_fast && !force_direct() && (n == 8 || n == 4)) {
         auto launch_fast = [&](auto kernel, int NP) -> int {
             DeviceInfo info;
