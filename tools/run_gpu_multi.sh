@@ -1,3 +1,4 @@
+# Round-2 recipe: gpurun --gpus N -- bash tools/run_gpu_multi.sh N   (cross-rank checks at N = 2, bench at N, config-5 sweep at N = 8)
 NG=${1:-2}
 mkdir -p gpurun_out
 if [ "$NG" = "2" ]; then

@@ -1,3 +1,4 @@
+# Round-2 recipe (run under gpurun on a B200 box): every GPU test, smoke, bench, sweep, config 3/4 and latency tools -> gpurun_out/
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/r2_pytest_gpu_all.txt; cat gpurun_out/r2_pytest_gpu_all.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

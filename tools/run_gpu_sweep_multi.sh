@@ -1,3 +1,4 @@
+# Round-2 recipe: gpurun --gpus N -- bash tools/run_gpu_sweep_multi.sh N   (bench.py --sweep over n at N GPUs)
 NG=${1:-2}
 mkdir -p gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NG --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus $NG --sweep 2,4,8,16,32,64 --steps 50 --warmup 5 > gpurun_out/r2_sweep_n$NG.jsonl 2> gpurun_out/r2_sweep_n$NG.err; python -c "
