@@ -226,6 +226,16 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
 int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
                   int32_t max_group, int32_t *d_best_idx, double *d_best_avg, void *stream);
 
+/* K4 with the other string similarities of the reference (ConsensusSettings.string_similarity_method, cu:56): KC_SIM_LEVENSHTEIN
+ * as above; KC_SIM_JACCARD = |A & B| / |A | B| on the character SETS (jaccard_similarity, cu:720-742); KC_SIM_HAMMING = 1 -
+ * mismatches / max_len position by position, the shorter string padded (hamming_similarity, cu:676-717); both floored at 1e-8.
+ * The 64-character contract applies to KC_SIM_LEVENSHTEIN only. */
+#define KC_SIM_LEVENSHTEIN 0
+#define KC_SIM_JACCARD 1
+#define KC_SIM_HAMMING 2
+int kc_medoid_str_method(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
+                         int32_t max_group, int32_t method, int32_t *d_best_idx, double *d_best_avg, void *stream);
+
 /* K4 with HOST buffers (H2D, one launch, D2H; synchronous): what the host planners call for a batch of string groups. */
 int kc_medoid_str_host(const uint8_t *h_chars, int64_t n_chars, const int32_t *h_str_off, const int32_t *h_grp_off, int64_t n_groups,
                        int32_t max_group, int32_t *h_best_idx, double *h_best_avg, int device);

@@ -27,7 +27,7 @@ EXPORTS = (
     "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
     "kc_consolidate_json_packed", "kc_json_result_view", "kc_json_result_free", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
-    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5", "kc_debug_s32_texts", "kc_push_results", "kc_vote_i32_wire",
+    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5", "kc_debug_s32_texts", "kc_push_results", "kc_vote_i32_wire", "kc_medoid_str_method",
 )
 
 
@@ -88,6 +88,8 @@ def load() -> ctypes.CDLL:
     lib.kc_medoid_str_host.restype = c.c_int
     lib.kc_medoid_str.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.kc_medoid_str.restype = c.c_int
+    lib.kc_medoid_str_method.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.kc_medoid_str_method.restype = c.c_int
     lib.kc_levenshtein.argtypes = [c.c_char_p, i32, c.c_char_p, i32]
     lib.kc_levenshtein.restype = i32
     lib.kc_free_strings.argtypes = [vp, i64]
@@ -272,18 +274,20 @@ def consensus_host(codes, none_code, vals, rel_eps=0.03, abs_eps=1e-6, device=0,
     return {"win_code": win, "vote_meta": vmeta, "value": value, "num_meta": nmeta, "device_ms": float(ms.value)}
 
 
-def medoid_str(chars, str_off, grp_off, max_group=MAX_CANDIDATES, stream=None):
+SIM_METHODS = {"levenshtein": 0, "embeddings": 0, "jaccard": 1, "hamming": 2}  # "embeddings": pairs the planner sends here are Levenshtein pairs
+
+
+def medoid_str(chars, str_off, grp_off, max_group=MAX_CANDIDATES, stream=None, method: str = "levenshtein"):
     """K4 on device tensors: chars uint8 [C], str_off int32 [S+1], grp_off int32 [G+1], max_group = largest group ->
-    (best index int32 [G], mean similarity float64 [G])."""
+    (best index int32 [G], mean similarity float64 [G]); method = the reference's string_similarity_method."""
     torch = _require_cuda()
     assert chars.is_cuda and chars.dtype == torch.uint8 and str_off.dtype == torch.int32 and grp_off.dtype == torch.int32
     G = grp_off.numel() - 1
     idx = torch.empty(G, dtype=torch.int32, device=chars.device)
     avg = torch.empty(G, dtype=torch.float64, device=chars.device)
     _bind(torch, chars)
-    check(load().kc_medoid_str(chars.data_ptr(), str_off.data_ptr(), grp_off.data_ptr(), G, max(2, int(max_group)), idx.data_ptr(),
-                               avg.data_ptr(),
-                               _stream_ptr(torch, stream)))
+    check(load().kc_medoid_str_method(chars.data_ptr(), str_off.data_ptr(), grp_off.data_ptr(), G, max(2, int(max_group)),
+                                      SIM_METHODS[method], idx.data_ptr(), avg.data_ptr(), _stream_ptr(torch, stream)))
     return idx, avg
 
 

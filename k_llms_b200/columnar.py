@@ -220,16 +220,18 @@ class Plan:
         return _Const(value, conf)
 
     def _medoid_on_device(self, live: Sequence[Any]) -> bool:
-        """K4 takes groups of plain ASCII strings whose every pair is a Levenshtein pair with a <= 64-character side:
-        method 'levenshtein', or 'embeddings' where no two strings are both longer than 50 characters (cu:813 would
-        ask the embeddings service for those)."""
-        if self.string_method not in ("levenshtein", "embeddings") or len(live) > MAX_CANDIDATES:
+        """K4 takes groups of plain ASCII strings: methods 'jaccard' and 'hamming' always; 'levenshtein' when every pair has a
+        <= 64-character side; 'embeddings' where, further, no two strings are both longer than 50 characters (cu:813 would ask
+        the embeddings service for those)."""
+        if self.string_method not in ("levenshtein", "embeddings", "jaccard", "hamming") or len(live) > MAX_CANDIDATES:
             return False
         if not all(isinstance(v, str) and v.isascii() for v in live):
             return False
         if self.string_method == "embeddings" and sum(1 for v in live if len(v) > 50) > 1:
             return False
         lens = [len(_normalize(v)) for v in live]
+        if self.string_method in ("jaccard", "hamming"):  # character sets / position-wise mismatches: no pattern-length contract
+            return max(lens) <= 2000
         return sum(1 for l in lens if l > 64) <= 1 and max(lens) <= 2000
 
     # -- device ----------------------------------------------------------------------------------------
@@ -260,7 +262,7 @@ class Plan:
             chars = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
             idx, avg = _native.medoid_str(torch.from_numpy(chars).to(dev), torch.tensor(str_off, dtype=torch.int32, device=dev),
                                           torch.tensor(grp_off, dtype=torch.int32, device=dev),
-                                          max_group=max(len(grp) for grp in self.medoid_groups))
+                                          max_group=max(len(grp) for grp in self.medoid_groups), method=self.string_method)
             out["medoid_idx"], out["medoid_avg"] = idx.cpu().numpy(), avg.cpu().numpy()
         return out
 

@@ -60,7 +60,7 @@ struct MedoidSmem {
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__restrict__ chars, const int32_t *__restrict__ str_off,
                                                             const int32_t *__restrict__ grp_off, int64_t n_groups, int kmax,
-                                                            int32_t *__restrict__ best_idx, double *__restrict__ best_avg) {
+                                                            int32_t *__restrict__ best_idx, double *__restrict__ best_avg, int method) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t per_warp = (MedoidSmem::bytes(kmax) + 15) & ~size_t(15);
@@ -148,7 +148,11 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
         for (int a = lane; a < u; a += 32) {
             const int i = s_uniq[a], o = s_off[i], l = s_len[i];
             uint64_t *tab = peq + (size_t)a * kPeqStride;
-            if (l <= kMedoidMaxPattern) {
+            if (method == 1) {  // jaccard_similarity (cu:720-742): the SET of characters, one bit per symbol of [a-z0-9]
+                uint64_t set = 0;
+                for (int q = 0; q < l; ++q) set |= 1ull << alnum_index(__ldg(chars + o + q));
+                tab[0] = set;
+            } else if (method == 0 && l <= kMedoidMaxPattern) {
 #pragma unroll 4
                 for (int c = 0; c < kAlphabet; ++c) tab[c] = 0;
                 for (int q = 0; q < l; ++q) tab[alnum_index(__ldg(chars + o + q))] |= 1ull << q;
@@ -171,8 +175,20 @@ __global__ void __launch_bounds__(WARPS * 32) medoid_kernel(const uint8_t *__res
                 ta = a;
             }
             const int m = s_len[s_uniq[pa]], to = s_off[s_uniq[ta]], tl = s_len[s_uniq[ta]];
+            if (method == 1) {  // |A & B| / |A | B| on the character sets; distinct strings, so the union is not empty
+                const uint64_t sa = peq[(size_t)a * kPeqStride], sb = peq[(size_t)b * kPeqStride];
+                double sv = __ddiv_rn((double)__popcll(sa & sb), (double)__popcll(sa | sb));
+                sv = sv > 1e-8 ? sv : 1e-8;
+                sim[a * kmax + b] = sv;
+                sim[b * kmax + a] = sv;
+                continue;
+            }
             int d;
-            if (m == 0)
+            if (method == 2) {  // hamming_similarity (cu:676-717): position by position, the shorter string padded with ' '
+                const int po = s_off[s_uniq[pa]];
+                d = tl - m;  // a pad never equals an alphanumeric character
+                for (int q = 0; q < m; ++q) d += __ldg(chars + po + q) != __ldg(chars + to + q) ? 1 : 0;
+            } else if (m == 0)
                 d = tl;
             else if (m <= 32)
                 d = myers<uint32_t>(peq + (size_t)pa * kPeqStride, m, chars + to, tl);

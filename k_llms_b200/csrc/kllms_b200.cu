@@ -801,6 +801,12 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
 
 int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
                   int32_t max_group, int32_t *d_best_idx, double *d_best_avg, void *stream) {
+    return kc_medoid_str_method(d_chars, d_str_off, d_grp_off, n_groups, max_group, KC_SIM_LEVENSHTEIN, d_best_idx, d_best_avg, stream);
+}
+
+int kc_medoid_str_method(const uint8_t *d_chars, const int32_t *d_str_off, const int32_t *d_grp_off, int64_t n_groups,
+                         int32_t max_group, int32_t method, int32_t *d_best_idx, double *d_best_avg, void *stream) {
+    if (method < KC_SIM_LEVENSHTEIN || method > KC_SIM_HAMMING) return fail(KC_EINVAL, "kc_medoid_str: unknown similarity method %d", method);
     if (n_groups < 0) return fail(KC_EINVAL, "kc_medoid_str: negative n_groups");
     if (max_group < 2 || max_group > kc::kMedoidMaxN)
         return fail(KC_EINVAL, "kc_medoid_str: max_group=%d outside [2,%d]", max_group, kc::kMedoidMaxN);
@@ -818,7 +824,7 @@ int kc_medoid_str(const uint8_t *d_chars, const int32_t *d_str_off, const int32_
     KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     const int grid = (int)std::min<int64_t>((n_groups + WARPS - 1) / WARPS, (int64_t)info.sm_count * std::max(per_sm, 1));
     kernel<<<grid, WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(d_chars, d_str_off, d_grp_off, n_groups, max_group,
-                                                                         d_best_idx, d_best_avg);
+                                                                         d_best_idx, d_best_avg, method);
     KC_CUDA(cudaGetLastError());
     return KC_OK;
 }

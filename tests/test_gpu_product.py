@@ -39,6 +39,23 @@ def test_medoid_goldens_on_gpu():
     assert [o[0]["k"] for o in outs] == [c["value"] for c in lev]
 
 
+def test_medoid_other_similarity_methods_on_gpu(monkeypatch):
+    """string_similarity_method 'jaccard' / 'hamming': K4 computes those pair similarities too (kc_medoid_str_method) — the
+    reference's outputs (tests/golden/medoid_methods.json), with a guard that the groups really went to the device."""
+    from k_llms_b200 import columnar
+    from k_llms_b200.utils.consensus_utils import ConsensusSettings, consensus_values
+    on_device = []
+    real = columnar.Plan._medoid_on_device
+    monkeypatch.setattr(columnar.Plan, "_medoid_on_device", lambda self, live: on_device.append(real(self, live)) or on_device[-1])
+    cases = load_golden("medoid_methods")
+    assert {c["method"] for c in cases} == {"jaccard", "hamming"}
+    for case in cases:
+        st = ConsensusSettings(string_similarity_method=case["method"])
+        got = consensus_values(case["values"], st, raising_embeddings, None, case["pvf"])
+        assert same(got[0], case["value"]) and same(got[1], case["conf"]), (case, got)
+    assert sum(on_device) > 0.9 * len(on_device) > 100
+
+
 def test_batch_entry_equals_per_record_and_goldens():
     from k_llms_b200.utils.consensus_utils import consensus_values_batch
     cases = [c for c in load_golden("random_cases") + load_golden("known_answers") if len(c["values"]) <= 64]

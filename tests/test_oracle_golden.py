@@ -37,3 +37,18 @@ def test_survey_table_spot_checks():
     assert c([30, 30, 31, None]) == (30.0, 0.66667)
     assert c([{"a": "x"}, {"a": "x"}, None, None]) == ({"a": "x"}, {"a": 0.5})
     assert c([]) == (None, 1.0) and c([None, None]) == (None, 0.0)
+
+
+def test_host_similarity_medoid_matches_reference_for_jaccard_and_hamming():
+    """k_llms_b200.utils.similarity (the host side of the medoid, used for what K4 does not take) against the reference's
+    outputs under string_similarity_method 'jaccard' / 'hamming' (tests/golden/medoid_methods.json)."""
+    from k_llms_b200.utils import similarity as S
+    from tests.helpers import load_golden
+    cases = load_golden("medoid_methods")
+    assert len(cases) > 400
+    for c in cases:
+        live = [v for v in c["values"] if v is not None]
+        if len(live) < 2:
+            continue
+        got = S.medoid(live, c["method"], None, c["pvf"] * len(live) / len(c["values"]))
+        assert got[0] == c["value"] and got[1] == c["conf"], (c, got)
