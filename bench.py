@@ -506,6 +506,7 @@ def run_gpu_arm(args):
 
     # --- end to end, the reference's unit of work: candidate JSON texts (pinned host memory) -> consensus / likelihoods texts
     e2e = None
+    e2e_sample = []
     if not args.no_e2e:
         # N > 1: a quarter-million records per rank (2.1 GB of texts each) keeps 8 ranks' page-locked buffers and generation time modest
         Rj = int(args.e2e_records) if world == 1 else min(int(args.e2e_records), 262144)
@@ -527,16 +528,13 @@ def run_gpu_arm(args):
         barrier()
         e2e_ms = max_over_ranks(statistics.mean(walls))
         assert stats["n_device"] == Rj, f"only {stats['n_device']} of {Rj} S32 records stayed on the device path"
-        # the texts must be the reference's: a sample against the oracle's client order (outside the timed region)
+        # keep a sample of (candidate texts, outputs): the cpu_baseline leg (rank 0, N = 1) checks it against the oracle's client order
+        e2e_sample = []
         if rank == 0:
-            import json as _json
-            from oracle import consensus_py as O
             text = jblob[: int(joff[-1])].tobytes()
-            embed = lambda t: [[0.0] for _ in t]  # noqa: E731
             for r in range(0, Rj, max(1, Rj // 64)):
-                cands = [_json.loads(text[joff[r * n + c]:joff[r * n + c + 1]]) for c in range(n)]
-                cv, cc = O.client_order(cands, embed=embed)
-                assert (res.content(r), res.likelihoods(r)) == (_json.dumps(cv), _json.dumps(cc)), f"e2e record {r} differs from the oracle"
+                e2e_sample.append(([text[joff[r * n + c]:joff[r * n + c + 1]].decode() for c in range(n)], res.content(r), res.likelihoods(r)))
+            del text
         res.close()
         e2e = {"value": world * Rj / (e2e_ms / 1e3), "unit": "records/s", "h2d_bytes_per_step": int(stats["input_bytes"] + joff.nbytes),
                "d2h_bytes_per_step": int(stats["output_bytes"] + 17 * Rj), "ms_per_step": e2e_ms, "steps": e2e_steps,
@@ -606,6 +604,14 @@ def run_gpu_arm(args):
         base = None
         if world == 1 and not args.no_cpu:
             cores = usable_cores()
+            if e2e is not None:  # the checker's second job in this leg: the e2e texts must be the reference's (outside every timed region)
+                import json as _json
+                from oracle import consensus_py as O
+                embed = lambda t: [[0.0] for _ in t]  # noqa: E731
+                for cand_texts, content, lik in e2e_sample:
+                    cv, cc = O.client_order([_json.loads(t) for t in cand_texts], embed=embed)
+                    assert (content, lik) == (_json.dumps(cv), _json.dumps(cc)), "an e2e record differs from the oracle's client order"
+                e2e["checked_against_oracle"] = len(e2e_sample)
             base = cpu_baseline(n, int(args.cpu_records_per_core), cores, "json")
             base["consensus_only"] = cpu_baseline(n, int(args.cpu_records_per_core), cores, "dicts")
         line = {"metric": METRIC, "value": value_rps, "unit": "records/s", "n_gpus": world, "steps": K_steps, "warmup": max(args.warmup, 3),
