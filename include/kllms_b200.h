@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KC_VERSION 100 /* 0.1.0 */
+#define KC_VERSION 200 /* 0.2.0 */
 #define KC_MAX_CANDIDATES 64
 
 /* ---- error codes ---- */

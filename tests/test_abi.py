@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/kllms_b200.h but not exported"
     assert sorted(_native.EXPORTS) == names
     _native.load()
-    assert _native.load().kc_version() == 100
+    assert _native.load().kc_version() == 200
 
 
 def test_sass_is_blackwell_native():
