@@ -334,7 +334,7 @@ typedef struct {
     int32_t chunks, streams;
     /* device time by stage, summed over the chunks (CUDA events on each chunk's stream; chunks overlap, so the sum of the
      * stages can exceed the wall time) */
-    double h2d_ms, plan_ms /* A0 + A1: scan, type, encode */, kernel_ms /* K1 + K2 */, emit_ms /* C0 + C1 */, d2h_ms;
+    double h2d_ms, plan_ms /* A0 + A1 (+ A2): scan, type, encode */, kernel_ms /* K1 + K2 (+ K4) */, emit_ms /* C0 + C1 */, d2h_ms;
     double device_path_wall_ms, host_path_wall_ms, wall_ms;
 } kc_json_stats;
 int kc_consolidate_json_packed(const char *h_text, const int64_t *h_off, int64_t n_records, int32_t n, double rel_eps, double abs_eps,
@@ -354,6 +354,11 @@ int kc_debug_jsongpu_inputs(const kc_debug_jsongpu *h, const int8_t **vote_cells
                             int64_t *n_num_groups, const uint8_t **status);
 int kc_debug_jsongpu_emit(kc_debug_jsongpu *h, const uint32_t *vote_meta, const double *num_value, const uint32_t *num_meta,
                           const char **content, const int64_t **content_off, const char **likelihoods, const int64_t **likelihoods_off);
+/* the batch's medoid groups (multi-word string fields) in kc_medoid_str's CSR form; K4's results go in through _set_medoid
+ * (before _emit; the arrays must stay alive until _emit has returned) */
+int kc_debug_jsongpu_medoid_inputs(const kc_debug_jsongpu *h, const uint8_t **chars, const int32_t **str_off, const int32_t **grp_off,
+                                   int64_t *n_groups);
+int kc_debug_jsongpu_set_medoid(kc_debug_jsongpu *h, const int32_t *medoid_idx, const double *medoid_avg);
 void kc_debug_jsongpu_free(kc_debug_jsongpu *h);
 int kc_debug_parse_doubles(const char *text, const int64_t *off, int64_t count, double *out, uint8_t *ok);
 int kc_debug_float_reprs(const double *xs, int64_t count, char *out /* [count][32] */, int32_t *lens);

@@ -27,7 +27,7 @@ EXPORTS = (
     "kc_version", "kc_last_error", "kc_device_count", "kc_sm_count", "kc_set_device", "kc_vote_i32", "kc_numeric_f64", "kc_vote_i32_ex", "kc_numeric_f64_ex", "kc_vote_i8", "kc_consensus_host_i8", "kc_consolidate_json", "kc_free_strings", "kc_levenshtein", "kc_medoid_str", "kc_medoid_str_host", "kc_align_json", "kc_debug_similarity_json", "kc_debug_lsap", "kc_json_plan", "kc_json_inputs", "kc_json_emit", "kc_json_free", "kc_vote_i32_peers", "kc_numeric_f64_peers", "kc_vote_i32_peers_packed",
     "kc_confidence_f64", "kc_logprob_sum_f32", "kc_weighted_vote_i32", "kc_consensus_host", "kc_host_alloc", "kc_host_free",
     "kc_consolidate_json_packed", "kc_json_result_view", "kc_json_result_free", "kc_debug_jsongpu_plan", "kc_debug_jsongpu_inputs",
-    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5", "kc_debug_s32_texts", "kc_push_results", "kc_vote_i32_wire", "kc_medoid_str_method",
+    "kc_debug_jsongpu_emit", "kc_debug_jsongpu_medoid_inputs", "kc_debug_jsongpu_set_medoid", "kc_debug_jsongpu_free", "kc_debug_parse_doubles", "kc_debug_float_reprs", "kc_debug_round5", "kc_debug_s32_texts", "kc_push_results", "kc_vote_i32_wire", "kc_medoid_str_method",
 )
 
 
@@ -101,6 +101,9 @@ def load() -> ctypes.CDLL:
     lib.kc_debug_jsongpu_plan.argtypes = [vp, vp, i64, i32, c.POINTER(vp)]
     lib.kc_debug_jsongpu_inputs.argtypes = [vp] + [vp] * 5
     lib.kc_debug_jsongpu_emit.argtypes = [vp, vp, vp, vp] + [c.POINTER(vp)] * 4
+    lib.kc_debug_jsongpu_medoid_inputs.argtypes = [vp] + [c.POINTER(vp)] * 3 + [c.POINTER(i64)]
+    lib.kc_debug_jsongpu_set_medoid.argtypes = [vp, vp, vp]
+    lib.kc_debug_jsongpu_medoid_inputs.restype = lib.kc_debug_jsongpu_set_medoid.restype = c.c_int
     lib.kc_debug_jsongpu_free.argtypes = [vp]
     lib.kc_debug_jsongpu_free.restype = None
     lib.kc_debug_parse_doubles.argtypes = [vp, vp, i64, vp, vp]

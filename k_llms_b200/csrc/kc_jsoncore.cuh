@@ -31,10 +31,11 @@ typedef unsigned __int128 u128;
 // value kinds of a token (JSON scalar types; nested values and non-standard tokens make the scanner decline)
 enum : uint8_t { K_NULL = 0, K_TRUE = 1, K_FALSE = 2, K_INT = 3, K_FLOAT = 4, K_STR = 5 };
 // which kernel decides a field (plan_leaf in kc_json.cpp; consensus_utils.py:1405-1411 vote, :1443-1453 numeric)
-enum : uint8_t { F_ALLNULL = 0, F_VOTE_STR = 1, F_VOTE_BOOL = 2, F_NUMERIC = 3 };
+// F_MEDOID: a string field that is not enum-like (some value has >= 3 words): the similarity medoid, K4 (:1221-1237)
+enum : uint8_t { F_ALLNULL = 0, F_VOTE_STR = 1, F_VOTE_BOOL = 2, F_NUMERIC = 3, F_MEDOID = 4 };
 
-// One (field, candidate) cell of a record: views into the chunk's text.  Strings: the raw inner span (no quotes; the scanner
-// declines escapes, so raw == value).  TOK_MULTIWORD: the string has >= 3 whitespace-separated words (not enum-like, cu:1405).
+// One (field, candidate) cell of a record: views into the chunk's text.  Strings: the raw inner span (no quotes); raw == value
+// unless TOK_ESCAPED (keys: always, the scanner declines escapes in keys).  TOK_MULTIWORD: the string has >= 3 whitespace-separated words (not enum-like, cu:1405).
 struct alignas(16) Tok {
     uint32_t vstart, vlen;  // value span, relative to the chunk's first byte
     uint32_t kstart;        // key span (inner)
@@ -43,6 +44,7 @@ struct alignas(16) Tok {
     uint8_t flags;
 };
 constexpr uint8_t TOK_MULTIWORD = 1;
+constexpr uint8_t TOK_ESCAPED = 2;  // the span holds two-character escapes (\" \\ \/ \b \f \n \r \t), never \uXXXX
 
 // why a record left the device path (diagnostics only; every non-zero code means "host path")
 enum : int32_t {
@@ -119,13 +121,25 @@ KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, T
             const uint32_t vs = p;
             uint32_t words = 0;
             bool prev_space = true;
+            bool escaped = false;
             for (;;) {
                 if (p >= len) return -D_SYNTAX;
                 const uint8_t d = s[p];
                 if (d == '"') break;
                 if (d < 0x20) return -D_SYNTAX;
-                if (d >= 0x80 || d == '\\') return -D_ESCAPE_OR_NON_ASCII;
-                const bool sp = d == ' ';  // the only str.split() whitespace a raw (unescaped) JSON string can hold
+                if (d >= 0x80) return -D_ESCAPE_OR_NON_ASCII;
+                bool sp = d == ' ';  // the only str.split() whitespace a raw JSON string can hold unescaped
+                if (d == '\\') {
+                    // the two-character escapes stay in the token (TOK_ESCAPED; every reader of the value skips or maps them);
+                    // \uXXXX (any code point, surrogate pairs, non-ASCII) is the host path's
+                    if (p + 1 >= len) return -D_SYNTAX;
+                    const uint8_t e = s[p + 1];
+                    if (e == 'u') return -D_ESCAPE_OR_NON_ASCII;
+                    if (!(e == '"' || e == '\\' || e == '/' || e == 'b' || e == 'f' || e == 'n' || e == 'r' || e == 't')) return -D_SYNTAX;
+                    sp = e == 't' || e == 'n' || e == 'r' || e == 'f';  // str.split() whitespace; \b (0x08) is not
+                    escaped = true;
+                    ++p;
+                }
                 words += (!sp && prev_space) ? 1u : 0u;
                 prev_space = sp;
                 ++p;
@@ -133,7 +147,7 @@ KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, T
             t.kind = K_STR;
             t.vstart = rel + vs;
             t.vlen = p - vs;
-            if (words >= 3) t.flags = TOK_MULTIWORD;
+            t.flags = (uint8_t)((words >= 3 ? TOK_MULTIWORD : 0) | (escaped ? TOK_ESCAPED : 0));
             ++p;
         } else if (c == 't') {
             if (len - p < 4 || s[p + 1] != 'r' || s[p + 2] != 'u' || s[p + 3] != 'e') return -D_SYNTAX;
@@ -216,6 +230,8 @@ KC_HD inline bool is_alnum_lower(uint8_t &c) {  // lower-cases c; true if it sur
 }
 
 // sanitize_value(a) == sanitize_value(b) on ASCII text: lower-case, keep [a-z0-9] (consensus_utils.py:925-933)
+// (a backslash in a value span always starts a two-character escape, and none of the escaped characters is alphanumeric:
+// the pair is skipped as a whole — "\n" must not leave an 'n')
 KC_HD inline bool sanitized_equal(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb) {
     uint32_t i = 0, j = 0;
     for (;;) {
@@ -223,18 +239,41 @@ KC_HD inline bool sanitized_equal(const uint8_t *a, uint32_t la, const uint8_t *
         while (i < la) {
             ca = a[i];
             if (is_alnum_lower(ca)) break;
-            ++i;
+            i += ca == '\\' ? 2u : 1u;
         }
         while (j < lb) {
             cb = b[j];
             if (is_alnum_lower(cb)) break;
-            ++j;
+            j += cb == '\\' ? 2u : 1u;
         }
         if (i >= la || j >= lb) return i >= la && j >= lb;
         if (ca != cb) return false;
         ++i;
         ++j;
     }
+}
+
+// normalize_string(s) on ASCII text (consensus_utils.py:660-673: the same lower-case [a-z0-9] filter): its length, and the
+// characters written to `out` (K4's input) when out != nullptr
+KC_HD inline uint32_t sanitized_copy(const uint8_t *a, uint32_t la, uint8_t *out) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < la; ++i) {
+        uint8_t c = a[i];
+        if (!is_alnum_lower(c)) {
+            i += c == '\\' ? 1u : 0u;
+            continue;
+        }
+        if (out) out[k] = c;
+        ++k;
+    }
+    return k;
+}
+
+// len(value) of a string token: every escape stands for one character
+KC_HD inline uint32_t unescaped_length(const uint8_t *a, uint32_t la) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < la; ++i, ++k) i += a[i] == '\\' ? 1u : 0u;
+    return k;
 }
 
 // bytewise three-way comparison (Python's str ordering on ASCII keys)
@@ -397,6 +436,21 @@ struct Sink {
     }
     KC_HD void lit(const char *s) {
         for (; *s; ++s) put((uint8_t)*s);
+    }
+    // json.dumps of a string value, quotes included, from its raw span: the two-character escapes are already what json.dumps
+    // prints, except "\/", which it prints as "/"
+    KC_HD void json_string(const uint8_t *s, uint32_t len, bool escaped) {
+        put('"');
+        if (!escaped) {
+            put(s, len);
+        } else {
+            for (uint32_t i = 0; i < len; ++i) {
+                if (s[i] == '\\' && s[i + 1] == '/') continue;  // a backslash is never the span's last byte
+                put(s[i]);
+                if (s[i] == '\\') put(s[++i]);
+            }
+        }
+        put('"');
     }
 };
 

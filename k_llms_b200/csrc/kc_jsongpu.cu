@@ -75,7 +75,7 @@ struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[7] = {};
     DBuf text, off, fcount, slot, status, vbase, xbase, counters, toks, fdesc, piece_c, piece_l, vcells, xcells, win, vmeta, xvalue, xmeta,
-        len_c, len_l, out_c, out_l, scan_tmp;
+        len_c, len_l, out_c, out_l, scan_tmp, mcount, scount, ccount, mchars, mstr_off, mgrp_off, midx, mavg;
     PBuf h_small;  // totals and counters (pinned so the small D2H copies are asynchronous)
     PBuf h_scan;   // the scanned record offsets and the statuses of a chunk
     bool busy = false;
@@ -206,7 +206,10 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     R_(w.status.reserve((size_t)Rc));
     R_(w.vbase.reserve((size_t)Rc * 4));
     R_(w.xbase.reserve((size_t)Rc * 4));
-    R_(w.counters.reserve(16));
+    R_(w.counters.reserve(32));
+    R_(w.mcount.reserve((size_t)(Rc + 1) * 4));
+    R_(w.scount.reserve((size_t)(Rc + 1) * 4));
+    R_(w.ccount.reserve((size_t)(Rc + 1) * 4));
     R_(w.len_c.reserve((size_t)(Rc + 1) * 8));
     R_(w.len_l.reserve((size_t)(Rc + 1) * 8));
     R_(w.h_small.reserve(64));
@@ -227,6 +230,9 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     ch.vbase = w.vbase.as<uint32_t>();
     ch.xbase = w.xbase.as<uint32_t>();
     ch.counters = w.counters.as<unsigned long long>();
+    ch.mcount = w.mcount.as<uint32_t>();
+    ch.scount = w.scount.as<uint32_t>();
+    ch.ccount = w.ccount.as<uint32_t>();
     ch.len_c = w.len_c.as<int64_t>();
     ch.len_l = w.len_l.as<int64_t>();
 
@@ -274,27 +280,54 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     ch.vmeta = w.vmeta.as<uint32_t>();
     ch.xvalue = w.xvalue.as<double>();
     ch.xmeta = w.xmeta.as<uint32_t>();
-    KC_CUDA_I(cudaMemsetAsync(w.counters.p, 0, 16, s));
+    KC_CUDA_I(cudaMemsetAsync(w.counters.p, 0, 24, s));
+    // records declined before slots_phase own no medoid groups
+    KC_CUDA_I(cudaMemsetAsync(w.mcount.p, 0, (size_t)(Rc + 1) * 4, s));
+    KC_CUDA_I(cudaMemsetAsync(w.scount.p, 0, (size_t)(Rc + 1) * 4, s));
+    KC_CUDA_I(cudaMemsetAsync(w.ccount.p, 0, (size_t)(Rc + 1) * 4, s));
     // rows reserved by a record that is declined while encoding stay untouched: give them defined contents
     KC_CUDA_I(cudaMemsetAsync(w.vcells.p, 0xFF, std::max<size_t>(Tn, 16), s));
     KC_CUDA_I(cudaMemsetAsync(w.xcells.p, 0, std::max<size_t>(Tn, 2) * 8, s));
-    int64_t gv = 0, gx = 0;
+    int64_t gv = 0, gx = 0, gm = 0;
     if (T) {
         const int64_t rounds = (Rc + tpw - 1) / tpw;
         kc::js::plan_kernel<<<grid_for(rounds * 32), 128, 0, s>>>(ch, team);
         KC_CUDA_I(cudaGetLastError());
         unsigned long long *h_cnt = w.h_small.as<unsigned long long>() + 1;
-        KC_CUDA_I(cudaMemcpyAsync(h_cnt, w.counters.p, 16, cudaMemcpyDeviceToHost, s));
+        KC_CUDA_I(cudaMemcpyAsync(h_cnt, w.counters.p, 24, cudaMemcpyDeviceToHost, s));
         KC_CUDA_I(cudaStreamSynchronize(s));
         gv = (int64_t)h_cnt[0];
         gx = (int64_t)h_cnt[1];
+        gm = (int64_t)h_cnt[2];
+    }
+    if (gm) {
+        // A2: multi-word string fields -> K4's CSR input.  Sizes by upper bound (no read-back): the normalised characters are a
+        // subset of the chunk's text, a group has at most n strings, a record at most fcount groups.
+        R_(w.mchars.reserve(bytes + 16));
+        R_(w.mstr_off.reserve((Tn + 2) * 4));
+        R_(w.mgrp_off.reserve((T + 2) * 4));
+        R_(w.midx.reserve((T + 1) * 4));
+        R_(w.mavg.reserve((T + 1) * 8));
+        ch.mchars = w.mchars.as<uint8_t>();
+        ch.mstr_off = w.mstr_off.as<int32_t>();
+        ch.mgrp_off = w.mgrp_off.as<int32_t>();
+        ch.midx = w.midx.as<int32_t>();
+        ch.mavg = w.mavg.as<double>();
+        for (uint32_t *cnt : {ch.mcount, ch.scount, ch.ccount}) {
+            tb = w.scan_tmp.cap;
+            KC_CUDA_I(cub::DeviceScan::ExclusiveSum(w.scan_tmp.p, tb, (const uint32_t *)cnt, cnt, (int)(Rc + 1), s));
+        }
+        const int64_t rounds = (Rc + tpw - 1) / tpw;
+        kc::js::medoid_kernel<<<grid_for(rounds * 32), 128, 0, s>>>(ch, team);
+        KC_CUDA_I(cudaGetLastError());
     }
     KC_CUDA_I(cudaEventRecord(w.ev[2], s));
     nvtxRangePop();
-    nvtxRangePushA("kc_json: K1 vote + K2 numeric");
-    // K1 / K2: the same kernels as the columnar path (one "field" per group: local codes, no none_code table)
+    nvtxRangePushA("kc_json: K1 vote + K2 numeric + K4 medoid");
+    // K1 / K2 / K4: the same kernels as the columnar path (one "field" per group: local codes, no none_code table)
     if (gv) R_(kc_vote_i8(ch.vcells, gv, n, nullptr, 1, w.win.as<int32_t>(), w.vmeta.as<uint32_t>(), s));
     if (gx) R_(kc_numeric_f64(ch.xcells, gx, n, rel_eps, abs_eps, w.xvalue.as<double>(), w.xmeta.as<uint32_t>(), s));
+    if (gm) R_(kc_medoid_str(ch.mchars, ch.mstr_off, ch.mgrp_off, gm, std::max(2, n), w.midx.as<int32_t>(), w.mavg.as<double>(), s));
     KC_CUDA_I(cudaEventRecord(w.ev[3], s));
     nvtxRangePop();
     nvtxRangePushA("kc_json: emit (C0 lengths, C1 write)");
@@ -575,7 +608,10 @@ struct kc_debug_jsongpu {
     std::vector<uint32_t> fcount, slot, fdesc, vbase, xbase, piece_c, piece_l;
     std::vector<uint8_t> status;
     std::vector<Tok> toks;
-    unsigned long long counters[2] = {0, 0};
+    unsigned long long counters[3] = {0, 0, 0};
+    std::vector<uint32_t> mcount, scount, ccount;
+    std::vector<uint8_t> mchars;
+    std::vector<int32_t> mstr_off, mgrp_off;
     std::vector<int8_t> vcells;
     std::vector<double> xcells;
     std::vector<int64_t> len_c, len_l;
@@ -598,6 +634,9 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     h->xbase.assign((size_t)R, 0);
     h->len_c.assign((size_t)R + 1, 0);
     h->len_l.assign((size_t)R + 1, 0);
+    h->mcount.assign((size_t)R + 1, 0);
+    h->scount.assign((size_t)R + 1, 0);
+    h->ccount.assign((size_t)R + 1, 0);
     Chunk &ch = h->ch;
     ch.text = h->text.data();
     ch.off = h->off.data();
@@ -609,6 +648,9 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     ch.vbase = h->vbase.data();
     ch.xbase = h->xbase.data();
     ch.counters = h->counters;
+    ch.mcount = h->mcount.data();
+    ch.scount = h->scount.data();
+    ch.ccount = h->ccount.data();
     ch.len_c = h->len_c.data();
     ch.len_l = h->len_l.data();
     for (int32_t r = 0; r < R; ++r) kc::js::count_record(ch, r);
@@ -633,7 +675,41 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
         kc::js::slots_phase(ch, r);
         for (int lane = 0; lane < team; ++lane) kc::js::encode_phase(ch, r, lane, team);
     }
+    for (std::vector<uint32_t> *cnt : {&h->mcount, &h->scount, &h->ccount}) {  // exclusive scans, in place
+        uint32_t acc = 0;
+        for (auto &x : *cnt) {
+            const uint32_t v = x;
+            x = acc;
+            acc += v;
+        }
+    }
+    h->mchars.assign((size_t)h->ccount[(size_t)R] + 1, 0);
+    h->mstr_off.assign((size_t)h->scount[(size_t)R] + 1, 0);
+    h->mgrp_off.assign((size_t)h->mcount[(size_t)R] + 1, 0);
+    ch.mchars = h->mchars.data();
+    ch.mstr_off = h->mstr_off.data();
+    ch.mgrp_off = h->mgrp_off.data();
+    for (int32_t r = 0; r < R; ++r)
+        for (int lane = 0; lane < team; ++lane) kc::js::medoid_phase(ch, r, lane, team);
     *out = h;
+    return KC_OK;
+}
+
+// the medoid groups of the planned batch in kc_medoid_str's CSR form, and where the test puts K4's results
+int kc_debug_jsongpu_medoid_inputs(const kc_debug_jsongpu *h, const uint8_t **chars, const int32_t **str_off, const int32_t **grp_off,
+                                   int64_t *n_groups) {
+    if (!h) return KC_EINVAL;
+    if (chars) *chars = h->mchars.data();
+    if (str_off) *str_off = h->mstr_off.data();
+    if (grp_off) *grp_off = h->mgrp_off.data();
+    if (n_groups) *n_groups = (int64_t)h->counters[2];
+    return KC_OK;
+}
+
+int kc_debug_jsongpu_set_medoid(kc_debug_jsongpu *h, const int32_t *medoid_idx, const double *medoid_avg) {
+    if (!h) return KC_EINVAL;
+    h->ch.midx = medoid_idx;  // must stay alive until kc_debug_jsongpu_emit has returned
+    h->ch.mavg = medoid_avg;
     return KC_OK;
 }
 

@@ -14,13 +14,15 @@
 //                 order, which kernel decides the field (plan_leaf of kc_json.cpp)
 //         slots   the team leader numbers the record's vote / numeric groups and reserves rows in the batch's cell matrices
 //         encode  lane j: sanitised-equality classes -> int8 local codes (K1 cells), exact decimal -> float64 (K2 cells)
-//   K1  kc_vote_i8, K2  kc_numeric_f64 on the cell matrices — the same kernels as the columnar path
+//   A2  medoid_kernel   only when the chunk has multi-word string fields (three exclusive scans of the per-record counts first):
+//                       lane j writes its field's normalised strings and their offsets in K4's CSR form
+//   K1  kc_vote_i8, K2  kc_numeric_f64, K4  kc_medoid_str on the cell matrices / string groups — the kernels of the columnar path
 //   C0  len_kernel      lane j formats its field's value and confidence (float.__repr__ by Ryu) to learn the lengths; the
 //                       leader turns them into piece offsets and record lengths          (then two exclusive scans: offsets)
 //   C1  write_kernel    lane j writes `"key": value` / `"key": confidence` at its offset of the two output blobs
 //
-// A record the device path does not model exactly (escapes, non-ASCII, nested values or lists, candidates with different
-// keys, multi-word strings = medoid fields, numbers outside the exact-conversion range, ...) gets a non-zero status and is
+// A record the device path does not model exactly (\u escapes, escapes in keys, non-ASCII, nested values or lists, candidates with different
+// keys, multi-word strings outside K4's contract, numbers outside the exact-conversion range, ...) gets a non-zero status and is
 // consolidated by the host path (kc_consolidate_json) instead: the device path never guesses.
 //
 // The phases are plain __host__ __device__ functions of (chunk, record, lane, team size) that communicate through global
@@ -50,9 +52,16 @@ struct Chunk {
     Tok *toks;          // [slots * n] token of (field slot, candidate)
     uint32_t *fdesc;    // [slots]
     uint32_t *vbase, *xbase;        // [R] first vote / numeric group of the record
-    unsigned long long *counters;   // [0] vote groups, [1] numeric groups of the chunk
+    unsigned long long *counters;   // [0] vote groups, [1] numeric groups, [2] medoid groups of the chunk
     int8_t *vcells;     // [vote groups][n]   K1 cells
     double *xcells;     // [numeric groups][n] K2 cells
+    // medoid fields (multi-word strings): per record the groups of >= 2 strings, their strings and normalised characters;
+    // after the exclusive scans (in place, entry R = the totals) the record's first group / string / character
+    uint32_t *mcount, *scount, *ccount;  // [R+1]
+    uint8_t *mchars;                     // K4 input: normalised strings back to back
+    int32_t *mstr_off, *mgrp_off;        //           [strings + 1], [groups + 1]
+    const int32_t *midx;                 // K4 results: medoid's index within its group,
+    const double *mavg;                  //             its mean similarity
     const uint32_t *vmeta;   // K1 result words
     const double *xvalue;    // K2 values
     const uint32_t *xmeta;   // K2 result words
@@ -135,10 +144,30 @@ KC_HD inline void type_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t t
                     decline(ch, r, D_MIXED_TYPES);
                     return;
                 }
-                if (row[c].flags & TOK_MULTIWORD) {  // not enum-like: similarity medoid (K4), planned by the host path
+                if (row[c].flags & TOK_MULTIWORD) kind = F_MEDOID;  // not enum-like (cu:1405): the similarity medoid (cu:1221-1237)
+            }
+            if (kind == F_MEDOID) {
+                // K4 takes the group when every pair is a Levenshtein pair inside its contract (plan_leaf of kc_json.cpp, the
+                // rule of columnar.Plan._medoid_on_device under the default similarity method): at most one string longer than
+                // 50 characters (two would go to the embeddings service, cu:813), at most one normalised string longer than 64
+                uint32_t live = 0, chars = 0, long_raw = 0, long_norm = 0;
+                bool fits = true;
+                for (int32_t c = 0; c < n; ++c) {
+                    if (row[c].kind == K_NULL) continue;
+                    const uint32_t nl = sanitized_copy(ch.text + row[c].vstart, row[c].vlen, nullptr);
+                    ++live;
+                    chars += nl;
+                    const uint32_t raw = (row[c].flags & TOK_ESCAPED) ? unescaped_length(ch.text + row[c].vstart, row[c].vlen) : row[c].vlen;
+                    long_raw += raw > 50u ? 1u : 0u;
+                    long_norm += nl > 64u ? 1u : 0u;
+                    fits &= nl <= 2000u;
+                }
+                if (live >= 2 && (!fits || long_raw > 1 || long_norm > 1)) {
                     decline(ch, r, D_MULTIWORD);
                     return;
                 }
+                ch.piece_c[ch.slot[r] + j] = live;   // scratch until C0: read by the leader in slots_phase
+                ch.piece_l[ch.slot[r] + j] = chars;
             }
         } else if (row[first].kind == K_TRUE || row[first].kind == K_FALSE) {
             kind = F_VOTE_BOOL;
@@ -159,23 +188,72 @@ KC_HD inline void slots_phase(const Chunk &ch, int32_t r) {
     if (load_status(ch, r)) return;
     const int32_t F = (int32_t)ch.fcount[r];
     uint32_t *fd = ch.fdesc + ch.slot[r];
-    uint32_t nv = 0, nx = 0;
+    uint32_t nv = 0, nx = 0, nm = 0, ns = 0, nc = 0;
     for (int32_t j = 0; j < F; ++j) {
         const uint32_t d = fd[j], kind = fdesc_kind(d);
         uint32_t g = 0;
-        if (kind == F_VOTE_STR || kind == F_VOTE_BOOL) g = nv++;
-        else if (kind == F_NUMERIC) g = nx++;
+        if (kind == F_VOTE_STR || kind == F_VOTE_BOOL) {
+            g = nv++;
+        } else if (kind == F_NUMERIC) {
+            g = nx++;
+        } else if (kind == F_MEDOID) {
+            uint32_t *pc = ch.piece_c + ch.slot[r] + j, *pl = ch.piece_l + ch.slot[r] + j;
+            const uint32_t live = *pc, chars = *pl;
+            if (live >= 2) {  // one string alone is its own consensus (cu:1085-1086): no group
+                g = nm++;
+                *pc = ns;     // the group's first string / character within the record, for medoid_phase
+                *pl = nc;
+                ns += live;
+                nc += chars;
+            }
+        }
         fd[j] = d | (g << 16);
     }
+    ch.mcount[r] = nm;
+    ch.scount[r] = ns;
+    ch.ccount[r] = nc;
 #ifdef __CUDA_ARCH__
     ch.vbase[r] = (uint32_t)atomicAdd(ch.counters + 0, (unsigned long long)nv);
     ch.xbase[r] = (uint32_t)atomicAdd(ch.counters + 1, (unsigned long long)nx);
+    if (nm) atomicAdd(ch.counters + 2, (unsigned long long)nm);
 #else
     ch.vbase[r] = (uint32_t)ch.counters[0];
     ch.counters[0] += nv;
     ch.xbase[r] = (uint32_t)ch.counters[1];
     ch.counters[1] += nx;
+    ch.counters[2] += nm;
 #endif
+}
+
+// A2, after the exclusive scans of mcount / scount / ccount: lane j writes its medoid group in K4's CSR form.  Group, string
+// and character ranges follow RECORD order (scans, not atomics), so the three offset arrays are monotonic as CSR needs.  A
+// record that was declined after slots_phase (a number out of range) still owns its ranges and fills them: K4 reads every group.
+KC_HD inline void medoid_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t team) {
+    const uint32_t g0 = ch.mcount[r], g1 = ch.mcount[r + 1];
+    if (g0 == g1) return;
+    const int32_t F = (int32_t)ch.fcount[r], n = ch.n;
+    const Tok *rt = ch.toks + (int64_t)ch.slot[r] * n;
+    const uint32_t n_groups = ch.mcount[ch.R], n_strings = ch.scount[ch.R];
+    for (int32_t j = lane; j < F; j += team) {
+        const uint32_t d = ch.fdesc[ch.slot[r] + j];
+        if (fdesc_kind(d) != F_MEDOID) continue;
+        const Tok *row = rt + (int64_t)j * n;
+        uint32_t live = 0;
+        for (int32_t c = 0; c < n; ++c) live += row[c].kind != K_NULL ? 1u : 0u;
+        if (live < 2) continue;
+        const uint32_t g = g0 + fdesc_gidx(d);
+        uint32_t s = ch.scount[r] + ch.piece_c[ch.slot[r] + j], at = ch.ccount[r] + ch.piece_l[ch.slot[r] + j];
+        ch.mgrp_off[g] = (int32_t)s;
+        for (int32_t c = 0; c < n; ++c) {
+            if (row[c].kind == K_NULL) continue;
+            ch.mstr_off[s++] = (int32_t)at;
+            at += sanitized_copy(ch.text + row[c].vstart, row[c].vlen, ch.mchars + at);
+        }
+        if (g + 1 == n_groups) {  // the chunk's last group closes both offset arrays
+            ch.mgrp_off[n_groups] = (int32_t)n_strings;
+            ch.mstr_off[n_strings] = (int32_t)at;
+        }
+    }
 }
 
 KC_HD inline void encode_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t team) {
@@ -241,9 +319,7 @@ KC_HD inline void format_field(const Chunk &ch, int32_t r, int32_t j, Sink &cont
         if (kind == F_VOTE_BOOL) {
             content.lit(row[idx].kind == K_TRUE ? "true" : "false");  // the processed key (cu:958)
         } else {
-            content.put('"');
-            content.put(ch.text + row[idx].vstart, row[idx].vlen);  // first original whose sanitised form wins (cu:971)
-            content.put('"');
+            content.json_string(ch.text + row[idx].vstart, row[idx].vlen, row[idx].flags & TOK_ESCAPED);  // first original whose sanitised form wins (cu:971)
         }
         conf = py_round5(1.0 * ((double)support / (double)present));
     } else if (kind == F_NUMERIC) {
@@ -261,9 +337,7 @@ KC_HD inline void format_field(const Chunk &ch, int32_t r, int32_t j, Sink &cont
                     to_double(ch.text + t.vstart, t.vlen, v);
                     float_repr(v, content);
                 } else if (t.kind == K_STR) {
-                    content.put('"');
-                    content.put(ch.text + t.vstart, t.vlen);
-                    content.put('"');
+                    content.json_string(ch.text + t.vstart, t.vlen, t.flags & TOK_ESCAPED);
                 } else {
                     content.lit(t.kind == K_TRUE ? "true" : (t.kind == K_FALSE ? "false" : "null"));
                 }
@@ -276,6 +350,26 @@ KC_HD inline void format_field(const Chunk &ch, int32_t r, int32_t j, Sink &cont
             content.lit("null");
             if (flags & KC_FLAG_NO_FINITE) conf = 1.0 * ((double)nn / (double)present);
             else conf = present == 0 ? 1.0 : 0.0;
+        }
+    } else if (kind == F_MEDOID) {
+        // cu:1444 then cu:1085-1086 (one non-None string: itself, unrounded) or cu:1233-1237 (the medoid, rounded)
+        uint32_t live = 0;
+        for (int32_t c = 0; c < n; ++c) live += row[c].kind != K_NULL ? 1u : 0u;
+        const double sub = 1.0 * ((double)live / (double)n);
+        int32_t want = 0;
+        if (live >= 2) {
+            const uint32_t gi = ch.mcount[r] + g;
+            want = ch.midx[gi];
+            conf = py_round5(sub * ch.mavg[gi]);
+        } else {
+            conf = sub * (1.0 / 1.0);
+        }
+        for (int32_t c = 0; c < n; ++c) {
+            if (row[c].kind == K_NULL) continue;
+            if (want-- == 0) {
+                content.json_string(ch.text + row[c].vstart, row[c].vlen, row[c].flags & TOK_ESCAPED);
+                break;
+            }
         }
     } else {
         content.lit("null");  // all None: (None, 0.0) (cu:1401-1402)
@@ -373,6 +467,17 @@ __global__ void __launch_bounds__(128) plan_kernel(const Chunk ch, int32_t team)
         __syncwarp();
         if (live) encode_phase(ch, r, lane, team);
         __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) medoid_kernel(const Chunk ch, int32_t team) {
+    const int32_t lane_w = threadIdx.x & 31, tpw = 32 / team;
+    const int32_t lane = lane_w % team, t = lane_w / team;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t rounds = ((int64_t)ch.R + tpw - 1) / tpw;
+    for (int64_t w = warp; w < rounds; w += n_warps) {
+        const int64_t r64 = w * tpw + t;
+        if (r64 < ch.R) medoid_phase(ch, (int32_t)r64, lane, team);
     }
 }
 

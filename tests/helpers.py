@@ -127,7 +127,7 @@ def consolidate_json_with_oracle(records):
 
 def jsongpu_with_oracle(records):
     """The DEVICE JSON path's phases (kc_jsongpu.cuh) instantiated on the host: kc_debug_jsongpu_plan -> the C ORACLE in the
-    place of K1 / K2 -> kc_debug_jsongpu_emit.  Returns (pairs, status): pairs[r] = (content, likelihoods) or None where the
+    place of K1 / K2 / K4 -> kc_debug_jsongpu_emit.  Returns (pairs, status): pairs[r] = (content, likelihoods) or None where the
     device path declines the record (status[r] = its reason code)."""
     import ctypes as c
     from k_llms_b200 import _native as K
@@ -152,6 +152,12 @@ def jsongpu_with_oracle(records):
         if gx.value:
             vals = np.ctypeslib.as_array(c.cast(nc, c.POINTER(c.c_double)), shape=(gx.value, n)).copy()
             nvalue, nmeta = OC.numeric(vals)
+        mc, so, go, gm = c.c_void_p(), c.c_void_p(), c.c_void_p(), c.c_int64()
+        K.check(lib.kc_debug_jsongpu_medoid_inputs(h, c.byref(mc), c.byref(so), c.byref(go), c.byref(gm)))
+        midx, mavg = np.zeros(max(gm.value, 1), dtype=np.int32), np.zeros(max(gm.value, 1), dtype=np.float64)
+        if gm.value:   # the C oracle in K4's place
+            OC.lib().ko_medoid_str(mc, so, go, gm.value, midx.ctypes.data, mavg.ctypes.data)
+        K.check(lib.kc_debug_jsongpu_set_medoid(h, midx.ctypes.data, mavg.ctypes.data))
         pc, po, pl, plo = c.c_void_p(), c.c_void_p(), c.c_void_p(), c.c_void_p()
         K.check(lib.kc_debug_jsongpu_emit(h, vmeta.ctypes.data, nvalue.ctypes.data, nmeta.ctypes.data, c.byref(pc), c.byref(po),
                                           c.byref(pl), c.byref(plo)))

@@ -10,7 +10,7 @@ import pytest
 
 from k_llms_b200 import _native as K
 from tests.test_gpu_json import _expected, _expected_with_lists, _random_nested_record, _random_record
-from tests.test_jsongpu_host_logic import _flat_record, s32_texts
+from tests.test_jsongpu_host_logic import _flat_record, _phrase_record, s32_texts
 
 pytestmark = pytest.mark.gpu
 
@@ -46,6 +46,33 @@ def test_flat_records_device_and_host_share():
             on_device += res.status[r] == 0
             assert (res.content(r), res.likelihoods(r)) == _expected(texts), (texts, res.status[r], res.why[r])
     assert on_device > 1200
+
+
+def test_phrase_fields_medoid_on_the_device():
+    """Multi-word string fields: A2 builds K4's CSR input on the device, K4 picks the medoid, C0 / C1 print the winner's original
+    text — byte-identical to the reference's client order."""
+    rng = random.Random(29)
+    by_n = {}
+    for _ in range(1500):
+        n = rng.choice([2, 3, 4, 5, 8, 16, 33])
+        by_n.setdefault(n, []).append(_phrase_record(rng, n))
+    on_device = 0
+    for _n, recs in by_n.items():
+        res = run(recs)
+        for r, texts in enumerate(recs):
+            if res.status[r] == 1:
+                continue
+            on_device += res.status[r] == 0
+            assert (res.content(r), res.likelihoods(r)) == _expected(texts), (texts, res.status[r], res.why[r])
+    assert on_device > 1200
+    # many records, several chunks: the CSR offsets stay consistent across records declined at different stages
+    recs = [_phrase_record(rng, 8) for _ in range(6000)]
+    recs[17] = ['{"a": "the big cat", "b": 1e999}'] * 8          # declined while encoding, after its medoid group was counted
+    res = run(recs)
+    assert res.stats.n_device > 5000
+    for r in random.Random(5).sample(range(len(recs)), 400) + [16, 17, 18]:
+        if res.status[r] != 1:
+            assert (res.content(r), res.likelihoods(r)) == _expected_with_lists(recs[r]), (recs[r], res.status[r])
 
 
 def test_general_and_mutated_records_never_wrong():
@@ -87,7 +114,7 @@ def test_general_and_mutated_records_never_wrong():
 
 
 def test_device_only_flag_and_reasons():
-    recs = [['{"a": "x\\ny"}', '{"a": "x"}'], ['{"a": 1, "b": "q"}', '{"a": 1, "b": "Q!"}'], ['{"a": [1]}', '{"a": [1]}']]
+    recs = [['{"a": "x\\u0041y"}', '{"a": "x"}'], ['{"a": 1, "b": "q"}', '{"a": 1, "b": "Q!"}'], ['{"a": [1]}', '{"a": [1]}']]
     res = run(recs, flags=K.JSON_DEVICE_ONLY)
     assert list(res.status) == [1, 0, 1] and res.why[0] != 0 and res.why[2] != 0
     assert res.content(1) == '{"a": 1.0, "b": "q"}' and res.likelihoods(1) == '{"a": 1.0, "b": 1.0}'
