@@ -29,13 +29,16 @@ namespace js {
 typedef unsigned __int128 u128;
 
 // value kinds of a token (JSON scalar types; nested values and non-standard tokens make the scanner decline)
-enum : uint8_t { K_NULL = 0, K_TRUE = 1, K_FALSE = 2, K_INT = 3, K_FLOAT = 4, K_STR = 5 };
+// K_OPEN / K_CLOSE: a nested object's `"key": {` and its `}` — structure tokens between which the object's members follow
+enum : uint8_t { K_NULL = 0, K_TRUE = 1, K_FALSE = 2, K_INT = 3, K_FLOAT = 4, K_STR = 5, K_OPEN = 6, K_CLOSE = 7 };
 // which kernel decides a field (plan_leaf in kc_json.cpp; consensus_utils.py:1405-1411 vote, :1443-1453 numeric)
 // F_MEDOID: a string field that is not enum-like (some value has >= 3 words): the similarity medoid, K4 (:1221-1237)
-enum : uint8_t { F_ALLNULL = 0, F_VOTE_STR = 1, F_VOTE_BOOL = 2, F_NUMERIC = 3, F_MEDOID = 4 };
+enum : uint8_t { F_ALLNULL = 0, F_VOTE_STR = 1, F_VOTE_BOOL = 2, F_NUMERIC = 3, F_MEDOID = 4, F_OPEN = 5, F_CLOSE = 6 };
+constexpr int32_t kMaxNesting = 8;  // nested objects below the top level; the depth lives in the token's flags (4 bits)
 
 // One (field, candidate) cell of a record: views into the chunk's text.  Strings: the raw inner span (no quotes); raw == value
-// unless TOK_ESCAPED (keys: always, the scanner declines escapes in keys).  TOK_MULTIWORD: the string has >= 3 whitespace-separated words (not enum-like, cu:1405).
+// unless TOK_ESCAPED (keys: always, the scanner declines escapes in keys).  flags: bit 0 TOK_MULTIWORD, bit 1 TOK_ESCAPED, bits 4-7
+// the nesting depth of the member.  K_OPEN carries the key of the nested object, K_CLOSE no key.  TOK_MULTIWORD: the string has >= 3 whitespace-separated words (not enum-like, cu:1405).
 struct alignas(16) Tok {
     uint32_t vstart, vlen;  // value span, relative to the chunk's first byte
     uint32_t kstart;        // key span (inner)
@@ -44,6 +47,7 @@ struct alignas(16) Tok {
     uint8_t flags;
 };
 constexpr uint8_t TOK_MULTIWORD = 1;
+KC_HD inline uint32_t tok_depth(const Tok &t) { return (uint32_t)t.flags >> 4; }  // 0 = a member of the top-level object
 constexpr uint8_t TOK_ESCAPED = 2;  // the span holds two-character escapes (\" \\ \/ \b \f \n \r \t), never \uXXXX
 
 // why a record left the device path (diagnostics only; every non-zero code means "host path")
@@ -77,11 +81,12 @@ KC_HD inline double bits_f64(uint64_t b) {
 
 // ---------------------------------------------------------------- scanner
 
-// Scans ONE candidate text `s[0..len)` as json.loads would a flat object of scalars.  Token j goes to toks[j * stride] when
-// toks != nullptr (spans are stored relative to `rel`: s == chunk + rel).  Returns the field count (>= 1) or -D_* — the
-// scanner never guesses: whatever it does not model exactly (escapes, non-ASCII, nested values, NaN/Infinity, free text that
-// the reference wraps as {"text": ...}, an empty object) is left to the host path.
-KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, Tok *toks, int32_t stride, int32_t cap) {
+// Scans ONE candidate text `s[0..len)` as json.loads would an object of scalars and nested objects.  Token j goes to
+// toks[j * stride] when toks != nullptr (spans are stored relative to `rel`: s == chunk + rel); a nested object is its K_OPEN
+// token, its members' tokens, its K_CLOSE token.  Returns the token count (>= 1) or -D_* — the scanner never guesses: whatever
+// it does not model exactly (\u escapes, non-ASCII, lists, NaN/Infinity, free text that the reference wraps as {"text": ...},
+// an empty object) is left to the host path.  *nested (optional): whether the object holds a nested object.
+KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, Tok *toks, int32_t stride, int32_t cap, bool *nested = nullptr) {
     uint32_t p = 0;
     while (p < len && is_json_ws(s[p])) ++p;
     if (p >= len) return -D_EMPTY;
@@ -90,6 +95,8 @@ KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, T
     while (p < len && is_json_ws(s[p])) ++p;
     if (p < len && s[p] == '}') return -D_EMPTY;  // {}: consensus of empty dicts — rare, host path
     int32_t j = 0;
+    uint32_t depth = 0;
+    if (nested) *nested = false;
     for (;;) {
         while (p < len && is_json_ws(s[p])) ++p;
         if (p >= len || s[p] != '"') return -D_SYNTAX;
@@ -149,6 +156,21 @@ KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, T
             t.vlen = p - vs;
             t.flags = (uint8_t)((words >= 3 ? TOK_MULTIWORD : 0) | (escaped ? TOK_ESCAPED : 0));
             ++p;
+        } else if (c == '{') {
+            ++p;
+            while (p < len && is_json_ws(s[p])) ++p;
+            if (p < len && s[p] == '}') return -D_NESTED;              // an empty nested object: host path
+            if ((int32_t)depth >= kMaxNesting) return -D_NESTED;
+            t.kind = K_OPEN;
+            t.vstart = rel + p;
+            t.vlen = 0;
+            t.flags = (uint8_t)(depth << 4);
+            if (j >= cap) return -D_TOO_MANY_FIELDS;
+            if (toks) toks[(int64_t)j * stride] = t;
+            ++j;
+            ++depth;
+            if (nested) *nested = true;
+            continue;  // the object's first member
         } else if (c == 't') {
             if (len - p < 4 || s[p + 1] != 'r' || s[p + 2] != 'u' || s[p + 3] != 'e') return -D_SYNTAX;
             t.kind = K_TRUE;
@@ -195,27 +217,44 @@ KC_HD inline int32_t scan_object(const uint8_t *s, uint32_t len, uint32_t rel, T
             t.kind = is_float ? K_FLOAT : K_INT;
             t.vstart = rel + vs;
             t.vlen = p - vs;
-        } else if (c == '{' || c == '[') {
-            return -D_NESTED;
+        } else if (c == '[') {
+            return -D_NESTED;  // lists need the alignment pre-pass: host path
         } else if (c == 'N' || c == 'I') {
             return -D_NONSTANDARD_NUMBER;  // NaN / Infinity: json.loads accepts them; the host path models them
         } else {
             return -D_SYNTAX;
         }
+        t.flags = (uint8_t)(t.flags | (depth << 4));
         if (j >= cap) return -D_TOO_MANY_FIELDS;
         if (toks) toks[(int64_t)j * stride] = t;
         ++j;
-        while (p < len && is_json_ws(s[p])) ++p;
-        if (p >= len) return -D_SYNTAX;
-        if (s[p] == ',') {
+        bool done = false;
+        for (;;) {  // after a value: the next member, or the end of one or more objects
+            while (p < len && is_json_ws(s[p])) ++p;
+            if (p >= len) return -D_SYNTAX;
+            if (s[p] == ',') {
+                ++p;
+                break;
+            }
+            if (s[p] != '}') return -D_SYNTAX;
             ++p;
-            continue;
+            if (depth == 0) {
+                done = true;
+                break;
+            }
+            --depth;
+            Tok e;
+            e.kind = K_CLOSE;
+            e.vstart = rel + p;
+            e.vlen = 0;
+            e.kstart = rel + p;
+            e.klen = 0;
+            e.flags = (uint8_t)(depth << 4);
+            if (j >= cap) return -D_TOO_MANY_FIELDS;
+            if (toks) toks[(int64_t)j * stride] = e;
+            ++j;
         }
-        if (s[p] == '}') {
-            ++p;
-            break;
-        }
-        return -D_SYNTAX;
+        if (done) break;
     }
     while (p < len && is_json_ws(s[p])) ++p;
     if (p != len) return -D_SYNTAX;

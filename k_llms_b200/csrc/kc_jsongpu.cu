@@ -75,7 +75,7 @@ struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[7] = {};
     DBuf text, off, fcount, slot, status, vbase, xbase, counters, toks, fdesc, piece_c, piece_l, vcells, xcells, win, vmeta, xvalue, xmeta,
-        len_c, len_l, out_c, out_l, scan_tmp, mcount, scount, ccount, mchars, mstr_off, mgrp_off, midx, mavg;
+        len_c, len_l, out_c, out_l, scan_tmp, mcount, scount, ccount, mchars, mstr_off, mgrp_off, midx, mavg, nest, gpos;
     PBuf h_small;  // totals and counters (pinned so the small D2H copies are asynchronous)
     PBuf h_scan;   // the scanned record offsets and the statuses of a chunk
     bool busy = false;
@@ -204,6 +204,7 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     R_(w.fcount.reserve((size_t)(Rc + 1) * 4));
     R_(w.slot.reserve((size_t)(Rc + 1) * 4));
     R_(w.status.reserve((size_t)Rc));
+    R_(w.nest.reserve((size_t)Rc));
     R_(w.vbase.reserve((size_t)Rc * 4));
     R_(w.xbase.reserve((size_t)Rc * 4));
     R_(w.counters.reserve(32));
@@ -227,6 +228,7 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     ch.fcount = w.fcount.as<uint32_t>();
     ch.slot = w.slot.as<uint32_t>();
     ch.status = w.status.as<uint8_t>();
+    ch.nest = w.nest.as<uint8_t>();
     ch.vbase = w.vbase.as<uint32_t>();
     ch.xbase = w.xbase.as<uint32_t>();
     ch.counters = w.counters.as<unsigned long long>();
@@ -263,6 +265,7 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     const size_t Tn = T * (size_t)n;
     R_(w.toks.reserve(std::max<size_t>(Tn, 1) * sizeof(Tok)));
     R_(w.fdesc.reserve(std::max<size_t>(T, 1) * 4));
+    R_(w.gpos.reserve(std::max<size_t>(T, 1) * 4));
     R_(w.piece_c.reserve(std::max<size_t>(T, 1) * 4));
     R_(w.piece_l.reserve(std::max<size_t>(T, 1) * 4));
     R_(w.vcells.reserve(std::max<size_t>(Tn, 16)));
@@ -273,6 +276,7 @@ int run_chunk(Worker &w, const char *h_text, const int64_t *h_off, int64_t r0, i
     R_(w.xmeta.reserve(std::max<size_t>(T, 1) * 4));
     ch.toks = w.toks.as<Tok>();
     ch.fdesc = w.fdesc.as<uint32_t>();
+    ch.gpos = w.gpos.as<uint32_t>();
     ch.piece_c = w.piece_c.as<uint32_t>();
     ch.piece_l = w.piece_l.as<uint32_t>();
     ch.vcells = w.vcells.as<int8_t>();
@@ -605,8 +609,8 @@ struct kc_debug_jsongpu {
     std::vector<uint8_t> text;
     int32_t n = 0;
     int64_t R = 0;
-    std::vector<uint32_t> fcount, slot, fdesc, vbase, xbase, piece_c, piece_l;
-    std::vector<uint8_t> status;
+    std::vector<uint32_t> fcount, slot, fdesc, gpos, vbase, xbase, piece_c, piece_l;
+    std::vector<uint8_t> status, nest;
     std::vector<Tok> toks;
     unsigned long long counters[3] = {0, 0, 0};
     std::vector<uint32_t> mcount, scount, ccount;
@@ -630,6 +634,7 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     h->fcount.assign((size_t)R + 1, 0);
     h->slot.assign((size_t)R + 1, 0);
     h->status.assign((size_t)R, 0);
+    h->nest.assign((size_t)R, 0);
     h->vbase.assign((size_t)R, 0);
     h->xbase.assign((size_t)R, 0);
     h->len_c.assign((size_t)R + 1, 0);
@@ -645,6 +650,7 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     ch.fcount = h->fcount.data();
     ch.slot = h->slot.data();
     ch.status = h->status.data();
+    ch.nest = h->nest.data();
     ch.vbase = h->vbase.data();
     ch.xbase = h->xbase.data();
     ch.counters = h->counters;
@@ -658,12 +664,14 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     const size_t T = h->slot[(size_t)R];
     h->toks.assign(std::max<size_t>(T * n, 1), Tok{});
     h->fdesc.assign(std::max<size_t>(T, 1), 0);
+    h->gpos.assign(std::max<size_t>(T, 1), 0);
     h->piece_c.assign(std::max<size_t>(T, 1), 0);
     h->piece_l.assign(std::max<size_t>(T, 1), 0);
     h->vcells.assign(std::max<size_t>(T * n, 16), (int8_t)-1);
     h->xcells.assign(std::max<size_t>(T * n, 2), 0.0);
     ch.toks = h->toks.data();
     ch.fdesc = h->fdesc.data();
+    ch.gpos = h->gpos.data();
     ch.piece_c = h->piece_c.data();
     ch.piece_l = h->piece_l.data();
     ch.vcells = h->vcells.data();
@@ -672,6 +680,7 @@ int kc_debug_jsongpu_plan(const char *h_text, const int64_t *h_off, int64_t n_re
     for (int32_t r = 0; r < R; ++r) {
         for (int lane = 0; lane < team; ++lane) kc::js::parse_phase(ch, r, lane, team);
         for (int lane = 0; lane < team; ++lane) kc::js::type_phase(ch, r, lane, team);
+        for (int lane = 0; lane < team; ++lane) kc::js::order_phase(ch, r, lane, team);
         kc::js::slots_phase(ch, r);
         for (int lane = 0; lane < team; ++lane) kc::js::encode_phase(ch, r, lane, team);
     }

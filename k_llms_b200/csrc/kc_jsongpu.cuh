@@ -10,8 +10,10 @@
 //   A0  count_kernel    one thread per record scans candidate 0 -> number of fields F_r        (then an exclusive scan: slots)
 //   A1  plan_kernel     a TEAM of lanes per record (team size = n rounded up to a power of two, <= 32):
 //         parse   lane c scans candidate c, one 16-byte token (key span, value span, kind) per field
-//         type    lane j (one per field): same key in every candidate, duplicate / special keys, rank of the key in sorted
-//                 order, which kernel decides the field (plan_leaf of kc_json.cpp)
+//         type    lane j (one per token): same shape in every candidate (same keys, nested objects open / close at the same
+//                 positions), duplicate / special keys, rank of the key among its siblings in sorted order, which kernel
+//                 decides the field (plan_leaf of kc_json.cpp)
+//         order   nested records: the token's position in output order (depth-first, keys sorted at every level)
 //         slots   the team leader numbers the record's vote / numeric groups and reserves rows in the batch's cell matrices
 //         encode  lane j: sanitised-equality classes -> int8 local codes (K1 cells), exact decimal -> float64 (K2 cells)
 //   A2  medoid_kernel   only when the chunk has multi-word string fields (three exclusive scans of the per-record counts first):
@@ -36,9 +38,10 @@ namespace js {
 
 constexpr int32_t kMaxFields = 1024;  // per record; the key ranking is quadratic in it
 
-// field descriptor word: kind:4 | rank:12 | group index within the record:16
-KC_HD inline uint32_t fdesc_pack(uint32_t kind, uint32_t rank, uint32_t gidx) { return kind | (rank << 4) | (gidx << 16); }
-KC_HD inline uint32_t fdesc_kind(uint32_t d) { return d & 15u; }
+// field descriptor word: kind:3 | last of its siblings in key order:1 | rank among its siblings:12 | group index within the record:16
+KC_HD inline uint32_t fdesc_pack(uint32_t kind, uint32_t last, uint32_t rank, uint32_t gidx) { return kind | (last << 3) | (rank << 4) | (gidx << 16); }
+KC_HD inline uint32_t fdesc_kind(uint32_t d) { return d & 7u; }
+KC_HD inline uint32_t fdesc_last(uint32_t d) { return (d >> 3) & 1u; }
 KC_HD inline uint32_t fdesc_rank(uint32_t d) { return (d >> 4) & 0xFFFu; }
 KC_HD inline uint32_t fdesc_gidx(uint32_t d) { return d >> 16; }
 
@@ -46,7 +49,9 @@ struct Chunk {
     const uint8_t *text;  // the chunk's candidate texts (device copy), text[0] is byte off[0] of the caller's blob
     const int64_t *off;   // [R*n + 1] byte offsets of the candidate texts in the caller's blob (record-major)
     int32_t R, n;
-    uint32_t *fcount;   // [R]   A0: fields of candidate 0 (0 when it does not scan)
+    uint32_t *fcount;   // [R]   A0: tokens of candidate 0 (0 when it does not scan)
+    uint8_t *nest;      // [R]   A0: 1 when candidate 0 holds a nested object
+    uint32_t *gpos;     // [slots] nested records only: the token's position in OUTPUT order (sorted keys at every level)
     uint32_t *slot;     // [R+1] exclusive scan of fcount: the record's first field slot
     uint8_t *status;    // [R]   0 = on the device path, else D_*
     Tok *toks;          // [slots * n] token of (field slot, candidate)
@@ -78,8 +83,10 @@ KC_HD inline void decline(const Chunk &ch, int32_t r, int32_t why) { *(volatile 
 KC_HD inline void count_record(const Chunk &ch, int32_t r) {
     const int64_t b = ch.off[(int64_t)r * ch.n], e = ch.off[(int64_t)r * ch.n + 1];
     int32_t f = -D_TOO_LONG;
-    if (e - b < ((int64_t)1 << 31)) f = scan_object(ch.text + (b - ch.off[0]), (uint32_t)(e - b), 0, nullptr, 0, kMaxFields);
+    bool nested = false;
+    if (e - b < ((int64_t)1 << 31)) f = scan_object(ch.text + (b - ch.off[0]), (uint32_t)(e - b), 0, nullptr, 0, kMaxFields, &nested);
     ch.fcount[r] = f > 0 ? (uint32_t)f : 0u;
+    ch.nest[r] = nested ? 1 : 0;
     ch.status[r] = f > 0 ? (uint8_t)D_OK : (uint8_t)(-f);
 }
 
@@ -99,35 +106,76 @@ KC_HD inline void parse_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t 
     }
 }
 
+// The siblings of a token at depth d: the tokens of depth d (other than K_CLOSE) in [lo, hi), the widest range around it in which
+// no token is shallower.  A flat record: every token.
+KC_HD inline void sibling_range(const Tok *rt, int32_t n, int32_t F, int32_t j, uint32_t d, bool flat, int32_t &lo, int32_t &hi) {
+    lo = 0;
+    hi = F;
+    if (flat) return;
+    lo = j;
+    while (lo > 0 && tok_depth(rt[(int64_t)(lo - 1) * n]) >= d) --lo;
+    hi = j + 1;
+    while (hi < F && tok_depth(rt[(int64_t)hi * n]) >= d) ++hi;
+}
+
 KC_HD inline void type_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t team) {
     if (load_status(ch, r)) return;
     const int32_t F = (int32_t)ch.fcount[r], n = ch.n;
+    const bool flat = ch.nest[r] == 0;
     const Tok *rt = ch.toks + (int64_t)ch.slot[r] * n;
     for (int32_t j = lane; j < F; j += team) {
         const Tok *row = rt + (int64_t)j * n;
-        const uint8_t *key = ch.text + row[0].kstart;
-        const uint32_t klen = row[0].klen;
-        // the same key at position j in every candidate (else the key union / missing -> None logic is the host path's)
-        for (int32_t c = 1; c < n; ++c)
-            if (row[c].klen != klen || key_compare(ch.text + row[c].kstart, klen, key, klen) != 0) {
-                decline(ch, r, D_KEYS_DIFFER);
+        const uint32_t k0 = row[0].kind, d = tok_depth(row[0]);
+        // the same SHAPE in every candidate: the same key at position j, nested objects open and close at the same positions
+        // (else the key union / missing -> None / None -> dict of Nones logic of the pre-pass is the host path's, cu:516-548)
+        int32_t ref = j;  // the token whose key orders this one among its siblings: itself, or a K_CLOSE's K_OPEN
+        if (k0 == K_CLOSE) {
+            for (int32_t c = 1; c < n; ++c)
+                if (row[c].kind != K_CLOSE || tok_depth(row[c]) != d) {
+                    decline(ch, r, D_KEYS_DIFFER);
+                    return;
+                }
+            ref = j - 1;  // its K_OPEN: the nearest token to the left at the same depth (everything between them is deeper)
+            while (ref > 0 && tok_depth(rt[(int64_t)ref * n]) != d) --ref;
+        }
+        const uint8_t *key = ch.text + rt[(int64_t)ref * n].kstart;
+        const uint32_t klen = rt[(int64_t)ref * n].klen;
+        if (k0 != K_CLOSE) {
+            for (int32_t c = 1; c < n; ++c) {
+                if ((row[c].kind == K_OPEN) != (k0 == K_OPEN) || row[c].kind == K_CLOSE) {  // an object here, a scalar / None there
+                    decline(ch, r, D_NESTED);
+                    return;
+                }
+                if (tok_depth(row[c]) != d || row[c].klen != klen || key_compare(ch.text + row[c].kstart, klen, key, klen) != 0) {
+                    decline(ch, r, D_KEYS_DIFFER);
+                    return;
+                }
+            }
+            if (contains(key, klen, "reasoning___", 12) || contains(key, klen, "source___", 9) ||  // skipped by consensus_dict (cu:1287-1294)
+                (F == 1 && klen == 4 && key_compare(key, 4, (const uint8_t *)"text", 4) == 0)) {   // {"text": s} -> s (cons:55-57)
+                decline(ch, r, D_SPECIAL_KEY);
                 return;
             }
-        if (contains(key, klen, "reasoning___", 12) || contains(key, klen, "source___", 9) ||  // skipped by consensus_dict (cu:1287-1294)
-            (F == 1 && klen == 4 && key_compare(key, 4, (const uint8_t *)"text", 4) == 0)) {   // {"text": s} -> s (cons:55-57)
-            decline(ch, r, D_SPECIAL_KEY);
-            return;
         }
-        uint32_t rank = 0;  // position of this key in sorted order (cu:521-522); duplicates: dict semantics, host path
-        for (int32_t i = 0; i < F; ++i) {
-            if (i == j) continue;
+        // position of the key among its siblings in sorted order (cu:521-522, at every level); duplicates: dict semantics, host path
+        int32_t lo, hi;
+        sibling_range(rt, n, F, ref, d, flat, lo, hi);
+        uint32_t rank = 0, after = 0;
+        for (int32_t i = lo; i < hi; ++i) {
             const Tok &o = rt[(int64_t)i * n];
+            if (i == ref || (!flat && (tok_depth(o) != d || o.kind == K_CLOSE))) continue;
             const int cmp = key_compare(ch.text + o.kstart, o.klen, key, klen);
             if (cmp == 0) {
                 decline(ch, r, D_DUP_KEY);
                 return;
             }
             rank += cmp < 0 ? 1u : 0u;
+            after += cmp > 0 ? 1u : 0u;
+        }
+        const uint32_t last = after == 0 ? 1u : 0u;
+        if (k0 == K_OPEN || k0 == K_CLOSE) {
+            ch.fdesc[ch.slot[r] + j] = fdesc_pack(k0 == K_OPEN ? F_OPEN : F_CLOSE, last, rank, 0);
+            continue;
         }
         // which kernel decides the field (plan_leaf, kc_json.cpp; cu:1405-1411, :1443-1453)
         int32_t first = -1;
@@ -179,8 +227,54 @@ KC_HD inline void type_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t t
         } else {
             kind = F_NUMERIC;  // strings / bools among the cells are "present, not a number" (cu:1105-1114)
         }
-        ch.fdesc[ch.slot[r] + j] = fdesc_pack(kind, rank, 0);
+        ch.fdesc[ch.slot[r] + j] = fdesc_pack(kind, last, rank, 0);
     }
+}
+
+// Nested records only, after type_phase: the token's position in output order.  Output is a depth-first walk with the members
+// of every object in key order, so a token comes after its parent's K_OPEN and after the whole subtrees of the siblings that
+// sort before it; a K_CLOSE comes last in its object's subtree.
+KC_HD inline void order_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t team) {
+    if (load_status(ch, r) || ch.nest[r] == 0) return;
+    const int32_t F = (int32_t)ch.fcount[r], n = ch.n;
+    const Tok *rt = ch.toks + (int64_t)ch.slot[r] * n;
+    const uint32_t *fd = ch.fdesc + ch.slot[r];
+    auto subtree = [&](int32_t i) -> uint32_t {  // tokens in the subtree of token i (itself included)
+        if (rt[(int64_t)i * n].kind != K_OPEN) return 1u;
+        const uint32_t d = tok_depth(rt[(int64_t)i * n]);
+        int32_t e = i + 1;
+        while (tok_depth(rt[(int64_t)e * n]) != d) ++e;  // its K_CLOSE
+        return (uint32_t)(e - i + 1);
+    };
+    for (int32_t j = lane; j < F; j += team) {
+        const bool closing = rt[(int64_t)j * n].kind == K_CLOSE;
+        uint32_t d = tok_depth(rt[(int64_t)j * n]);
+        int32_t cur = j;
+        if (closing) {
+            cur = j - 1;
+            while (cur > 0 && tok_depth(rt[(int64_t)cur * n]) != d) --cur;
+        }
+        uint32_t pos = closing ? subtree(cur) - 1u : 0u;
+        for (;;) {
+            int32_t lo, hi;
+            sibling_range(rt, n, F, cur, d, false, lo, hi);
+            const uint32_t rank = fdesc_rank(fd[cur]);
+            for (int32_t i = lo; i < hi; ++i) {
+                const Tok &o = rt[(int64_t)i * n];
+                if (i == cur || tok_depth(o) != d || o.kind == K_CLOSE) continue;
+                if (fdesc_rank(fd[i]) < rank) pos += subtree(i);
+            }
+            if (d == 0) break;
+            pos += 1u;     // the parent's K_OPEN, the token just before the first sibling
+            cur = lo - 1;
+            --d;
+        }
+        ch.gpos[ch.slot[r] + j] = pos;
+    }
+}
+
+KC_HD inline uint32_t out_pos(const Chunk &ch, int32_t r, int32_t j) {
+    return ch.nest[r] ? ch.gpos[ch.slot[r] + j] : fdesc_rank(ch.fdesc[ch.slot[r] + j]);
 }
 
 // team leader only: number the groups, reserve rows of the cell matrices (chunk-wide counters)
@@ -381,12 +475,22 @@ KC_HD inline void len_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t te
     if (load_status(ch, r)) return;
     const int32_t F = (int32_t)ch.fcount[r], n = ch.n;
     for (int32_t j = lane; j < F; j += team) {
-        Sink c{nullptr, 0}, l{nullptr, 0};
-        format_field(ch, r, j, c, l);
+        const uint32_t d = ch.fdesc[ch.slot[r] + j], kind = fdesc_kind(d), sep = fdesc_last(d) ? 0u : 2u;  // ", " unless last of its siblings
         const uint32_t klen = ch.toks[((int64_t)ch.slot[r] + j) * n].klen;
-        const uint32_t rank = fdesc_rank(ch.fdesc[ch.slot[r] + j]);
-        ch.piece_c[ch.slot[r] + rank] = klen + 4u + (uint32_t)c.n;  // "key": value
-        ch.piece_l[ch.slot[r] + rank] = klen + 4u + (uint32_t)l.n;
+        const uint32_t pos = out_pos(ch, r, j);
+        uint32_t lc, ll;
+        if (kind == F_OPEN) {
+            lc = ll = klen + 5u;  // "key": {
+        } else if (kind == F_CLOSE) {
+            lc = ll = 1u + sep;   // }
+        } else {
+            Sink c{nullptr, 0}, l{nullptr, 0};
+            format_field(ch, r, j, c, l);
+            lc = klen + 4u + (uint32_t)c.n + sep;  // "key": value
+            ll = klen + 4u + (uint32_t)l.n + sep;
+        }
+        ch.piece_c[ch.slot[r] + pos] = lc;
+        ch.piece_l[ch.slot[r] + pos] = ll;
     }
 }
 
@@ -400,12 +504,12 @@ KC_HD inline void offsets_phase(const Chunk &ch, int32_t r) {
     const int32_t F = (int32_t)ch.fcount[r];
     uint32_t *pc = ch.piece_c + ch.slot[r], *pl = ch.piece_l + ch.slot[r];
     uint32_t oc = 1, ol = 1;  // after '{'
-    for (int32_t k = 0; k < F; ++k) {
+    for (int32_t k = 0; k < F; ++k) {  // pieces in output order, separators included
         const uint32_t lc = pc[k], ll = pl[k];
         pc[k] = oc;
         pl[k] = ol;
-        oc += lc + (k + 1 < F ? 2u : 0u);  // ", "
-        ol += ll + (k + 1 < F ? 2u : 0u);
+        oc += lc;
+        ol += ll;
     }
     ch.len_c[r] = (int64_t)oc + 1;  // '}'
     ch.len_l[r] = (int64_t)ol + 1;
@@ -417,23 +521,34 @@ KC_HD inline void write_phase(const Chunk &ch, int32_t r, int32_t lane, int32_t 
     uint8_t *oc = ch.out_c + ch.len_c[r], *ol = ch.out_l + ch.len_l[r];  // len_* hold the scanned offsets now
     for (int32_t j = lane; j < F; j += team) {
         const Tok &t0 = ch.toks[((int64_t)ch.slot[r] + j) * n];
-        const uint32_t rank = fdesc_rank(ch.fdesc[ch.slot[r] + j]);
-        Sink c{oc + ch.piece_c[ch.slot[r] + rank], 0}, l{ol + ch.piece_l[ch.slot[r] + rank], 0};
-        if (rank == 0) {
+        const uint32_t d = ch.fdesc[ch.slot[r] + j], kind = fdesc_kind(d);
+        const uint32_t pos = out_pos(ch, r, j);
+        Sink c{oc + ch.piece_c[ch.slot[r] + pos], 0}, l{ol + ch.piece_l[ch.slot[r] + pos], 0};
+        if (pos == 0) {
             oc[0] = '{';
             ol[0] = '{';
         }
-        c.put('"');
-        c.put(ch.text + t0.kstart, t0.klen);
-        c.lit("\": ");
-        l.put('"');
-        l.put(ch.text + t0.kstart, t0.klen);
-        l.lit("\": ");
-        format_field(ch, r, j, c, l);
-        if ((int32_t)rank + 1 < F) {
+        if (kind == F_CLOSE) {
+            c.put('}');
+            l.put('}');
+        } else {
+            c.put('"');
+            c.put(ch.text + t0.kstart, t0.klen);
+            c.lit("\": ");
+            l.put('"');
+            l.put(ch.text + t0.kstart, t0.klen);
+            l.lit("\": ");
+            if (kind == F_OPEN) {
+                c.put('{');
+                l.put('{');
+                continue;
+            }
+            format_field(ch, r, j, c, l);
+        }
+        if (!fdesc_last(d)) {
             c.lit(", ");
             l.lit(", ");
-        } else {
+        } else if (tok_depth(t0) == 0) {  // the last piece of the record closes the top-level object
             c.put('}');
             l.put('}');
         }
@@ -462,6 +577,8 @@ __global__ void __launch_bounds__(128) plan_kernel(const Chunk ch, int32_t team)
         if (live) parse_phase(ch, r, lane, team);
         __syncwarp();
         if (live) type_phase(ch, r, lane, team);
+        __syncwarp();
+        if (live) order_phase(ch, r, lane, team);  // nested records only; reads the ranks its team wrote
         __syncwarp();
         if (live && lane == 0) slots_phase(ch, r);
         __syncwarp();

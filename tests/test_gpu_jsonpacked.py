@@ -10,7 +10,7 @@ import pytest
 
 from k_llms_b200 import _native as K
 from tests.test_gpu_json import _expected, _expected_with_lists, _random_nested_record, _random_record
-from tests.test_jsongpu_host_logic import _flat_record, _phrase_record, s32_texts
+from tests.test_jsongpu_host_logic import _flat_record, _phrase_record, _shaped_record, s32_texts
 
 pytestmark = pytest.mark.gpu
 
@@ -73,6 +73,27 @@ def test_phrase_fields_medoid_on_the_device():
     for r in random.Random(5).sample(range(len(recs)), 400) + [16, 17, 18]:
         if res.status[r] != 1:
             assert (res.content(r), res.likelihoods(r)) == _expected_with_lists(recs[r]), (recs[r], res.status[r])
+
+
+def test_nested_objects_on_the_device():
+    """Candidates of one shape with nested objects (depth <= 4): structure tokens, per-level key order and the nested output are
+    the device's; byte-identical to the reference's client order."""
+    rng = random.Random(41)
+    by_n = {}
+    for _ in range(1500):
+        n = rng.choice([2, 3, 4, 5, 8, 16, 33])
+        by_n.setdefault(n, []).append(_shaped_record(rng, n))
+    on_device = nested = 0
+    for _n, recs in by_n.items():
+        res = run(recs)
+        for r, texts in enumerate(recs):
+            if res.status[r] == 1:
+                continue
+            if res.status[r] == 0:
+                on_device += 1
+                nested += any(isinstance(v, dict) for v in json.loads(texts[0]).values())
+            assert (res.content(r), res.likelihoods(r)) == _expected(texts), (texts, res.status[r], res.why[r])
+    assert on_device > 1300 and nested > 700, (on_device, nested)
 
 
 def test_general_and_mutated_records_never_wrong():

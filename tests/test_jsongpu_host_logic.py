@@ -184,6 +184,71 @@ def test_two_character_escapes_in_values():
     assert accepted > 200, accepted
 
 
+def _shaped_record(rng, n):
+    """n candidates of ONE shape (same keys in the same textual order at every level, keys not in sorted order) whose leaves
+    disagree: nested objects up to depth 4 next to every kind of scalar field."""
+    def shape(depth):
+        keys = rng.sample(["zeta", "Alpha", "b", "a", "aa", "k1", "k10", "k2", "Z", "id", "name", "addr"], rng.randrange(1, 6))
+        out = []
+        for k in keys:
+            if depth < 4 and rng.random() < 0.3:
+                out.append((k, shape(depth + 1)))
+            else:
+                out.append((k, rng.choice(["enum", "bool", "int", "float", "phrase", "allnull", "one"])))
+        return out
+
+    def truth_of(sh):
+        return [(k, truth_of(v) if isinstance(v, list) else
+                 {"enum": lambda: rng.choice(["alpha", "Bravo", "two words", ""]), "bool": lambda: rng.random() < 0.5,
+                  "int": lambda: rng.randrange(-5, 10 ** rng.randrange(1, 7)), "float": lambda: rng.uniform(-10, 1e4),
+                  "phrase": lambda: rng.choice(PHRASES[:10]), "allnull": lambda: None, "one": lambda: rng.choice([7, "solo", 2.5])}[v]())
+                for k, v in sh]
+
+    def candidate(sh, tr, c):
+        d = {}
+        for (k, kind), (_k, tv) in zip(sh, tr):
+            if isinstance(kind, list):
+                d[k] = candidate(kind, tv, c)
+                continue
+            v, r = tv, rng.random()
+            if kind == "one":
+                v = v if c == 0 else None
+            elif r < 0.3:
+                v = {"enum": lambda: rng.choice(["ALPHA", "bravo!", "x"]), "bool": lambda: rng.random() < 0.5, "int": lambda: rng.randrange(0, 100),
+                     "float": lambda: rng.uniform(0, 10), "phrase": lambda: rng.choice(PHRASES), "allnull": lambda: None}[kind]()
+            elif r > 0.92:
+                v = None
+            d[k] = v
+        return d
+
+    sh = shape(1)
+    tr = truth_of(sh)
+    texts = []
+    for c in range(n):
+        t = json.dumps(candidate(sh, tr, c))
+        if rng.random() < 0.1:
+            t = t.replace(", ", " ,\n\t").replace("{", "{ ").replace("}", " }\r\n")
+        texts.append(t)
+    return texts
+
+
+def test_nested_objects_of_one_shape():
+    rng = random.Random(41)
+    by_n, on_device, nested = {}, 0, 0
+    for _ in range(1500):
+        n = rng.choice([2, 3, 4, 5, 8, 16, 33])
+        by_n.setdefault(n, []).append(_shaped_record(rng, n))
+    for _n, recs in by_n.items():
+        pairs, status = jsongpu_with_oracle(recs)
+        for texts, got, st in zip(recs, pairs, status):
+            if got is None:
+                continue
+            on_device += 1
+            nested += any(isinstance(v, dict) for v in json.loads(texts[0]).values())
+            assert got == _expected(texts), (texts, st)
+    assert on_device > 1300 and nested > 700, (on_device, nested)
+
+
 def test_general_records_accepted_or_declined():
     """The generators of the host-path tests (missing keys, nested objects, phrases, big ints, escapes, mixed types): the device
     path declines most of them; what it accepts must be exact."""
@@ -245,7 +310,15 @@ def test_declines_what_it_does_not_model():
         "escape in a key": ['{"a\\n": "x"}', '{"a\\n": "x"}'],
         "bad escape": ['{"a": "x\\qy"}', '{"a": "x"}'],
         "non-ascii": ['{"a": "café"}', '{"a": "cafe"}'],
-        "nested": ['{"a": {"b": 1}}', '{"a": {"b": 1}}'],
+        "nested here, None there": ['{"a": {"b": 1}}', '{"a": null}'],
+        "nested here, scalar there": ['{"a": {"b": 1}}', '{"a": 3}'],
+        "nested keys differ": ['{"a": {"b": 1}}', '{"a": {"c": 1}}'],
+        "nested shapes differ": ['{"a": {"b": 1}, "c": 2}', '{"a": {"b": 1, "c": 2}}'],
+        "empty nested object": ['{"a": {}}', '{"a": {}}'],
+        "nested duplicate key": ['{"a": {"b": 1, "b": 2}}', '{"a": {"b": 1, "b": 2}}'],
+        "nested special key": ['{"a": {"reasoning___b": "x", "c": 1}}', '{"a": {"reasoning___b": "y", "c": 1}}'],
+        "list in a nested object": ['{"a": {"b": [1]}}', '{"a": {"b": [1]}}'],
+        "nine levels": ['{"a": ' * 10 + '1' + '}' * 10] * 2,
         "list": ['{"a": [1, 2]}', '{"a": [1, 2]}'],
         "keys differ": ['{"a": 1, "b": 2}', '{"a": 1}'],
         "key order differs": ['{"a": 1, "b": 2}', '{"b": 2, "a": 1}'],

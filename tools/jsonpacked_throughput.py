@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from k_llms_b200 import _native as K  # noqa: E402
 
 
-def invoice_texts(records, n, seed):
+def invoice_texts(records, n, seed, nested=False):
     """An extraction-like schema with FREE-TEXT fields (multi-word strings -> similarity medoid, K4) next to enums, bools and
     numbers: 4 phrases, 3 enums, 2 bools, 3 numbers per record; every candidate copies the record's truth with probability 0.8
     per field, otherwise a variant (case / punctuation / one word changed / another value), None with probability 0.05."""
@@ -54,6 +54,11 @@ def invoice_texts(records, n, seed):
                     else:
                         v = v + rng.choice([0, 1])
                 d[k] = v
+            if nested:  # the same fields as an extraction schema would nest them (depth 3)
+                d = {"vendor": {"name": d["vendor"], "location": {"address": d["address"], "currency": d["currency"]}},
+                     "payment": {"terms": d["terms"], "status": d["status"], "signed": d["signed"]},
+                     "amounts": {"total": d["total"], "tax": d["tax"], "taxable": d["taxable"]},
+                     "kind": d["kind"], "note": d["note"], "items": d["items"]}
             cands.append(json.dumps(d))
         out.append(cands)
     return out
@@ -61,8 +66,9 @@ def invoice_texts(records, n, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", choices=["s32", "invoice"], default="s32",
-                    help="s32: the bench schema (enum / bool / number fields); invoice: 12 fields, 4 of them free text (medoid, K4)")
+    ap.add_argument("--workload", choices=["s32", "invoice", "invoice_nested"], default="s32",
+                    help="s32: the bench schema (enum / bool / number fields); invoice: 12 fields, 4 of them free text (medoid, K4); "
+                         "invoice_nested: the same fields in nested objects (depth 3)")
     ap.add_argument("--records", type=int, default=262144)
     ap.add_argument("--n", type=int, default=16)
     ap.add_argument("--reps", type=int, default=4)
@@ -71,8 +77,8 @@ def main():
     ap.add_argument("--pageable", action="store_true", help="input blob in ordinary (not page-locked) memory")
     args = ap.parse_args()
     t0 = time.perf_counter()
-    if args.workload == "invoice":
-        blob, off, _n = K.pack_texts(invoice_texts(args.records, args.n, 11), pinned=not args.pageable)
+    if args.workload != "s32":
+        blob, off, _n = K.pack_texts(invoice_texts(args.records, args.n, 11, nested=args.workload == "invoice_nested"), pinned=not args.pageable)
     else:
         blob, off = K.s32_texts_packed(args.records, args.n, 11, pinned=not args.pageable)
     gen_s = time.perf_counter() - t0
