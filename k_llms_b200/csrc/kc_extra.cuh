@@ -246,6 +246,94 @@ __global__ void __launch_bounds__(128) weighted_vote_kernel(const int32_t *__res
     }
 }
 
+// The weighted vote of ONE group by one thread: rawrow = the group's cells (code >= 0, KC_CODE_NONE, absent < KC_CODE_NONE), nc = the
+// code None votes as (KC_CODE_NONE: it does not), w = the candidate weights of the group's record (shared memory).
+template <int NP>
+__device__ __forceinline__ void weighted_core(const int32_t (&rawrow)[NP], int32_t nc, const float *w, int32_t &out_code,
+                                              uint32_t &out_meta, float &out_weight) {
+    using M = typename MaskOf<NP>::type;
+    int32_t x[NP];
+    M live = 0;
+    int present = 0;
+    float total = 0.0f, wmax = -1.0f;
+    int32_t cmax = KC_CODE_NONE;  // the code of this group's heaviest VOTING cell (first of equals)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int32_t raw = rawrow[i];
+        int32_t c = (raw == KC_CODE_NONE) ? nc : raw;  // None votes as none_code where it is >= 0
+        c = c < KC_CODE_NONE ? KC_CODE_NONE : c;        // absent cells never vote
+        x[i] = c;
+        present += raw < KC_CODE_NONE ? 0 : 1;
+        if (c >= 0) {
+            live |= M(1) << i;
+            const float wi = w[i];
+            total = __fadd_rn(total, wi);
+            if (wi > wmax) {
+                wmax = wi;
+                cmax = c;
+            }
+        }
+    }
+    const int voters = popc_m(live);
+    float best_w = -1.0f;
+    int best_idx = 0, best_cnt = 0;
+    int32_t best_code = KC_CODE_NONE;
+    bool tie = false;
+    float consumed = 0.0f;
+    // Order of the walk: always the class of the heaviest cell still waiting (the first one: this group's heaviest
+    // voting cell).  The outcome does not depend on the order (the heaviest class wins, equal weights go to the class
+    // seen first = smaller first index, `tie` says whether another class equals the winner), but the COST does: a warp
+    // loops until its slowest lane is done.  The heaviest voter's class usually holds more than half of the weight and
+    // ends the walk at once; where it does not, going by weight makes the remainder shrink fastest.  (Round 1 walked
+    // in first-seen order after the record's heaviest candidate: 4.3 class passes per warp, and it parked every
+    // group's codes in a shared-memory plane to fetch the next class's code by a data-dependent index; here the pass
+    // over the cells finds the next class itself — no shared memory for the codes at all.)
+    int32_t c = cmax;
+    while (live) {
+        // Every class still waiting sums a subset of the unconsumed weights, so its fp32 sum is at most
+        // (total - consumed) up to rounding (< 32 * 2^-23 relative on each side); 5e-5 * total is a safe slack.
+        // Below best_w it can neither win nor tie: stop.
+        if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;
+        M eq = 0;
+        float cw = 0.0f, nw = -1.0f;
+        int32_t nc2 = KC_CODE_NONE;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const bool e = x[j] == c;  // cells with this code that came earlier were consumed with their class
+            const float wj = w[j];
+            eq |= e ? (M(1) << j) : M(0);
+            cw = e ? __fadd_rn(cw, wj) : cw;
+            const bool waiting = !e && ((live >> j) & 1);
+            if (waiting && wj > nw) {  // heaviest cell of the classes still waiting (first of equals)
+                nw = wj;
+                nc2 = x[j];
+            }
+        }
+        const int i = ffs_mask(eq) - 1;  // the class's first cell
+        if (cw > best_w) {
+            best_w = cw;
+            best_idx = i;
+            best_cnt = popc_m(eq);
+            best_code = c;
+            tie = false;
+        } else if (cw == best_w) {
+            tie = true;
+            if (i < best_idx) {  // an equally heavy class that was seen earlier
+                best_idx = i;
+                best_cnt = popc_m(eq);
+                best_code = c;
+            }
+        }
+        consumed = __fadd_rn(consumed, cw);
+        live &= ~eq;
+        c = nc2;
+        if (c < 0) break;  // no waiting cell had a comparable weight (NaN logprobs: outside the spec); never spin
+    }
+    out_code = best_code;
+    out_meta = pack_meta(best_idx, best_cnt, voters, present, voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
+    out_weight = voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
+}
+
 // K3b, weights once per record: the candidate weights depend on the record only, not on the field.  A CTA of T threads
 // covers T consecutive groups (fields of a handful of records); its warps first compute w_c = kexp(s_c - max s) for
 // those records into shared memory (lane = candidate, warp max by shuffles), then every thread votes its group with the
@@ -283,89 +371,332 @@ __global__ void __launch_bounds__(T) weighted_vote_rec_kernel(const int32_t *__r
             const float *w = wts + rec_local * NP;
             // (requesting the row BEFORE the weights phase was tried: it keeps 32 more registers live across the barrier,
             // 67 -> 94, and the lost occupancy cost more than the overlap gained: 0.357 -> 0.379 ms)
-            int32_t x[NP], rawrow[NP];
+            int32_t rawrow[NP];
             if (n == NP) load_row<NP, true>(codes, g, n, rawrow);
             else load_row<NP, false>(codes, g, n, rawrow);
-            M live = 0;
-            int present = 0;
-            float total = 0.0f, wmax = -1.0f;
-            int32_t cmax = KC_CODE_NONE;  // the code of this group's heaviest VOTING cell (first of equals)
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int32_t raw = rawrow[i];
-                int32_t c = (raw == KC_CODE_NONE) ? nc : raw;  // None votes as none_code where it is >= 0
-                c = c < KC_CODE_NONE ? KC_CODE_NONE : c;        // absent cells never vote
-                x[i] = c;
-                present += raw < KC_CODE_NONE ? 0 : 1;
-                if (c >= 0) {
-                    live |= M(1) << i;
-                    const float wi = w[i];
-                    total = __fadd_rn(total, wi);
-                    if (wi > wmax) {
-                        wmax = wi;
-                        cmax = c;
-                    }
-                }
-            }
-            const int voters = popc_m(live);
-            float best_w = -1.0f;
-            int best_idx = 0, best_cnt = 0;
-            int32_t best_code = KC_CODE_NONE;
-            bool tie = false;
-            float consumed = 0.0f;
-            // Order of the walk: always the class of the heaviest cell still waiting (the first one: this group's heaviest
-            // voting cell).  The outcome does not depend on the order (the heaviest class wins, equal weights go to the class
-            // seen first = smaller first index, `tie` says whether another class equals the winner), but the COST does: a warp
-            // loops until its slowest lane is done.  The heaviest voter's class usually holds more than half of the weight and
-            // ends the walk at once; where it does not, going by weight makes the remainder shrink fastest.  (Round 1 walked
-            // in first-seen order after the record's heaviest candidate: 4.3 class passes per warp, and it parked every
-            // group's codes in a shared-memory plane to fetch the next class's code by a data-dependent index; here the pass
-            // over the cells finds the next class itself — no shared memory for the codes at all.)
-            int32_t c = cmax;
-            while (live) {
-                // Every class still waiting sums a subset of the unconsumed weights, so its fp32 sum is at most
-                // (total - consumed) up to rounding (< 32 * 2^-23 relative on each side); 5e-5 * total is a safe slack.
-                // Below best_w it can neither win nor tie: stop.
-                if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;
-                M eq = 0;
-                float cw = 0.0f, nw = -1.0f;
-                int32_t nc2 = KC_CODE_NONE;
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const bool e = x[j] == c;  // cells with this code that came earlier were consumed with their class
-                    const float wj = w[j];
-                    eq |= e ? (M(1) << j) : M(0);
-                    cw = e ? __fadd_rn(cw, wj) : cw;
-                    const bool waiting = !e && ((live >> j) & 1);
-                    if (waiting && wj > nw) {  // heaviest cell of the classes still waiting (first of equals)
-                        nw = wj;
-                        nc2 = x[j];
-                    }
-                }
-                const int i = ffs_mask(eq) - 1;  // the class's first cell
-                if (cw > best_w) {
-                    best_w = cw;
-                    best_idx = i;
-                    best_cnt = popc_m(eq);
-                    best_code = c;
-                    tie = false;
-                } else if (cw == best_w) {
-                    tie = true;
-                    if (i < best_idx) {  // an equally heavy class that was seen earlier
-                        best_idx = i;
-                        best_cnt = popc_m(eq);
-                        best_code = c;
-                    }
-                }
-                consumed = __fadd_rn(consumed, cw);
-                live &= ~eq;
-                c = nc2;
-            }
-            win[g] = best_code;
-            meta[g] = pack_meta(best_idx, best_cnt, voters, present, voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
-            weight[g] = voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
+            weighted_core<NP>(rawrow, nc, w, win[g], meta[g], weight[g]);
         }
         __syncthreads();
+    }
+}
+
+// ---- K3b, TMA front-end: first pass per lane, undecided groups by the whole warp
+
+// What a lane knows about its group after ONE pass over the cells: the mapped codes, the total weight of the voting cells and the
+// class of the record's heaviest candidate (the guess), summed in index order exactly as a walk pass would.
+template <int N>
+struct WvFirst {
+    using M = typename MaskOf<N>::type;
+    int32_t x[N];
+    M eq_g;
+    float total, cw_g;
+    int32_t guess;
+    int voters, present;
+    bool decided;  // the guess's class holds a strict majority of the weight: it is the unique winner
+};
+
+template <int N>
+__device__ __forceinline__ void wv_first_pass(const int32_t (&raw)[N], int32_t lo, int32_t nc, const float *w, int32_t graw, WvFirst<N> &f) {
+    using M = typename MaskOf<N>::type;
+    f.eq_g = 0;
+    f.total = 0.0f;
+    f.cw_g = 0.0f;
+    if (lo >= 0) {
+        // every cell votes with its own code (no None, no absent cell — the common row): 2-3 ALU instructions per cell
+        f.guess = graw < 0 ? KC_CODE_NONE : graw;
+        f.voters = f.present = N;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float wi = w[i];
+            const bool e = raw[i] == f.guess;
+            f.x[i] = raw[i];
+            f.total = __fadd_rn(f.total, wi);
+            if (e) {
+                f.eq_g |= M(1) << i;
+                f.cw_g = __fadd_rn(f.cw_g, wi);
+            }
+        }
+    } else {
+        int32_t guess = (graw == KC_CODE_NONE) ? nc : graw;
+        f.guess = guess < KC_CODE_NONE ? KC_CODE_NONE : guess;  // the heaviest candidate does not vote here: no guess
+        M live = 0;
+        int present = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int32_t r = raw[i];
+            int32_t c = (r == KC_CODE_NONE) ? nc : r;  // None votes as none_code where it is >= 0
+            c = c < KC_CODE_NONE ? KC_CODE_NONE : c;    // absent cells never vote
+            f.x[i] = c;
+            present += r < KC_CODE_NONE ? 0 : 1;
+            if (c >= 0) {
+                live |= M(1) << i;
+                const float wi = w[i];
+                f.total = __fadd_rn(f.total, wi);
+                if (c == f.guess) {
+                    f.eq_g |= M(1) << i;
+                    f.cw_g = __fadd_rn(f.cw_g, wi);
+                }
+            }
+        }
+        f.voters = popc_m(live);
+        f.present = present;
+    }
+    // every other class sums a subset of the remaining weights: at most (total - cw_g) up to rounding (< 64 * 2^-23 relative on
+    // each side; 5e-5 * total is a safe slack).  Strictly below cw_g it can neither win nor tie.
+    f.decided = f.guess >= 0 && f.cw_g > __fadd_rn(__fadd_rn(f.total, -f.cw_g), __fmul_rn(f.total, 5e-5f));
+}
+
+// The general walk (see weighted_core) for ONE group by the WHOLE warp: lane j holds cells j and j + 32 of the owner's group.  A
+// thread-per-group walk makes the warp wait for its slowest lane — a few percent of the groups are undecided after the first
+// pass, but most warps hold one — and spends 32 lanes on one lane's work; here an undecided group costs ~150 warp instructions.
+// Same visiting order (the class of the heaviest cell still waiting, first of equals), same class sums (index order, one
+// rounding per addition), same tie rules: the result is bit-identical.  All arguments except `owner` are the OWNER's values.
+template <int N>
+__device__ __forceinline__ void wv_warp_walk(uint32_t lane, uint32_t owner, const WvFirst<N> &f, const float *wts, uint32_t rec_local, int WROW,
+                                             int32_t &out_code, uint32_t &out_meta, float &out_weight) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    // the owner's cells, one (two) per lane
+    int32_t c_lo = KC_CODE_NONE, c_hi = KC_CODE_NONE;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int32_t v = __shfl_sync(FULL, f.x[j], owner);
+        if (lane == (uint32_t)(j & 31)) {
+            if (j < 32) c_lo = v;
+            else c_hi = v;
+        }
+    }
+    const float *w = wts + __shfl_sync(FULL, rec_local, owner) * WROW;
+    const float w_lo = w[lane], w_hi = N > 32 ? w[lane + 32] : 0.0f;
+    const float total = __shfl_sync(FULL, f.total, owner);
+    const int32_t guess = __shfl_sync(FULL, f.guess, owner);
+    const float cw_g = __shfl_sync(FULL, f.cw_g, owner);
+    uint32_t live_lo = __ballot_sync(FULL, c_lo >= 0), live_hi = N > 32 ? __ballot_sync(FULL, c_hi >= 0) : 0u;
+    float best_w = -1.0f, consumed = 0.0f;
+    int best_idx = 0, best_cnt = 0;
+    int32_t best_code = KC_CODE_NONE;
+    bool tie = false;
+    if (guess >= 0) {  // the first pass summed the guess's class: it is the best so far
+        const uint32_t g_lo = __ballot_sync(FULL, c_lo == guess), g_hi = N > 32 ? __ballot_sync(FULL, c_hi == guess) : 0u;
+        best_w = cw_g;
+        best_idx = g_lo ? __ffs((int)g_lo) - 1 : 31 + __ffs((int)g_hi);
+        best_cnt = __popc(g_lo) + __popc(g_hi);
+        best_code = guess;
+        consumed = cw_g;
+        live_lo &= ~g_lo;
+        live_hi &= ~g_hi;
+    }
+    while (live_lo | live_hi) {
+        if (__fadd_rn(__fadd_rn(total, -consumed), __fmul_rn(total, 5e-5f)) < best_w) break;  // the rest can neither win nor tie
+        // the heaviest cell still waiting, first of equals
+        float mx = fmaxf(((live_lo >> lane) & 1u) ? w_lo : -1.0f, (N > 32 && ((live_hi >> lane) & 1u)) ? w_hi : -1.0f);
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, st));
+        const uint32_t a_lo = __ballot_sync(FULL, ((live_lo >> lane) & 1u) && w_lo == mx);
+        const uint32_t a_hi = N > 32 ? __ballot_sync(FULL, ((live_hi >> lane) & 1u) && w_hi == mx) : 0u;
+        if (!(a_lo | a_hi)) break;  // only NaN weights are left (NaN logprobs: outside the spec); never spin
+        const int32_t c = a_lo ? __shfl_sync(FULL, c_lo, __ffs((int)a_lo) - 1) : __shfl_sync(FULL, c_hi, __ffs((int)a_hi) - 1);
+        const uint32_t e_lo = __ballot_sync(FULL, c_lo == c), e_hi = N > 32 ? __ballot_sync(FULL, c_hi == c) : 0u;
+        float cw = 0.0f;  // the class's weights in index order
+        for (uint32_t m = e_lo; m; m &= m - 1) cw = __fadd_rn(cw, __shfl_sync(FULL, w_lo, __ffs((int)m) - 1));
+        if (N > 32)
+            for (uint32_t m = e_hi; m; m &= m - 1) cw = __fadd_rn(cw, __shfl_sync(FULL, w_hi, __ffs((int)m) - 1));
+        const int i = e_lo ? __ffs((int)e_lo) - 1 : 31 + __ffs((int)e_hi);
+        const int cnt = __popc(e_lo) + __popc(e_hi);
+        if (cw > best_w) {
+            best_w = cw;
+            best_idx = i;
+            best_cnt = cnt;
+            best_code = c;
+            tie = false;
+        } else if (cw == best_w) {
+            tie = true;
+            if (i < best_idx) {  // an equally heavy class that was seen earlier
+                best_idx = i;
+                best_cnt = cnt;
+                best_code = c;
+            }
+        }
+        consumed = __fadd_rn(consumed, cw);
+        live_lo &= ~e_lo;
+        live_hi &= ~e_hi;
+    }
+    if (lane == owner) {
+        out_code = best_code;
+        out_meta = pack_meta(best_idx, best_cnt, f.voters, f.present, f.voters > 0 ? (KC_FLAG_HAS_VALUE | (tie ? KC_FLAG_TIE : 0u)) : 0u);
+        out_weight = f.voters > 0 ? __fdiv_rn(best_w, total) : 0.0f;
+    }
+}
+
+// K3b with K1's TMA front-end (n in {32, 64} cells per group = 128 / 256 byte rows): every WARP runs its own pipeline of STAGES
+// tiles of 32 consecutive groups (one cp.async.bulk.tensor.2d per tile, hardware swizzle, the warp's own mbarrier, conflict-free
+// LDS.128; see vote_tma_kernel) instead of one 128-byte row per thread straight from global memory (latency-bound at 0.39 of the
+// HBM peak: a warp's 32 rows are 32 separate lines per load instruction).  The weights of the tile's records (32 groups span
+// 32 / n_fields + 2 records at most) are computed by the warp itself into its own shared-memory rows (lane = candidate, warp
+// max by shuffles), padded by one float so that lanes of different records read different banks; the pad slot carries the index of
+// the record's heaviest candidate, whose class weighted_core sums in its first pass (one pass decides most groups).  No block-wide
+// barrier.
+template <int N, int WARPS, int STAGES, int MIN_CTAS, bool PREFETCH>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) weighted_vote_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ seq_lp,
+                                                                       uint32_t n_groups, FieldMap fm, bool has_nc, int rec_cap, uint64_t inv_fields,
+                                                                       int32_t *__restrict__ win, uint32_t *__restrict__ meta,
+                                                                       float *__restrict__ weight) {
+    constexpr int ROW_BYTES = N * 4;
+    constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
+    constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
+    constexpr int WROW = N + 1;
+    // x / n_fields for any 32-bit x without a division: inv_fields = floor(2^64 / n_fields) + 1 (exact for n_fields >= 2)
+    auto record_of = [&](uint32_t x) -> uint32_t { return fm.n_fields == 1u ? x : (uint32_t)__umul64hi((uint64_t)x, inv_fields); };
+    static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
+    static_assert((STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t my_smem = smem_base + warp * (STAGES * TILE_BYTES);
+    const uint32_t my_bar = smem_u32(full_bar) + warp * (STAGES * 8);
+    // the weight rows live behind the tiles of all warps
+    float *wts = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)WARPS * STAGES * TILE_BYTES) +
+                 (size_t)warp * rec_cap * WROW;
+
+    const uint32_t n_tiles = (n_groups + 31u) >> 5;
+    const uint32_t first = blockIdx.x * WARPS + warp;
+    const uint32_t step = gridDim.x * WARPS;
+    uint64_t policy = 0;
+    if (lane == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init_a(my_bar + s * 8, 1);
+        fence_barrier_init();
+        policy = policy_evict_first();
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const uint32_t t = first + (uint32_t)s * step;
+            if (t < n_tiles) {
+                mbar_arrive_expect_tx_a(my_bar + s * 8, TILE_BYTES);
+                tma_load_2d_a(my_smem + s * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP), my_bar + s * 8, policy, 0);
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t piece[N / 4];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) piece[q] = Swizzle<ROW_BYTES>::apply(lane * ROW_BYTES + q * 16);
+
+    // The sequence logprobs of a tile's records are requested one tile AHEAD (a warp works through its tiles one after the other:
+    // a global-memory round trip per tile in front of the weights would be exposed every time).  Up to PF records per tile are
+    // prefetched (32 groups span 31 / n_fields + 2 records); wider tiles load them on the spot.
+    constexpr int PF = 4;
+    const bool prefetch = PREFETCH && rec_cap <= PF;
+    float cur_lo[PF], cur_hi[PF], nxt_lo[PF], nxt_hi[PF];
+    auto fetch = [&](uint32_t tt, float (&lo)[PF], float (&hi)[PF]) {
+        const uint32_t a = tt * 32, b = min(a + 31u, n_groups - 1u);
+        const uint32_t ra = record_of(a), rb = record_of(b);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            lo[k] = hi[k] = -3.0e38f;
+            if (ra + k <= rb) {
+                const float *s = seq_lp + (size_t)(ra + k) * N;
+                lo[k] = __ldg(s + lane);
+                if (N > 32) hi[k] = __ldg(s + lane + 32);
+            }
+        }
+    };
+    if (prefetch && first < n_tiles) fetch(first, cur_lo, cur_hi);
+
+    uint32_t it = 0;
+    for (uint32_t t = first; t < n_tiles; t += step, ++it) {
+        const uint32_t stage = it & (STAGES - 1);
+        const uint32_t parity = (it / STAGES) & 1;
+        const uint32_t bar = my_bar + stage * 8;
+        const uint32_t tile = my_smem + stage * TILE_BYTES;
+        if (prefetch && t + step < n_tiles) fetch(t + step, nxt_lo, nxt_hi);
+        // the weights of this tile's records, while the tile is still on its way
+        const uint32_t g0 = t * 32, g_last = min(g0 + 31u, n_groups - 1u);
+        const uint32_t r0 = record_of(g0), r_last = record_of(g_last);
+        for (uint32_t r = r0; r <= r_last; ++r) {
+            const float *s = seq_lp + (size_t)r * N;
+            float s_lo, s_hi = -3.0e38f;
+            if (prefetch) {
+                const uint32_t k = r - r0;  // < PF
+                s_lo = k == 0 ? cur_lo[0] : k == 1 ? cur_lo[1] : k == 2 ? cur_lo[2] : cur_lo[3];
+                if (N > 32) s_hi = k == 0 ? cur_hi[0] : k == 1 ? cur_hi[1] : k == 2 ? cur_hi[2] : cur_hi[3];
+            } else {
+                s_lo = __ldg(s + lane);
+                if (N > 32) s_hi = __ldg(s + lane + 32);
+            }
+            float smax = fmaxf(s_lo, s_hi);
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xFFFFFFFFu, smax, st));
+            float *w = wts + (r - r0) * WROW;
+            w[lane] = kexp(__fadd_rn(s_lo, -smax));
+            if (N > 32) w[lane + 32] = kexp(__fadd_rn(s_hi, -smax));
+            // the record's heaviest candidate (first of the largest sums; N = none, e.g. all NaN) rides in the row's pad slot
+            const uint32_t b_lo = __ballot_sync(0xFFFFFFFFu, s_lo == smax), b_hi = __ballot_sync(0xFFFFFFFFu, N > 32 && s_hi == smax);
+            const int imax = b_lo ? __ffs((int)b_lo) - 1 : (b_hi ? 31 + __ffs((int)b_hi) : N);
+            if (lane == 0) w[N] = __int_as_float(imax);
+        }
+        __syncwarp();
+        mbar_wait_a(bar, parity);
+        int32_t raw[N];
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const int4 v4 = lds_v4(tile + piece[q]);
+            raw[4 * q + 0] = v4.x;
+            raw[4 * q + 1] = v4.y;
+            raw[4 * q + 2] = v4.z;
+            raw[4 * q + 3] = v4.w;
+        }
+        const uint32_t g = g0 + lane;
+        const uint32_t fpos = (g0 - r0 * fm.n_fields) + lane;  // offset inside the tile's first record: < n_fields + 32
+        const uint32_t rec_local = g < n_groups ? fm.div_small(fpos) : 0u;
+        const float *wrow = wts + rec_local * WROW;
+        // this group's cell of its record's heaviest candidate: read from the tile while the stage is still ours
+        const int imax = __float_as_int(wrow[N]);
+        int32_t graw = KC_CODE_NONE - 1;
+        if (imax < N) {
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(graw) : "r"(tile + Swizzle<ROW_BYTES>::apply(lane * ROW_BYTES + (uint32_t)imax * 4u)));
+        }
+        // hand the stage back to the TMA unit only after every lane's row is in registers (see vote_tma_kernel)
+        const int32_t lo = min(row_min<N>(raw), graw);
+        const uint32_t order = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, 0) ^ (uint32_t)lo;
+        const uint32_t tn = t + STAGES * step;
+        if (lane == 0 && tn < n_tiles) {
+            mbar_arrive_expect_tx_a(bar, TILE_BYTES);
+            tma_load_2d_a(tile, &tmap, 0, (int32_t)(tn * 32 * BOX_ROWS_PER_GROUP + order), bar, policy, 0);
+        }
+        WvFirst<N> f;
+        bool undecided = false;
+        int32_t o_code = KC_CODE_NONE;
+        uint32_t o_meta = 0;
+        float o_weight = 0.0f;
+        if (g < n_groups) {
+            const uint32_t field = fpos - rec_local * fm.n_fields;
+            const int32_t nc = has_nc ? __ldg(fm.none_code + field) : KC_CODE_NONE;
+            wv_first_pass<N>(raw, lo, nc, wrow, graw, f);
+            undecided = !f.decided;
+            if (f.decided) {
+                o_code = f.guess;
+                o_meta = pack_meta(ffs_mask(f.eq_g) - 1, popc_m(f.eq_g), f.voters, f.present, KC_FLAG_HAS_VALUE);
+                o_weight = __fdiv_rn(f.cw_g, f.total);
+            }
+        }
+        for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, undecided); todo; todo &= todo - 1)
+            wv_warp_walk<N>(lane, (uint32_t)__ffs((int)todo) - 1u, f, wts, rec_local, WROW, o_code, o_meta, o_weight);
+        if (g < n_groups) {
+            win[g] = o_code;
+            meta[g] = o_meta;
+            weight[g] = o_weight;
+        }
+        __syncwarp();  // the next tile's weights overwrite these rows
+        if (prefetch) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                cur_lo[k] = nxt_lo[k];
+                cur_hi[k] = nxt_hi[k];
+            }
+        }
     }
 }
 

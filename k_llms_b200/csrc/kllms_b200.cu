@@ -770,7 +770,33 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
     const kc::FieldMap fm = make_field_map(d_none_code, n_fields);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool per_record = [] { const char *e = getenv("KC_K3B_REC"); return !e || e[0] != '0'; }();
-    if (per_record && n >= 8) {  // weights once per record, codes in a shared-memory plane
+    static const bool use_tma = [] { const char *e = getenv("KC_K3B_TMA"); return !e || e[0] != '0'; }();
+    if (per_record && use_tma && (n == 32 || n == 64) && n_fields < 60000) {  // rows through K1's warp-private TMA pipelines
+        auto launch_tma = [&](auto kernel, int N, int WARPS, int STAGES) -> int {
+            const int rec_cap = std::min(32, 31 / n_fields + 2);  // records a tile of 32 groups can span
+            const size_t smem = (size_t)WARPS * STAGES * 32 * N * 4 + 1024 + (size_t)WARPS * rec_cap * (N + 1) * 4;
+            const int64_t slab = std::max<int64_t>(n_fields, kMaxGroupsPerLaunch / n_fields * n_fields);  // slabs start on record boundaries
+            for (int64_t g0 = 0; g0 < G; g0 += slab) {
+                const int64_t gs = std::min(slab, G - g0);
+                CUtensorMap map;
+                int rc2 = make_row_tensor_map(map, d_codes + g0 * N, gs, N * 4, 32);
+                if (rc2) return rc2;
+                int grid2 = 0;
+                rc2 = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid2);
+                if (rc2) return rc2;
+                const uint64_t inv_fields = n_fields > 1 ? ~uint64_t(0) / (uint64_t)n_fields + 1 : 0;
+                kernel<<<grid2, WARPS * 32, smem, st>>>(map, d_seq_logprob + (g0 / n_fields) * N, (uint32_t)gs, fm, d_none_code != nullptr, rec_cap,
+                                                        inv_fields, d_win_code + g0, d_meta + g0, d_weight + g0);
+                KC_CUDA(cudaGetLastError());
+            }
+            return KC_OK;
+        };
+        // measured on B200 (profiles/r2_k3b_variants.txt): n = 32 with 3 CTAs / SM (80 registers) and the logprobs requested a tile ahead;
+        // n = 64 (2 x the registers per row) without the prefetch
+        if (n == 32) return launch_tma(kc::weighted_vote_tma_kernel<32, 8, 2, 3, true>, 32, 8, 2);
+        return launch_tma(kc::weighted_vote_tma_kernel<64, 4, 2, 3, false>, 64, 4, 2);
+    }
+    if (per_record && n >= 8) {  // weights once per record, one row per thread straight from global memory
         const int max_recs = threads / n_fields + 2;
         auto launch = [&](auto kernel, int NP) -> int {
             const size_t smem = (size_t)max_recs * NP * 4;  // the candidate weights of the tile's records
