@@ -700,4 +700,156 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) weighted_vote_tma_kernel
     }
 }
 
+// ---- K3b with the weights OUT of the tile loop.  A pre-pass writes, once per record, the row [w_0 .. w_{N-1}, index of the heaviest
+// candidate, 3 pad words] (N + 4 floats: rows stay 16-byte multiples and consecutive rows start 4 banks apart); the vote kernel
+// fetches the rows of a tile's records with ONE cp.async.bulk next to the tile's tensor copy, completing on the same mbarrier.
+
+template <int N>
+__global__ void __launch_bounds__(256) weight_rows_kernel(const float *__restrict__ seq_lp, int64_t n_records, float *__restrict__ rows) {
+    constexpr int WROW = N + 4;
+    const uint32_t lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_records; r += n_warps) {
+        const float *s = seq_lp + r * N;
+        const float s_lo = __ldg(s + lane), s_hi = N > 32 ? __ldg(s + lane + 32) : -3.0e38f;
+        float smax = fmaxf(s_lo, s_hi);
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xFFFFFFFFu, smax, st));
+        float *w = rows + r * WROW;
+        w[lane] = kexp(__fadd_rn(s_lo, -smax));
+        if (N > 32) w[lane + 32] = kexp(__fadd_rn(s_hi, -smax));
+        const uint32_t b_lo = __ballot_sync(0xFFFFFFFFu, s_lo == smax), b_hi = __ballot_sync(0xFFFFFFFFu, N > 32 && s_hi == smax);
+        const int imax = b_lo ? __ffs((int)b_lo) - 1 : (b_hi ? 31 + __ffs((int)b_hi) : N);
+        if (lane < 4) w[N + lane] = lane == 0 ? __int_as_float(imax) : 0.0f;
+    }
+}
+
+__device__ __forceinline__ void bulk_load_1d_a(uint32_t smem_dst, const void *src, uint32_t bytes, uint32_t bar, uint32_t dep) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 kc_dep1;\n\t"
+        "mov.b32 kc_dep1, %4;\n\t"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}\n" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "r"(dep)
+        : "memory");
+}
+
+template <int N, int WARPS, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) weighted_vote_rows_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ wrows,
+                                                                        uint32_t n_groups, FieldMap fm, bool has_nc, int rec_cap, uint64_t inv_fields,
+                                                                        int32_t *__restrict__ win, uint32_t *__restrict__ meta,
+                                                                        float *__restrict__ weight) {
+    constexpr int ROW_BYTES = N * 4;
+    constexpr int BOX_ROWS_PER_GROUP = ROW_BYTES > 128 ? ROW_BYTES / 128 : 1;
+    constexpr uint32_t TILE_BYTES = 32 * ROW_BYTES;
+    constexpr int WROW = N + 4;
+    constexpr int WSLOTS = STAGES + 1;  // the slot of the tile being voted is not the one the re-arm refills
+    auto record_of = [&](uint32_t x) -> uint32_t { return fm.n_fields == 1u ? x : (uint32_t)__umul64hi((uint64_t)x, inv_fields); };
+    static_assert(TILE_BYTES % 1024 == 0, "warp tile must keep the swizzle atom alignment");
+    static_assert((STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t my_smem = smem_base + warp * (STAGES * TILE_BYTES);
+    const uint32_t my_bar = smem_u32(full_bar) + warp * (STAGES * 8);
+    const uint32_t slot_bytes = (uint32_t)rec_cap * WROW * 4;
+    const uint32_t my_rows = smem_base + WARPS * STAGES * TILE_BYTES + warp * (WSLOTS * slot_bytes);     // shared-space address
+    const float *my_rows_p = reinterpret_cast<const float *>(smem_raw + (my_rows - smem_u32(smem_raw)));  // the same, generic
+
+    const uint32_t n_tiles = (n_groups + 31u) >> 5;
+    const uint32_t first = blockIdx.x * WARPS + warp;
+    const uint32_t step = gridDim.x * WARPS;
+    uint64_t policy = 0;
+    // one tile's copies: the 32 rows of cells and the weight rows of the records they belong to, on one barrier
+    auto request = [&](uint32_t t, uint32_t stage, uint32_t slot, uint32_t dep) {
+        const uint32_t a = t * 32, b = min(a + 31u, n_groups - 1u);
+        const uint32_t ra = record_of(a), rb = record_of(b);
+        const uint32_t wbytes = (rb - ra + 1u) * WROW * 4;
+        const uint32_t bar = my_bar + stage * 8;
+        mbar_arrive_expect_tx_a(bar, TILE_BYTES + wbytes);
+        tma_load_2d_a(my_smem + stage * TILE_BYTES, &tmap, 0, (int32_t)(t * 32 * BOX_ROWS_PER_GROUP + dep), bar, policy, 0);
+        bulk_load_1d_a(my_rows + slot * slot_bytes, wrows + (size_t)ra * WROW, wbytes, bar, dep);
+    };
+    if (lane == 0) {
+        tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init_a(my_bar + s * 8, 1);
+        fence_barrier_init();
+        policy = policy_evict_first();
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const uint32_t t = first + (uint32_t)s * step;
+            if (t < n_tiles) request(t, (uint32_t)s, (uint32_t)s, 0u);
+        }
+    }
+    __syncwarp();
+    uint32_t piece[N / 4];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) piece[q] = Swizzle<ROW_BYTES>::apply(lane * ROW_BYTES + q * 16);
+
+    uint32_t it = 0, slot = 0;  // slot = it % WSLOTS
+    for (uint32_t t = first; t < n_tiles; t += step, ++it) {
+        const uint32_t stage = it & (STAGES - 1);
+        const uint32_t parity = (it / STAGES) & 1;
+        const uint32_t bar = my_bar + stage * 8;
+        const uint32_t tile = my_smem + stage * TILE_BYTES;
+        const uint32_t g0 = t * 32, g = g0 + lane;
+        const uint32_t r0 = record_of(g0);
+        const uint32_t fpos = (g0 - r0 * fm.n_fields) + lane;  // offset inside the tile's first record: < n_fields + 32
+        const uint32_t rec_local = g < n_groups ? fm.div_small(fpos) : 0u;
+        const float *wts = my_rows_p + slot * (slot_bytes / 4);
+        const float *wrow = wts + rec_local * WROW;
+        mbar_wait_a(bar, parity);
+        int32_t raw[N];
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const int4 v4 = lds_v4(tile + piece[q]);
+            raw[4 * q + 0] = v4.x;
+            raw[4 * q + 1] = v4.y;
+            raw[4 * q + 2] = v4.z;
+            raw[4 * q + 3] = v4.w;
+        }
+        // this group's cell of its record's heaviest candidate: read from the tile while the stage is still ours
+        const int imax = __float_as_int(wrow[N]);
+        int32_t graw = KC_CODE_NONE - 1;
+        if (imax < N) {
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(graw) : "r"(tile + Swizzle<ROW_BYTES>::apply(lane * ROW_BYTES + (uint32_t)imax * 4u)));
+        }
+        // hand the stage back only after every lane's row is in registers (see vote_tma_kernel); the shuffle also means that
+        // every lane has left the previous tile, whose weight slot the request below refills
+        const int32_t lo = min(row_min<N>(raw), graw);
+        const uint32_t order = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, 0) ^ (uint32_t)lo;
+        const uint32_t tn = t + STAGES * step;
+        if (lane == 0 && tn < n_tiles) request(tn, stage, (slot + STAGES) % WSLOTS, order);
+        WvFirst<N> f;
+        bool undecided = false;
+        int32_t o_code = KC_CODE_NONE;
+        uint32_t o_meta = 0;
+        float o_weight = 0.0f;
+        if (g < n_groups) {
+            const uint32_t field = fpos - rec_local * fm.n_fields;
+            const int32_t nc = has_nc ? __ldg(fm.none_code + field) : KC_CODE_NONE;
+            wv_first_pass<N>(raw, lo, nc, wrow, graw, f);
+            undecided = !f.decided;
+            if (f.decided) {
+                o_code = f.guess;
+                o_meta = pack_meta(ffs_mask(f.eq_g) - 1, popc_m(f.eq_g), f.voters, f.present, KC_FLAG_HAS_VALUE);
+                o_weight = __fdiv_rn(f.cw_g, f.total);
+            }
+        }
+        for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, undecided); todo; todo &= todo - 1)
+            wv_warp_walk<N>(lane, (uint32_t)__ffs((int)todo) - 1u, f, wts, rec_local, WROW, o_code, o_meta, o_weight);
+        if (g < n_groups) {
+            win[g] = o_code;
+            meta[g] = o_meta;
+            weight[g] = o_weight;
+        }
+        slot = slot + 1 == WSLOTS ? 0u : slot + 1;
+    }
+}
+
 }  // namespace kc

@@ -791,6 +791,35 @@ int kc_weighted_vote_i32(const int32_t *d_codes, const float *d_seq_logprob, int
             }
             return KC_OK;
         };
+        static const bool rows = [] { const char *e = getenv("KC_K3B_ROWS"); return !e || e[0] != '0'; }();
+        const int rec_cap0 = std::min(32, 31 / n_fields + 2);
+        if (rows && n == 32 && rec_cap0 <= 8) {  // weights by a pre-pass, fetched per tile by a bulk copy (n_fields >= 6; n = 64 measured slower)
+            auto launch_rows = [&](auto pre_kernel, auto kernel, int N, int WARPS, int STAGES) -> int {
+                const int WROW = N + 4;
+                float *d_rows = nullptr;
+                KC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_rows), (size_t)n_records * WROW * 4, st));
+                const int pre_grid = (int)std::min<int64_t>((n_records + 7) / 8, (int64_t)info.sm_count * 8);
+                pre_kernel<<<pre_grid, 256, 0, st>>>(d_seq_logprob, n_records, d_rows);
+                int rc2 = cudaGetLastError() == cudaSuccess ? KC_OK : fail(KC_ECUDA, "kc_weighted_vote_i32: weight_rows_kernel launch failed");
+                const size_t smem = (size_t)WARPS * STAGES * 32 * N * 4 + 1024 + (size_t)WARPS * (STAGES + 1) * rec_cap0 * WROW * 4;
+                const int64_t slab = std::max<int64_t>(n_fields, kMaxGroupsPerLaunch / n_fields * n_fields);
+                for (int64_t g0 = 0; g0 < G && !rc2; g0 += slab) {
+                    const int64_t gs = std::min(slab, G - g0);
+                    CUtensorMap map;
+                    rc2 = make_row_tensor_map(map, d_codes + g0 * N, gs, N * 4, 32);
+                    int grid2 = 0;
+                    if (!rc2) rc2 = persistent_grid(kernel, WARPS * 32, smem, ((gs + 31) / 32 + WARPS - 1) / WARPS, grid2);
+                    if (rc2) break;
+                    const uint64_t inv_fields = n_fields > 1 ? ~uint64_t(0) / (uint64_t)n_fields + 1 : 0;
+                    kernel<<<grid2, WARPS * 32, smem, st>>>(map, d_rows + (g0 / n_fields) * WROW, (uint32_t)gs, fm, d_none_code != nullptr, rec_cap0,
+                                                            inv_fields, d_win_code + g0, d_meta + g0, d_weight + g0);
+                    if (cudaGetLastError() != cudaSuccess) rc2 = fail(KC_ECUDA, "kc_weighted_vote_i32: launch failed");
+                }
+                cudaFreeAsync(d_rows, st);
+                return rc2;
+            };
+            return launch_rows(kc::weight_rows_kernel<32>, kc::weighted_vote_rows_kernel<32, 8, 2, 3>, 32, 8, 2);
+        }
         // measured on B200 (profiles/r2_k3b_variants.txt): n = 32 with 3 CTAs / SM (80 registers) and the logprobs requested a tile ahead;
         // n = 64 (2 x the registers per row) without the prefetch
         if (n == 32) return launch_tma(kc::weighted_vote_tma_kernel<32, 8, 2, 3, true>, 32, 8, 2);
