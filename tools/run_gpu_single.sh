@@ -11,3 +11,7 @@ for l in open('gpurun_out/r2_sweep_bench_n1.jsonl'):
 timeout 300 python tools/config4_timing.py --min-tokens 8 --max-tokens 64 > gpurun_out/r2_config4.json; cat gpurun_out/r2_config4.json
 timeout 600 python tools/config3_timing.py --records 20000 > gpurun_out/r2_config3.json 2> gpurun_out/r2_config3.err; cut -c1-700 gpurun_out/r2_config3.json; tail -3 gpurun_out/r2_config3.err
 timeout 600 python tools/latency.py > gpurun_out/r2_latency.json 2> gpurun_out/r2_latency.err; cat gpurun_out/r2_latency.json
+timeout 300 python tools/jsonpacked_throughput.py --workload invoice --records 131072 --n 8 --reps 3 > gpurun_out/r2_jsonpacked_invoice_n8.json; cut -c1-400 gpurun_out/r2_jsonpacked_invoice_n8.json
+timeout 300 python tools/jsonpacked_throughput.py --workload invoice_nested --records 131072 --n 8 --reps 3 > gpurun_out/r2_jsonpacked_invoice_nested_n8.json; cut -c1-400 gpurun_out/r2_jsonpacked_invoice_nested_n8.json
+timeout 300 python tools/config4_timing.py --iters 30 > gpurun_out/r2_config4_k3b_tma_32_96.json; cat gpurun_out/r2_config4_k3b_tma_32_96.json
+KC_K3B_ROWS=0 timeout 300 python tools/config4_timing.py --iters 30; KC_K3B_TMA=0 timeout 300 python tools/config4_timing.py --iters 30   # K3b: in-loop weights; one row per thread from global memory
