@@ -206,6 +206,7 @@ bool py_isclose(double a, double b, double rel_tol) {  // math.isclose(a, b, rel
 
 double string_similarity(AlignCtx &cx, const std::string &s1, const std::string &s2) {  // cu:797-824, method "embeddings"
     if (s1.size() > 50 && s2.size() > 50) cx.decline = true;  // the caller gives the record to the Python path
+    if (s1 == s2) return 1.0;  // equal texts normalise alike: distance 0 (or two empty forms) — the common pair among candidates
     thread_local std::string a, b;
     sanitize(s1, a);  // == normalize_string (cu:660-673) on ASCII
     sanitize(s2, b);
