@@ -36,7 +36,7 @@ def main():
     out = [plan.materialise(root, res) for root in roots]
     t3 = time.perf_counter()
     # the same records as candidate TEXTS through the batched native path (consolidate_contents_batch -> kc_consolidate_json_packed:
-    # the device JSON path declines nested / list records, the native host path H1 — C++ parse, alignment pre-pass H2, encode,
+    # the device JSON path declines records with lists or with candidates of different shapes, the native host path H1 — C++ parse, alignment pre-pass H2, encode,
     # K1/K2/K4, decode, multi-threaded — consolidates them inside the same call)
     from k_llms_b200.utils import consolidation as C
     from k_llms_b200 import _native as K
