@@ -38,6 +38,7 @@ bool aparse(Scanner &sc, ATree &tr, int32_t &out, int depth) {
     if (c == '{') {
         ++sc.p;
         out = tr.add(A_DICT);
+        tr.v[(size_t)out].kv.reserve(8);  // one allocation for the usual object instead of four doublings
         sc.ws();
         if (sc.p < sc.end && *sc.p == '}') {
             ++sc.p;
@@ -81,6 +82,7 @@ bool aparse(Scanner &sc, ATree &tr, int32_t &out, int depth) {
     if (c == '[') {
         ++sc.p;
         out = tr.add(A_LIST);
+        tr.v[(size_t)out].items.reserve(8);
         sc.ws();
         if (sc.p < sc.end && *sc.p == ']') {
             ++sc.p;
