@@ -444,7 +444,7 @@ int kc_consolidate_json_packed(const char *h_text, const int64_t *h_off, int64_t
     }
     // chunks of ~chunk_mb of text; records are never split
     size_t chunk_bytes = (size_t)64 << 20;
-    if (const char *e = getenv("KC_JSON_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("KC_JSON_CHUNK_MB")) chunk_bytes = (size_t)std::min(1024, std::max(1, atoi(e))) << 20;  // K4's CSR offsets are int32
     std::vector<int64_t> cuts{0};
     {
         int64_t r = 0;
